@@ -1,0 +1,30 @@
+"""AST-extraction of the reference's own pure-torch functions (only possible where /root/reference exists).
+
+Nothing is copied into the repo: the function source is read from the reference checkout at test time, compiled
+in a scratch namespace and called, so the comparison is against the reference's code itself."""
+import ast
+import os
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+
+
+def have_reference():
+    return os.path.isdir(os.path.join(REF, 'src'))
+
+
+def extract(relpath, names, extra_ns=None):
+    src = open(os.path.join(REF, relpath)).read()
+    tree = ast.parse(src)
+    ns = {'torch': torch, 'np': np, 'F': torch.nn.functional}
+    ns.update(extra_ns or {})
+    for node in tree.body:
+        if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), relpath, 'exec')
+            exec(code, ns)
+        elif isinstance(node, ast.Assign) and any(isinstance(t, ast.Name) and t.id in names for t in node.targets):
+            code = compile(ast.Module(body=[node], type_ignores=[]), relpath, 'exec')
+            exec(code, ns)
+    return ns
