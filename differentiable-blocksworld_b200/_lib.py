@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI in include/dbw_render.h (the drop-in boundary).  There is NO CPU fallback: if the
+shared library is missing or a call fails, this raises."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdbw_render.so')
+
+ABI_VERSION = 1
+
+
+class DbwRenderSettings(ctypes.Structure):
+    _fields_ = [
+        ('n_views', ctypes.c_int32), ('height', ctypes.c_int32), ('width', ctypes.c_int32),
+        ('faces_per_pixel', ctypes.c_int32), ('n_verts', ctypes.c_int32), ('n_faces', ctypes.c_int32),
+        ('n_maps', ctypes.c_int32), ('alpha_view_stride', ctypes.c_int32),
+        ('fx', ctypes.c_float), ('fy', ctypes.c_float), ('px', ctypes.c_float), ('py', ctypes.c_float),
+        ('sigma', ctypes.c_float), ('blur_radius', ctypes.c_float), ('z_clip', ctypes.c_float),
+        ('proj_eps', ctypes.c_float), ('background', ctypes.c_float * 3),
+        ('clip_inside', ctypes.c_int32), ('perspective_correct', ctypes.c_int32),
+        ('clip_barycentric', ctypes.c_int32), ('detach_bary', ctypes.c_int32), ('verts_are_ndc', ctypes.c_int32),
+    ]
+
+
+class DbwMapDesc(ctypes.Structure):
+    _fields_ = [('offset', ctypes.c_int32), ('height', ctypes.c_int32), ('width', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
+
+
+EXPORTS = ['dbw_abi_version', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_backward',
+           'dbw_composite_mse', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count']
+
+_lib = None
+
+
+class DbwError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DbwError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                           f'or `make -C differentiable-blocksworld_b200/csrc` (there is no CPU fallback)')
+        L = ctypes.CDLL(LIB_PATH)
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.dbw_abi_version.restype = ctypes.c_int
+        L.dbw_last_error.restype = ctypes.c_char_p
+        L.dbw_launch_count.restype = ctypes.c_uint64
+        L.dbw_workspace_bytes.argtypes = [ctypes.POINTER(DbwRenderSettings), ctypes.POINTER(sz), ctypes.POINTER(sz)]
+        L.dbw_render_forward.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 12 + [sz, vp]
+        L.dbw_render_backward.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 11 + [sz] + [vp] * 5 + [sz, vp]
+        L.dbw_composite_mse.argtypes = [ctypes.c_int32] * 3 + [vp] * 3 + [ctypes.c_float] + [vp] * 5
+        L.dbw_render_forward_host.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 5 + [sz] + [vp] * 6
+        L.dbw_host_arena_release.restype = None
+        if L.dbw_abi_version() != ABI_VERSION:
+            raise DbwError(f'ABI mismatch: library {L.dbw_abi_version()} != binding {ABI_VERSION}')
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DbwError(f'{what} failed: {lib().dbw_last_error().decode()}')
+
+
+def launch_count():
+    return int(lib().dbw_launch_count())

@@ -1,0 +1,201 @@
+// dbw_math.cuh -- per-(pixel, face) math shared by the forward and backward rasterization kernels.
+//
+// The operation order follows PyTorch3D 0.7.1's geometry_utils, which is what the
+// reference's MeshRasterizer executes (src/model/renderer.py:50-54).  Arithmetic that feeds a DISCRETE decision
+// (edge-function signs -> inside test, pixel NDC coordinates) is written with non-contracting intrinsics so that it
+// is bit-identical to an IEEE-754 evaluation without FMA; everything else may be contracted by the compiler.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DBW_KEPS 1e-8f
+
+struct f2 { float x, y; };
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ float edge_nc(f2 p, f2 a, f2 b) {
+  // (p.x-a.x)*(b.y-a.y) - (p.y-a.y)*(b.x-a.x), no FMA contraction
+  return __fsub_rn(__fmul_rn(p.x - a.x, b.y - a.y), __fmul_rn(p.y - a.y, b.x - a.x));
+}
+
+// rasterization_utils: PixToNonSquareNdc, bit-identical to the non-contracted evaluation
+__device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
+  float range = 2.0f;
+  if (S1 > S2) range = __fdiv_rn(__fmul_rn((float)S1, range), (float)S2);
+  const float offset = __fdiv_rn(range, 2.0f);
+  return __fadd_rn(-offset, __fdiv_rn(__fadd_rn(__fmul_rn(range, (float)i), offset), (float)S1));
+}
+
+struct TriGeom {
+  f2 v0, v1, v2;
+  float z0, z1, z2;
+  int face;      // original face id
+  int neighbor;  // slot of the other half of a z-clipped quad, or -1
+  int flags;     // bit0: clipped (barycentric conversion matrix present)
+};
+
+__device__ __forceinline__ TriGeom unpack_tri(float4 r0, float4 r1, float4 r2) {
+  TriGeom t;
+  t.v0 = {r0.x, r0.y}; t.v1 = {r0.z, r0.w}; t.v2 = {r1.x, r1.y};
+  t.z0 = r1.z; t.z1 = r1.w; t.z2 = r2.x;
+  t.face = __float_as_int(r2.y); t.neighbor = __float_as_int(r2.z); t.flags = __float_as_int(r2.w);
+  return t;
+}
+
+struct Bary {
+  f3 b0;    // screen-space barycentrics
+  f3 bp;    // perspective-corrected
+  f3 bc;    // clipped + renormalised (what is interpolated with)
+  bool inside;
+  float pz;
+};
+
+__device__ __forceinline__ f3 persp_forward(f3 b, float z0, float z1, float z2) {
+  const float t0 = b.x * z1 * z2, t1 = z0 * b.y * z2, t2 = z0 * z1 * b.z;
+  const float denom = fmaxf(t0 + t1 + t2, DBW_KEPS);
+  return {t0 / denom, t1 / denom, t2 / denom};
+}
+
+__device__ __forceinline__ f3 clip_forward(f3 b) {
+  f3 w = {fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f)};
+  const float s = fmaxf(w.x + w.y + w.z, 1e-5f);
+  return {w.x / s, w.y / s, w.z / s};
+}
+
+__device__ __forceinline__ Bary eval_bary(f2 p, const TriGeom& t, bool persp, bool clipb) {
+  Bary r;
+  const float area = __fadd_rn(edge_nc(t.v2, t.v0, t.v1), DBW_KEPS);
+  r.b0 = {edge_nc(p, t.v1, t.v2) / area, edge_nc(p, t.v2, t.v0) / area, edge_nc(p, t.v0, t.v1) / area};
+  r.bp = persp ? persp_forward(r.b0, t.z0, t.z1, t.z2) : r.b0;
+  r.inside = r.bp.x > 0.f && r.bp.y > 0.f && r.bp.z > 0.f;
+  r.bc = clipb ? clip_forward(r.bp) : r.bp;
+  r.pz = r.bc.x * t.z0 + r.bc.y * t.z1 + r.bc.z * t.z2;
+  return r;
+}
+
+// squared distance from p to the segment a-b; also returns the clamped parameter t and whether the degenerate
+// (|ba|^2 <= eps) branch was taken
+__device__ __forceinline__ float seg_dist2(f2 p, f2 a, f2 b) {
+  const float bax = b.x - a.x, bay = b.y - a.y;
+  const float l2 = bax * bax + bay * bay;
+  if (l2 <= DBW_KEPS) {
+    const float dx = p.x - b.x, dy = p.y - b.y;
+    return dx * dx + dy * dy;
+  }
+  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) / l2;
+  tt = fminf(fmaxf(tt, 0.f), 1.f);
+  const float dx = a.x + tt * bax - p.x, dy = a.y + tt * bay - p.y;
+  return dx * dx + dy * dy;
+}
+
+__device__ __forceinline__ float tri_dist2(f2 p, const TriGeom& t) {
+  const float e01 = seg_dist2(p, t.v0, t.v1), e02 = seg_dist2(p, t.v0, t.v2), e12 = seg_dist2(p, t.v1, t.v2);
+  return fminf(fminf(e01, e02), e12);
+}
+
+// ------------------------------------------------------------------ backward pieces
+
+__device__ __forceinline__ void edge_backward(f2 p, f2 a, f2 b, float g, f2& ga, f2& gb) {
+  ga.x += g * (p.y - b.y); ga.y += g * (b.x - p.x);
+  gb.x += g * (a.y - p.y); gb.y += g * (p.x - a.x);
+}
+
+__device__ __forceinline__ void bary_backward(f2 p, const TriGeom& t, f3 g, f2& g0, f2& g1, f2& g2) {
+  const float area = __fadd_rn(edge_nc(t.v2, t.v0, t.v1), DBW_KEPS);
+  const float e0 = edge_nc(p, t.v1, t.v2), e1 = edge_nc(p, t.v2, t.v0), e2 = edge_nc(p, t.v0, t.v1);
+  const float inv = 1.f / area;
+  const float garea = -(g.x * e0 + g.y * e1 + g.z * e2) * inv * inv;
+  edge_backward(p, t.v1, t.v2, g.x * inv, g1, g2);
+  edge_backward(p, t.v2, t.v0, g.y * inv, g2, g0);
+  edge_backward(p, t.v0, t.v1, g.z * inv, g0, g1);
+  // area = edge(v2; v0, v1): here the "point" v2 also receives gradient
+  g2.x += garea * (t.v1.y - t.v0.y); g2.y += garea * (t.v0.x - t.v1.x);
+  edge_backward(t.v2, t.v0, t.v1, garea, g0, g1);
+}
+
+__device__ __forceinline__ f3 persp_backward(f3 b, float z0, float z1, float z2, f3 g, float& gz0, float& gz1, float& gz2) {
+  const float t0 = b.x * z1 * z2, t1 = z0 * b.y * z2, t2 = z0 * z1 * b.z;
+  const float sum = t0 + t1 + t2;
+  const float denom = fmaxf(sum, DBW_KEPS);
+  const float inv = 1.f / denom;
+  const float gden = (sum > DBW_KEPS) ? -(t0 * g.x + t1 * g.y + t2 * g.z) * inv * inv : 0.f;
+  const float gt0 = gden + g.x * inv, gt1 = gden + g.y * inv, gt2 = gden + g.z * inv;
+  gz0 += gt1 * b.y * z2 + gt2 * b.z * z1;
+  gz1 += gt0 * b.x * z2 + gt2 * b.z * z0;
+  gz2 += gt0 * b.x * z1 + gt1 * b.y * z0;
+  return {gt0 * z1 * z2, gt1 * z0 * z2, gt2 * z0 * z1};
+}
+
+__device__ __forceinline__ f3 clip_backward(f3 b, f3 g) {
+  const f3 w = {fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f)};
+  float s = w.x + w.y + w.z;
+  float on = 1.f;
+  if (s < 1e-5f) { on = 0.f; s = 1e-5f; }
+  const float inv = 1.f / s;
+  const float gsum = -(g.x * w.x + g.y * w.y + g.z * w.z) * inv * inv * on;
+  return {b.x < 0.f ? 0.f : g.x * inv + gsum, b.y < 0.f ? 0.f : g.y * inv + gsum, b.z < 0.f ? 0.f : g.z * inv + gsum};
+}
+
+// gradient of seg_dist2 w.r.t. a and b (the closest point's parameter is treated as a constant)
+__device__ __forceinline__ void seg_backward(f2 p, f2 a, f2 b, float g, f2& ga, f2& gb) {
+  const float bax = b.x - a.x, bay = b.y - a.y;
+  const float l2 = bax * bax + bay * bay;
+  if (l2 <= DBW_KEPS) {
+    gb.x += g * 2.f * (b.x - p.x); gb.y += g * 2.f * (b.y - p.y);
+    return;
+  }
+  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) / l2;
+  tt = fminf(fmaxf(tt, 0.f), 1.f);
+  const float dx = a.x + tt * bax - p.x, dy = a.y + tt * bay - p.y;
+  ga.x += g * (1.f - tt) * 2.f * dx; ga.y += g * (1.f - tt) * 2.f * dy;
+  gb.x += g * tt * 2.f * dx;         gb.y += g * tt * 2.f * dy;
+}
+
+__device__ __forceinline__ void tri_dist_backward(f2 p, const TriGeom& t, float g, f2& g0, f2& g1, f2& g2) {
+  const float e01 = seg_dist2(p, t.v0, t.v1), e02 = seg_dist2(p, t.v0, t.v2), e12 = seg_dist2(p, t.v1, t.v2);
+  if (e01 <= e02 && e01 <= e12) seg_backward(p, t.v0, t.v1, g, g0, g1);
+  else if (e02 <= e01 && e02 <= e12) seg_backward(p, t.v0, t.v2, g, g0, g2);
+  else seg_backward(p, t.v1, t.v2, g, g1, g2);
+}
+
+// ------------------------------------------------------------------ texture fetch
+// TexturesUV.sample_textures: grid = 2*uv - 1 on the map flipped along H, F.grid_sample(bilinear,
+// align_corners=True, padding_mode='border').  Row r of the flipped map is row H-1-r of the stored map.
+struct TexTap {
+  int i00, i01, i10, i11;   // float offsets (within the packed maps buffer) of the 4 texels, or -1 if out of bounds
+  float w00, w01, w10, w11; // nw, ne, sw, se weights
+  float ix, iy;             // un-normalised (clipped) coordinates in the flipped map
+  float mx, my;             // d(ix)/du, d(iy)/dv incl. the border-clip mask
+  int x0, y0;
+};
+
+__device__ __forceinline__ TexTap tex_tap(float u, float v, int off, int H, int W) {
+  TexTap t;
+  const float gx = u * 2.f - 1.f, gy = v * 2.f - 1.f;
+  float ix = ((gx + 1.f) / 2.f) * (float)(W - 1);
+  float iy = ((gy + 1.f) / 2.f) * (float)(H - 1);
+  // clip_coordinates_set_grad: the borders themselves count as out of bounds for the gradient
+  t.mx = (float)(W - 1); t.my = (float)(H - 1);
+  if (ix <= 0.f) { ix = 0.f; t.mx = 0.f; } else if (ix >= (float)(W - 1)) { ix = (float)(W - 1); t.mx = 0.f; }
+  if (iy <= 0.f) { iy = 0.f; t.my = 0.f; } else if (iy >= (float)(H - 1)) { iy = (float)(H - 1); t.my = 0.f; }
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const float ex = fx0 + 1.f, ey = fy0 + 1.f;       // south-east corner
+  t.w00 = (ex - ix) * (ey - iy);
+  t.w01 = (ix - fx0) * (ey - iy);
+  t.w10 = (ex - ix) * (iy - fy0);
+  t.w11 = (ix - fx0) * (iy - fy0);
+  const bool x1ok = x1 <= W - 1, y1ok = y1 <= H - 1;
+  const int r0 = (H - 1 - y0) * W, r1 = (H - 1 - y1) * W;
+  t.i00 = off + (r0 + x0) * 3;
+  t.i01 = x1ok ? off + (r0 + x1) * 3 : -1;
+  t.i10 = y1ok ? off + (r1 + x0) * 3 : -1;
+  t.i11 = (x1ok && y1ok) ? off + (r1 + x1) * 3 : -1;
+  t.ix = ix; t.iy = iy; t.x0 = x0; t.y0 = y0;
+  return t;
+}
+
+__device__ __forceinline__ f3 ld3(const float* __restrict__ m, int i) {
+  if (i < 0) return {0.f, 0.f, 0.f};
+  return {__ldg(m + i), __ldg(m + i + 1), __ldg(m + i + 2)};
+}

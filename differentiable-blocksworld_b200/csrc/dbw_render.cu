@@ -1,0 +1,853 @@
+// dbw_render.cu -- sm_100a kernels + C-ABI of the differentiable primitive renderer (see include/dbw_render.h).
+//
+// Replaces, for the reference's render hot path (src/model/renderer.py:84-98, 219-273):
+//   PerspectiveCameras/MeshRasterizer.transform, clip_faces, _C.rasterize_meshes{,_backward},
+//   interpolate_face_attributes, F.grid_sample on the (B*K)-replicated atlas, and the ~15 eager kernels of
+//   layered_rgb_blend -- with  project -> face setup (z-clip) -> ONE fused raster+shade+blend kernel per pass,
+//   and the mirror-image backward.  No fragments tensors (pix_to_face/zbuf/bary/dists, 28 B/px/K) are ever written:
+//   the forward keeps the per-pixel top-K in registers and stores only K int32 slot ids per pixel for the backward.
+//
+// Layout in HBM (all fp32 / int32):
+//   verts_ndc  (B,V,3)            projected vertices (x_ndc, y_ndc, z_view)
+//   bbox       (B,2F) float4      blur-expanded NDC bbox of each face slot (xmin,xmax,ymin,ymax); xmin=+inf: empty
+//   rec        (B,2F,3) float4    v0xy v1xy | v2xy z0 z1 | z2 face neighbor flags
+//   conv       (B,2F,9)           barycentric conversion (clipped -> original face), only for clipped slots
+//   slots [0,F) hold each face's (first) triangle, slots [F,2F) the second triangle of a z-clipped quad.
+//   out_rgba   (B,4,H,W), topk_ids (B,K,H,W) planar so that every warp store is a run of full 32 B sectors.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dbw_render.h"
+#include "dbw_math.cuh"
+
+// ------------------------------------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+static uint64_t g_launches = 0;
+
+static int fail(const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  else snprintf(g_err, sizeof(g_err), "%s", what);
+  return -1;
+}
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(#call, _e); } while (0)
+#define LAUNCH_CK(name) do { ++g_launches; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail(name, _e); } while (0)
+
+extern "C" int dbw_abi_version(void) { return DBW_ABI_VERSION; }
+extern "C" const char* dbw_last_error(void) { return g_err; }
+extern "C" uint64_t dbw_launch_count(void) { return g_launches; }
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Workspace {
+  float* verts_ndc; float4* bbox; float4* rec; float* conv; int* view_flags; size_t total;
+};
+static Workspace carve(const DbwRenderSettings& s, void* base) {
+  Workspace w; char* p = (char*)base; size_t off = 0;
+  const size_t B = s.n_views, V = s.n_verts, S = 2 * (size_t)s.n_faces;
+  w.verts_ndc = (float*)(p + off); off += align_up(B * V * 3 * sizeof(float));
+  w.bbox = (float4*)(p + off);     off += align_up(B * S * sizeof(float4));
+  w.rec = (float4*)(p + off);      off += align_up(B * S * 3 * sizeof(float4));
+  w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
+  w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
+  w.total = off; return w;
+}
+struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; size_t total; };
+static BwdScratch carve_bwd(const DbwRenderSettings& s, void* base) {
+  BwdScratch w; char* p = (char*)base; size_t off = 0;
+  const size_t B = s.n_views, V = s.n_verts, S = 2 * (size_t)s.n_faces;
+  w.g_tri = (float*)(p + off);        off += align_up(B * S * 9 * sizeof(float));
+  w.g_conv = (float*)(p + off);       off += align_up(B * S * 9 * sizeof(float));
+  w.g_verts_ndc = (float*)(p + off);  off += align_up(B * V * 3 * sizeof(float));
+  w.total = off; return w;
+}
+
+extern "C" int dbw_workspace_bytes(const DbwRenderSettings* s, size_t* fwd, size_t* bwd) {
+  if (!s) return fail("dbw_workspace_bytes: null settings");
+  if (fwd) *fwd = carve(*s, nullptr).total;
+  if (bwd) *bwd = carve_bwd(*s, nullptr).total;
+  return 0;
+}
+
+static int validate(const DbwRenderSettings* s) {
+  if (!s) return fail("null settings");
+  if (s->n_views <= 0 || s->height <= 0 || s->width <= 0) return fail("n_views, height, width must be positive");
+  if (s->faces_per_pixel <= 0 || s->faces_per_pixel > DBW_MAX_FACES_PER_PIXEL) return fail("faces_per_pixel out of range [1, 64]");
+  if (s->n_verts <= 0 || s->n_faces <= 0 || s->n_maps <= 0) return fail("n_verts, n_faces, n_maps must be positive");
+  if (s->alpha_view_stride != 0 && s->alpha_view_stride != s->n_faces) return fail("alpha_view_stride must be 0 or n_faces");
+  if (s->sigma < 0.f || s->blur_radius < 0.f) return fail("sigma and blur_radius must be >= 0");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ projection (A1)
+__global__ void project_verts_kernel(const float* __restrict__ vw, const float* __restrict__ R, const float* __restrict__ T,
+                                     float fx, float fy, float px, float py, float eps, int B, int V, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * V) return;
+  const int b = i / V, v = i - b * V;
+  const float X = vw[v * 3], Y = vw[v * 3 + 1], Z = vw[v * 3 + 2];
+  const float* r = R + b * 9; const float* t = T + b * 3;
+  const float xv = X * r[0] + Y * r[3] + Z * r[6] + t[0];
+  const float yv = X * r[1] + Y * r[4] + Z * r[7] + t[1];
+  const float zv = X * r[2] + Y * r[5] + Z * r[8] + t[2];
+  const float sgn = (zv > 0.f) ? 1.f : ((zv < 0.f) ? -1.f : 1.f);
+  const float den = sgn * fmaxf(fabsf(zv), eps);
+  out[i * 3] = (fx * xv + px * zv) / den;
+  out[i * 3 + 1] = (fy * yv + py * zv) / den;
+  out[i * 3 + 2] = zv;
+}
+
+// one thread per vertex, deterministic sum over the views
+__global__ void project_verts_backward_kernel(const float* __restrict__ vw, const float* __restrict__ R, const float* __restrict__ T,
+                                              float fx, float fy, float px, float py, float eps, int B, int V,
+                                              const float* __restrict__ g_ndc, float* __restrict__ g_vw) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float X = vw[v * 3], Y = vw[v * 3 + 1], Z = vw[v * 3 + 2];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float* r = R + b * 9; const float* t = T + b * 3;
+    const float xv = X * r[0] + Y * r[3] + Z * r[6] + t[0];
+    const float yv = X * r[1] + Y * r[4] + Z * r[7] + t[1];
+    const float zv = X * r[2] + Y * r[5] + Z * r[8] + t[2];
+    const float sgn = (zv > 0.f) ? 1.f : ((zv < 0.f) ? -1.f : 1.f);
+    const bool clamped = fabsf(zv) < eps;
+    const float den = sgn * fmaxf(fabsf(zv), eps);
+    const float* g = g_ndc + ((size_t)b * V + v) * 3;
+    const float gx = g[0], gy = g[1], gz = g[2];
+    const float nx = fx * xv + px * zv, ny = fy * yv + py * zv;
+    const float gxv = gx * fx / den, gyv = gy * fy / den;
+    float gzv = gz + (gx * px + gy * py) / den;
+    if (!clamped) gzv -= (gx * nx + gy * ny) / (den * den);
+    ax += r[0] * gxv + r[1] * gyv + r[2] * gzv;
+    ay += r[3] * gxv + r[4] * gyv + r[5] * gzv;
+    az += r[6] * gxv + r[7] * gyv + r[8] * gzv;
+  }
+  g_vw[v * 3] += ax; g_vw[v * 3 + 1] += ay; g_vw[v * 3 + 2] += az;
+}
+
+// ------------------------------------------------------------------------------------------------ face setup + z-clip (A3)
+struct ClipResult {
+  int ntri;            // 0, 1 or 2 triangles
+  bool clipped;
+  int i1;              // isolated vertex
+  float w2, w3;
+  float tri[2][9];     // (x,y,z) x 3
+  float conv[2][9];    // rows = barycentrics of the clipped triangle's vertices in the original face
+};
+
+__device__ __forceinline__ void lerp_clip(const float* p1, const float* p2, float w, bool persp, float* out) {
+  if (persp) {
+    const float q1x = p1[0] * p1[2], q1y = p1[1] * p1[2], q2x = p2[0] * p2[2], q2y = p2[1] * p2[2];
+    const float Px = q1x * (1.f - w) + q2x * w, Py = q1y * (1.f - w) + q2y * w, Pz = p1[2] * (1.f - w) + p2[2] * w;
+    out[0] = Px / Pz; out[1] = Py / Pz; out[2] = Pz;
+  } else {
+    out[0] = p1[0] * (1.f - w) + p2[0] * w; out[1] = p1[1] * (1.f - w) + p2[1] * w; out[2] = p1[2] * (1.f - w) + p2[2] * w;
+  }
+}
+
+__device__ __forceinline__ void set3(float* d, const float* s) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; }
+
+__device__ void clip_face(const float a[3][3], float z_clip, bool persp, ClipResult& r) {
+  int nb = 0, behind[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { behind[i] = (z_clip >= 0.f) && (a[i][2] < z_clip); nb += behind[i]; }
+  r.clipped = false; r.i1 = 0; r.w2 = r.w3 = 0.f;
+  if (nb == 0) {
+    r.ntri = 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) set3(&r.tri[0][i * 3], a[i]);
+    return;
+  }
+  if (nb == 3) { r.ntri = 0; return; }
+  r.clipped = true;
+  int i1 = 0;
+  if (nb == 2) { for (int i = 0; i < 3; ++i) if (!behind[i]) i1 = i; }   // the single vertex in front
+  else         { for (int i = 0; i < 3; ++i) if (behind[i]) i1 = i; }    // the single vertex behind
+  const int i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+  const float* p1 = a[i1]; const float* p2 = a[i2]; const float* p3 = a[i3];
+  const float w2 = (p1[2] - z_clip) / (p1[2] - p2[2]);
+  const float w3 = (p1[2] - z_clip) / (p1[2] - p3[2]);
+  float p4[3], p5[3], b1[3] = {0, 0, 0}, b2[3] = {0, 0, 0}, b3[3] = {0, 0, 0}, b4[3] = {0, 0, 0}, b5[3] = {0, 0, 0};
+  lerp_clip(p1, p2, w2, persp, p4);
+  lerp_clip(p1, p3, w3, persp, p5);
+  b1[i1] = 1.f; b2[i2] = 1.f; b3[i3] = 1.f;
+  b4[i1] = 1.f - w2; b4[i2] = w2;
+  b5[i1] = 1.f - w3; b5[i3] = w3;
+  r.i1 = i1; r.w2 = w2; r.w3 = w3;
+  if (nb == 2) {          // (p4, p5, p1)
+    r.ntri = 1;
+    set3(&r.tri[0][0], p4); set3(&r.tri[0][3], p5); set3(&r.tri[0][6], p1);
+    set3(&r.conv[0][0], b4); set3(&r.conv[0][3], b5); set3(&r.conv[0][6], b1);
+  } else {                // (p4, p2, p5) and (p5, p2, p3)
+    r.ntri = 2;
+    set3(&r.tri[0][0], p4); set3(&r.tri[0][3], p2); set3(&r.tri[0][6], p5);
+    set3(&r.conv[0][0], b4); set3(&r.conv[0][3], b2); set3(&r.conv[0][6], b5);
+    set3(&r.tri[1][0], p5); set3(&r.tri[1][3], p2); set3(&r.tri[1][6], p3);
+    set3(&r.conv[1][0], b5); set3(&r.conv[1][3], b2); set3(&r.conv[1][6], b3);
+  }
+}
+
+__device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float* conv, size_t slot, const float* tri,
+                                           const float* cv, bool clipped, int face, int neighbor, float sqrt_blur) {
+  const float x0 = tri[0], y0 = tri[1], z0 = tri[2], x1 = tri[3], y1 = tri[4], z1 = tri[5], x2 = tri[6], y2 = tri[7], z2 = tri[8];
+  const float zmin = fminf(fminf(z0, z1), z2);
+  const f2 a = {x0, y0}, b = {x1, y1}, c = {x2, y2};
+  const float area = edge_nc(c, a, b);
+  const bool degenerate = (area <= DBW_KEPS && area >= -DBW_KEPS);
+  const bool valid = !(zmin < DBW_KEPS) && !degenerate;
+  float4 bb;
+  if (valid) {
+    bb.x = fminf(fminf(x0, x1), x2) - sqrt_blur; bb.y = fmaxf(fmaxf(x0, x1), x2) + sqrt_blur;
+    bb.z = fminf(fminf(y0, y1), y2) - sqrt_blur; bb.w = fmaxf(fmaxf(y0, y1), y2) + sqrt_blur;
+  } else {
+    bb.x = INFINITY; bb.y = -INFINITY; bb.z = INFINITY; bb.w = -INFINITY;
+  }
+  bbox[slot] = bb;
+  rec[slot * 3 + 0] = make_float4(x0, y0, x1, y1);
+  rec[slot * 3 + 1] = make_float4(x2, y2, z0, z1);
+  rec[slot * 3 + 2] = make_float4(z2, __int_as_float(face), __int_as_float(neighbor), __int_as_float(clipped ? 1 : 0));
+  if (clipped) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) conv[slot * 9 + i] = cv[i];
+  }
+}
+
+__global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
+                                  float z_clip, int persp, float sqrt_blur, float4* __restrict__ bbox, float4* __restrict__ rec,
+                                  float* __restrict__ conv, int* __restrict__ view_flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * F) return;
+  const int b = i / F, f = i - b * F;
+  float a[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const float* v = verts_ndc + ((size_t)b * V + faces[f * 3 + j]) * 3;
+    a[j][0] = v[0]; a[j][1] = v[1]; a[j][2] = v[2];
+  }
+  ClipResult r;
+  clip_face(a, z_clip, persp != 0, r);
+  const size_t s0 = (size_t)b * 2 * F + f, s1 = s0 + F;
+  const float inval[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // zmin = 0 < eps -> marked empty
+  write_slot(bbox, rec, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur);
+  write_slot(bbox, rec, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur);
+  if (r.ntri == 2) atomicOr(&view_flags[b], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ raster + shade + blend, forward
+struct RasterParams {
+  int B, H, W, K, V, F, M;
+  int alpha_stride;
+  float sigma, blur, bg0, bg1, bg2;
+  int clip_inside, persp, clipb, detach_bary;
+  const float4* bbox; const float4* rec; const float* conv; const int* view_flags;
+  const float* faces_uvs; const int* face_map; const float* maps; const DbwMapDesc* map_table;
+  const float* faces_alpha;
+  float* out_rgba; int* topk;
+  // backward only
+  const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float* g_maps;
+};
+
+#define TILE_W 16
+#define TILE_H 16
+#define NTHREADS 256
+#define LIST_CAP 512
+
+__device__ __forceinline__ unsigned long long make_key(float pz, int slot) {
+  return ((unsigned long long)__float_as_uint(pz + 0.f) << 32) | (unsigned)slot;
+}
+
+// opacity of one fragment from its signed squared distance (layered_rgb_blend, src/model/renderer.py:252-257)
+__device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_inside) {
+  if (sigma == 0.f) return d <= 0.f ? 1.f : 0.f;
+  if (clip_inside) return expf(-fmaxf(d, 0.f) / sigma);
+  return 1.f / (1.f + expf(d / sigma));
+}
+
+// shared by forward shading and backward: colour of fragment (slot) at pixel p
+struct Shade {
+  TriGeom t; Bary b; f3 bu;       // bu: barycentrics w.r.t. the ORIGINAL face (after un-clipping)
+  float u, v; int m_off, mH, mW; TexTap tap; f3 c00, c01, c10, c11, color;
+};
+
+__device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
+  const size_t gs = (size_t)view * 2 * P.F + slot;
+  s.t = unpack_tri(__ldg(&P.rec[gs * 3]), __ldg(&P.rec[gs * 3 + 1]), __ldg(&P.rec[gs * 3 + 2]));
+  s.b = eval_bary(p, s.t, P.persp, P.clipb);
+  s.bu = s.b.bc;
+  if (s.t.flags & 1) {
+    const float* cv = P.conv + gs * 9;
+    s.bu.x = s.b.bc.x * cv[0] + s.b.bc.y * cv[3] + s.b.bc.z * cv[6];
+    s.bu.y = s.b.bc.x * cv[1] + s.b.bc.y * cv[4] + s.b.bc.z * cv[7];
+    s.bu.z = s.b.bc.x * cv[2] + s.b.bc.y * cv[5] + s.b.bc.z * cv[8];
+  }
+  const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
+  s.u = s.bu.x * __ldg(fu) + s.bu.y * __ldg(fu + 2) + s.bu.z * __ldg(fu + 4);
+  s.v = s.bu.x * __ldg(fu + 1) + s.bu.y * __ldg(fu + 3) + s.bu.z * __ldg(fu + 5);
+  const DbwMapDesc md = P.map_table[__ldg(&P.face_map[s.t.face])];
+  s.m_off = md.offset; s.mH = md.height; s.mW = md.width;
+  s.tap = tex_tap(s.u, s.v, md.offset, md.height, md.width);
+  s.c00 = ld3(P.maps, s.tap.i00); s.c01 = ld3(P.maps, s.tap.i01);
+  s.c10 = ld3(P.maps, s.tap.i10); s.c11 = ld3(P.maps, s.tap.i11);
+  s.color.x = s.c00.x * s.tap.w00 + s.c01.x * s.tap.w01 + s.c10.x * s.tap.w10 + s.c11.x * s.tap.w11;
+  s.color.y = s.c00.y * s.tap.w00 + s.c01.y * s.tap.w01 + s.c10.y * s.tap.w10 + s.c11.y * s.tap.w11;
+  s.color.z = s.c00.z * s.tap.w00 + s.c01.z * s.tap.w01 + s.c10.z * s.tap.w10 + s.c11.z * s.tap.w11;
+}
+
+template <int K>
+__global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterParams P) {
+  __shared__ float4 s_bbox[LIST_CAP];
+  __shared__ float4 s_rec[LIST_CAP * 3];
+  __shared__ int s_slot[LIST_CAP];
+  __shared__ int s_count;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int view = blockIdx.z;
+  const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+  // a warp covers an 8x4 pixel patch; 2x4 warps cover the 16x16 tile
+  const int xi = tx0 + (warp & 1) * 8 + (lane & 7);
+  const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
+  const bool live = xi < P.W && yi < P.H;
+  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
+  // NDC extent of the tile's pixel centres (+X is left, +Y is up)
+  const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
+  const float t_xmin = pix_to_ndc(P.W - 1 - tx1, P.W, P.H), t_xmax = pix_to_ndc(P.W - 1 - tx0, P.W, P.H);
+  const float t_ymin = pix_to_ndc(P.H - 1 - ty1, P.H, P.W), t_ymax = pix_to_ndc(P.H - 1 - ty0, P.H, P.W);
+
+  unsigned long long key[K];
+  float dk[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) { key[k] = ~0ull; dk[k] = 0.f; }
+
+  const int nslots = (P.view_flags[view] & 1) ? 2 * P.F : P.F;
+  const float4* bbox = P.bbox + (size_t)view * 2 * P.F;
+  const float4* rec = P.rec + (size_t)view * 2 * P.F * 3;
+  const bool dist_inside = (!P.clip_inside && P.sigma > 0.f);
+
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+
+  for (int base = 0; base < nslots; base += NTHREADS) {
+    // ---- bin: which face slots of this batch touch the tile?
+    const int s = base + tid;
+    bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
+    if (s < nslots) {
+      bb = __ldg(&bbox[s]);
+      hit = !(bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (hit) {
+      const int pos = wbase + __popc(m & ((1u << lane) - 1u));
+      s_slot[pos] = s; s_bbox[pos] = bb;
+    }
+    __syncthreads();
+    const int cnt = s_count;
+    const bool last = base + NTHREADS >= nslots;
+    if (cnt > LIST_CAP - NTHREADS || last) {
+      // ---- stage the records of the listed faces in shared memory
+      for (int j = tid; j < cnt; j += NTHREADS) {
+        const int sl = s_slot[j];
+        s_rec[j * 3 + 0] = __ldg(&rec[sl * 3 + 0]);
+        s_rec[j * 3 + 1] = __ldg(&rec[sl * 3 + 1]);
+        s_rec[j * 3 + 2] = __ldg(&rec[sl * 3 + 2]);
+      }
+      __syncthreads();
+      // ---- per pixel: test every listed face, keep the K nearest
+      if (live) {
+        for (int j = 0; j < cnt; ++j) {
+          const float4 b4 = s_bbox[j];
+          if (p.x > b4.y || p.x < b4.x || p.y > b4.w || p.y < b4.z) continue;
+          const TriGeom t = unpack_tri(s_rec[j * 3], s_rec[j * 3 + 1], s_rec[j * 3 + 2]);
+          const Bary b = eval_bary(p, t, P.persp, P.clipb);
+          if (b.pz < 0.f) continue;
+          float dist = 1.f;
+          const bool need_dist = !b.inside || dist_inside || t.neighbor >= 0;
+          if (need_dist) dist = tri_dist2(p, t);
+          if (!b.inside && dist >= P.blur) continue;
+          const float sd = b.inside ? -dist : dist;
+          const int slot = s_slot[j];
+          if (t.neighbor >= 0) {
+            // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3)
+            bool drop_new = false;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) {
+                if (dist < fabsf(dk[k])) {
+#pragma unroll
+                  for (int q = 0; q < K - 1; ++q) if (q >= k) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
+                  key[K - 1] = ~0ull; dk[K - 1] = 0.f;
+                } else drop_new = true;
+                break;
+              }
+            }
+            if (drop_new) continue;
+          }
+          const unsigned long long nk = make_key(b.pz, slot);
+          if (nk >= key[K - 1]) continue;
+          // sorted insertion with static indexing
+#pragma unroll
+          for (int k = K - 1; k >= 1; --k) {
+            const bool up = nk < key[k - 1];
+            const bool here = !up && nk < key[k];
+            key[k] = up ? key[k - 1] : (here ? nk : key[k]);
+            dk[k] = up ? dk[k - 1] : (here ? sd : dk[k]);
+          }
+          if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      __syncthreads();
+    }
+  }
+
+  if (!live) return;
+  // ---- shade + blend the sorted fragments front to back (layered_rgb_blend, Appendix B)
+  float occ = 1.f, r = 0.f, g = 0.f, bl = 0.f;
+  const size_t plane = (size_t)P.H * P.W;
+  const size_t pix = (size_t)yi * P.W + xi;
+  int* ids = P.topk + (size_t)view * P.K * plane + pix;
+#pragma unroll 1
+  for (int k = 0; k < P.K; ++k) {
+    const unsigned long long k0 = key[0];
+    const float d0 = dk[0];
+#pragma unroll
+    for (int q = 0; q < K - 1; ++q) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
+    key[K - 1] = ~0ull;
+    if (k0 == ~0ull) { ids[(size_t)k * plane] = -1; continue; }
+    const int slot = (int)(unsigned)k0;
+    ids[(size_t)k * plane] = slot;
+    Shade s;
+    shade_fragment(P, view, slot, p, s);
+    float a = frag_alpha(d0, P.sigma, P.clip_inside);
+    if (P.faces_alpha) a *= __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]);
+    const float w = occ * a;
+    r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
+    occ *= (1.f - a);
+  }
+  float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
+  o[0] = r + occ * P.bg0; o[plane] = g + occ * P.bg1; o[2 * plane] = bl + occ * P.bg2; o[3 * plane] = 1.f - occ;
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// One thread per pixel.  Pass 1 walks the K saved fragments front to back, recomputes colour/opacity, scatters the
+// texture gradient and (unless detach_bary) the barycentric-path vertex gradient; pass 2 walks back to front with the
+// division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
+__global__ void __launch_bounds__(NTHREADS) raster_backward_kernel(const RasterParams P) {
+  extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int view = blockIdx.z;
+  const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
+  const int yi = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+  if (xi >= P.W || yi >= P.H) return;
+  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
+  const size_t plane = (size_t)P.H * P.W;
+  const size_t pix = (size_t)yi * P.W + xi;
+  const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
+  const float gr = go[0], gg = go[plane], gb = go[2 * plane], ga = go[3 * plane];
+  const int* ids = P.topk + (size_t)view * P.K * plane + pix;
+  float* s_alpha = s_store;
+  float* s_cdot = s_store + (size_t)P.K * NTHREADS;
+  float* s_e = s_store + 2 * (size_t)P.K * NTHREADS;
+  float* s_occ = s_store + 3 * (size_t)P.K * NTHREADS;
+  const bool any_grad = (gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f);
+
+  float occ = 1.f;
+  int n = 0;
+  for (int k = 0; k < P.K; ++k) {
+    const int slot = ids[(size_t)k * plane];
+    if (slot < 0) break;
+    ++n;
+    Shade s;
+    shade_fragment(P, view, slot, p, s);
+    float d;
+    if (s.b.inside && P.clip_inside) d = -1.f;
+    else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
+    const float e = frag_alpha(d, P.sigma, P.clip_inside);
+    const float fa = P.faces_alpha ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
+    const float a = e * fa;
+    const float cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
+    s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
+    s_occ[k * NTHREADS + tid] = occ;
+    const float w = occ * a;                 // d RGB / d colour_k
+    if (w != 0.f && any_grad) {
+      const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
+      if (P.g_maps) {
+        float* gm = P.g_maps;
+        atomicAdd(gm + s.tap.i00, gcx * s.tap.w00); atomicAdd(gm + s.tap.i00 + 1, gcy * s.tap.w00); atomicAdd(gm + s.tap.i00 + 2, gcz * s.tap.w00);
+        if (s.tap.i01 >= 0) { atomicAdd(gm + s.tap.i01, gcx * s.tap.w01); atomicAdd(gm + s.tap.i01 + 1, gcy * s.tap.w01); atomicAdd(gm + s.tap.i01 + 2, gcz * s.tap.w01); }
+        if (s.tap.i10 >= 0) { atomicAdd(gm + s.tap.i10, gcx * s.tap.w10); atomicAdd(gm + s.tap.i10 + 1, gcy * s.tap.w10); atomicAdd(gm + s.tap.i10 + 2, gcz * s.tap.w10); }
+        if (s.tap.i11 >= 0) { atomicAdd(gm + s.tap.i11, gcx * s.tap.w11); atomicAdd(gm + s.tap.i11 + 1, gcy * s.tap.w11); atomicAdd(gm + s.tap.i11 + 2, gcz * s.tap.w11); }
+      }
+      if (!P.detach_bary) {
+        // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
+        const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
+        const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
+        const float d00 = s.c00.x * gcx + s.c00.y * gcy + s.c00.z * gcz, d01 = s.c01.x * gcx + s.c01.y * gcy + s.c01.z * gcz;
+        const float d10 = s.c10.x * gcx + s.c10.y * gcy + s.c10.z * gcz, d11 = s.c11.x * gcx + s.c11.y * gcy + s.c11.z * gcz;
+        const float gix = (d01 - d00) * ey + (d11 - d10) * wy;
+        const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
+        const float gu = gix * s.tap.mx, gv = giy * s.tap.my;
+        const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
+        f3 gbu = {gu * __ldg(fu) + gv * __ldg(fu + 1), gu * __ldg(fu + 2) + gv * __ldg(fu + 3), gu * __ldg(fu + 4) + gv * __ldg(fu + 5)};
+        const size_t gs = (size_t)view * 2 * P.F + slot;
+        f3 gbc = gbu;
+        if (s.t.flags & 1) {
+          const float* cv = P.conv + gs * 9;
+          gbc.x = cv[0] * gbu.x + cv[1] * gbu.y + cv[2] * gbu.z;
+          gbc.y = cv[3] * gbu.x + cv[4] * gbu.y + cv[5] * gbu.z;
+          gbc.z = cv[6] * gbu.x + cv[7] * gbu.y + cv[8] * gbu.z;
+          float* gc = P.g_conv + gs * 9;
+          const float bcv[3] = {s.b.bc.x, s.b.bc.y, s.b.bc.z}; const float gv3[3] = {gbu.x, gbu.y, gbu.z};
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) atomicAdd(gc + i * 3 + j, bcv[i] * gv3[j]);
+        }
+        float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+        f3 gb_ = gbc;
+        if (P.clipb) gb_ = clip_backward(s.b.bp, gb_);
+        if (P.persp) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
+        f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
+        bary_backward(p, s.t, gb_, g0, g1, g2);
+        float* gt = P.g_tri + gs * 9;
+        atomicAdd(gt + 0, g0.x); atomicAdd(gt + 1, g0.y); atomicAdd(gt + 2, gz0);
+        atomicAdd(gt + 3, g1.x); atomicAdd(gt + 4, g1.y); atomicAdd(gt + 5, gz1);
+        atomicAdd(gt + 6, g2.x); atomicAdd(gt + 7, g2.y); atomicAdd(gt + 8, gz2);
+      }
+    }
+    occ *= (1.f - a);
+  }
+  if (!any_grad || n == 0) return;
+
+  // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
+  float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
+  for (int k = n - 1; k >= 0; --k) {
+    const float a = s_alpha[k * NTHREADS + tid], cdot = s_cdot[k * NTHREADS + tid], e = s_e[k * NTHREADS + tid];
+    const float occ_k = s_occ[k * NTHREADS + tid];
+    const float g_alpha = occ_k * (cdot - Tacc);
+    Tacc = a * cdot + (1.f - a) * Tacc;
+    if (g_alpha == 0.f) continue;
+    const int slot = ids[(size_t)k * plane];
+    const size_t gs = (size_t)view * 2 * P.F + slot;
+    const TriGeom t = unpack_tri(__ldg(&P.rec[gs * 3]), __ldg(&P.rec[gs * 3 + 1]), __ldg(&P.rec[gs * 3 + 2]));
+    float fa = 1.f;
+    if (P.faces_alpha) {
+      fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
+      if (P.g_faces_alpha) atomicAdd(P.g_faces_alpha + (size_t)view * P.alpha_stride + t.face, g_alpha * e);
+    }
+    if (P.sigma > 0.f) {
+      const Bary b = eval_bary(p, t, P.persp, P.clipb);
+      float g_sd;           // gradient w.r.t. the SIGNED squared distance
+      if (P.clip_inside) {
+        if (b.inside) continue;                        // clamp(d, 0): flat inside the face
+        g_sd = g_alpha * fa * (-e / P.sigma);
+      } else {
+        g_sd = g_alpha * fa * (-e * (1.f - e) / P.sigma);
+      }
+      const float g_dist = b.inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
+      if (g_dist == 0.f) continue;
+      f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
+      tri_dist_backward(p, t, g_dist, g0, g1, g2);
+      float* gt = P.g_tri + gs * 9;
+      if (g0.x != 0.f || g0.y != 0.f) { atomicAdd(gt + 0, g0.x); atomicAdd(gt + 1, g0.y); }
+      if (g1.x != 0.f || g1.y != 0.f) { atomicAdd(gt + 3, g1.x); atomicAdd(gt + 4, g1.y); }
+      if (g2.x != 0.f || g2.y != 0.f) { atomicAdd(gt + 6, g2.x); atomicAdd(gt + 7, g2.y); }
+    }
+  }
+}
+
+// per (view, face): fold the gradients of the (clipped) triangle slots back onto the face's 3 projected vertices
+__device__ __forceinline__ void lerp_clip_backward(const float* p1, const float* p2, float w, bool persp, const float* gp4,
+                                                   float* gp1, float* gp2, float& gw) {
+  if (persp) {
+    const float q1x = p1[0] * p1[2], q1y = p1[1] * p1[2], q2x = p2[0] * p2[2], q2y = p2[1] * p2[2];
+    const float Px = q1x * (1.f - w) + q2x * w, Py = q1y * (1.f - w) + q2y * w, Pz = p1[2] * (1.f - w) + p2[2] * w;
+    const float gPx = gp4[0] / Pz, gPy = gp4[1] / Pz;
+    const float gPz = gp4[2] - (gp4[0] * Px + gp4[1] * Py) / (Pz * Pz);
+    gw += gPx * (q2x - q1x) + gPy * (q2y - q1y) + gPz * (p2[2] - p1[2]);
+    const float a = 1.f - w;
+    // q = (x z, y z, z)
+    gp1[0] += gPx * a * p1[2]; gp1[1] += gPy * a * p1[2]; gp1[2] += gPx * a * p1[0] + gPy * a * p1[1] + gPz * a;
+    gp2[0] += gPx * w * p2[2]; gp2[1] += gPy * w * p2[2]; gp2[2] += gPx * w * p2[0] + gPy * w * p2[1] + gPz * w;
+  } else {
+    const float a = 1.f - w;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gp1[i] += gp4[i] * a; gp2[i] += gp4[i] * w; gw += gp4[i] * (p2[i] - p1[i]); }
+  }
+}
+
+__global__ void face_setup_backward_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
+                                           float z_clip, int persp, const float* __restrict__ g_tri, const float* __restrict__ g_conv,
+                                           float* __restrict__ g_verts_ndc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * F) return;
+  const int b = i / F, f = i - b * F;
+  const size_t s0 = (size_t)b * 2 * F + f, s1 = s0 + F;
+  float a[3][3]; int vid[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    vid[j] = faces[f * 3 + j];
+    const float* v = verts_ndc + ((size_t)b * V + vid[j]) * 3;
+    a[j][0] = v[0]; a[j][1] = v[1]; a[j][2] = v[2];
+  }
+  int nb = 0, behind[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { behind[j] = (z_clip >= 0.f) && (a[j][2] < z_clip); nb += behind[j]; }
+  if (nb == 3) return;
+  float ga[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  const float* gt0 = g_tri + s0 * 9;
+  if (nb == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { ga[j][0] = gt0[j * 3]; ga[j][1] = gt0[j * 3 + 1]; ga[j][2] = gt0[j * 3 + 2]; }
+  } else {
+    int i1 = 0;
+    if (nb == 2) { for (int j = 0; j < 3; ++j) if (!behind[j]) i1 = j; }
+    else         { for (int j = 0; j < 3; ++j) if (behind[j]) i1 = j; }
+    const int i2 = (i1 + 1) % 3, i3 = (i1 + 2) % 3;
+    const float* p1 = a[i1]; const float* p2 = a[i2]; const float* p3 = a[i3];
+    const float den2 = p1[2] - p2[2], den3 = p1[2] - p3[2];
+    const float w2 = (p1[2] - z_clip) / den2, w3 = (p1[2] - z_clip) / den3;
+    float gp1[3] = {0, 0, 0}, gp2[3] = {0, 0, 0}, gp3[3] = {0, 0, 0}, gp4[3] = {0, 0, 0}, gp5[3] = {0, 0, 0};
+    float gb4[3] = {0, 0, 0}, gb5[3] = {0, 0, 0};
+    const float* gc0 = g_conv + s0 * 9;
+    if (nb == 2) {      // slot0 = (p4, p5, p1), conv rows (b4, b5, b1)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { gp4[c] += gt0[c]; gp5[c] += gt0[3 + c]; gp1[c] += gt0[6 + c]; gb4[c] += gc0[c]; gb5[c] += gc0[3 + c]; }
+    } else {            // slot0 = (p4, p2, p5) ; slot1 = (p5, p2, p3)
+      const float* gt1 = g_tri + s1 * 9; const float* gc1 = g_conv + s1 * 9;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        gp4[c] += gt0[c]; gp2[c] += gt0[3 + c] + gt1[3 + c]; gp5[c] += gt0[6 + c] + gt1[c]; gp3[c] += gt1[6 + c];
+        gb4[c] += gc0[c]; gb5[c] += gc0[6 + c] + gc1[c];
+      }
+    }
+    float gw2 = 0.f, gw3 = 0.f;
+    // b4 = e_i1 (1-w2) + e_i2 w2 ; b5 = e_i1 (1-w3) + e_i3 w3
+    gw2 += gb4[i2] - gb4[i1];
+    gw3 += gb5[i3] - gb5[i1];
+    lerp_clip_backward(p1, p2, w2, persp != 0, gp4, gp1, gp2, gw2);
+    lerp_clip_backward(p1, p3, w3, persp != 0, gp5, gp1, gp3, gw3);
+    // w = (z1 - zc) / (z1 - z_other)
+    gp1[2] += gw2 * (z_clip - p2[2]) / (den2 * den2) + gw3 * (z_clip - p3[2]) / (den3 * den3);
+    gp2[2] += gw2 * (p1[2] - z_clip) / (den2 * den2);
+    gp3[2] += gw3 * (p1[2] - z_clip) / (den3 * den3);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { ga[i1][c] = gp1[c]; ga[i2][c] = gp2[c]; ga[i3][c] = gp3[c]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float* g = g_verts_ndc + ((size_t)b * V + vid[j]) * 3;
+    if (ga[j][0] != 0.f) atomicAdd(g, ga[j][0]);
+    if (ga[j][1] != 0.f) atomicAdd(g + 1, ga[j][1]);
+    if (ga[j][2] != 0.f) atomicAdd(g + 2, ga[j][2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ compositing + MSE (dbw.py:223, 366-367)
+__global__ void composite_mse_kernel(int n_px_total, int plane, const float* __restrict__ fg, const float* __restrict__ env,
+                                     const float* __restrict__ imgs, float inv_count, float* __restrict__ rec,
+                                     float* __restrict__ loss_sum, float* __restrict__ g_fg, float* __restrict__ g_env) {
+  float local = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px_total; i += gridDim.x * blockDim.x) {
+    const int b = i / plane, px = i - b * plane;
+    const float* f = fg + (size_t)b * 4 * plane + px;
+    const float* e = env + (size_t)b * 4 * plane + px;
+    const float* im = imgs + (size_t)b * 3 * plane + px;
+    const float m = f[3 * (size_t)plane];
+    float gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float fc = f[(size_t)c * plane], ec = e[(size_t)c * plane];
+      const float r = fc * m + (1.f - m) * ec;
+      const float diff = r - im[(size_t)c * plane];
+      local += diff * diff;
+      if (rec) rec[(size_t)b * 3 * plane + (size_t)c * plane + px] = r;
+      const float gr = 2.f * diff * inv_count;
+      if (g_fg) g_fg[(size_t)b * 4 * plane + (size_t)c * plane + px] = gr * m;
+      if (g_env) g_env[(size_t)b * 4 * plane + (size_t)c * plane + px] = gr * (1.f - m);
+      gm += gr * (fc - ec);
+    }
+    if (g_fg) g_fg[(size_t)b * 4 * plane + 3 * (size_t)plane + px] = gm;
+    if (g_env) g_env[(size_t)b * 4 * plane + 3 * (size_t)plane + px] = 0.f;
+  }
+  // block reduction -> one atomic per block
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) atomicAdd(loss_sum, v * inv_count);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, const float* faces_uvs, const int32_t* face_map,
+                                const float* maps, const DbwMapDesc* map_table, const float* faces_alpha) {
+  RasterParams P;
+  memset(&P, 0, sizeof(P));
+  P.B = s.n_views; P.H = s.height; P.W = s.width; P.K = s.faces_per_pixel; P.V = s.n_verts; P.F = s.n_faces; P.M = s.n_maps;
+  P.alpha_stride = s.alpha_view_stride;
+  P.sigma = s.sigma; P.blur = s.blur_radius; P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
+  P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
+  P.bbox = w.bbox; P.rec = w.rec; P.conv = w.conv; P.view_flags = w.view_flags;
+  P.faces_uvs = faces_uvs; P.face_map = face_map; P.maps = maps; P.map_table = map_table; P.faces_alpha = faces_alpha;
+  return P;
+}
+
+template <int K>
+static void launch_forward(const RasterParams& P, dim3 grid, cudaStream_t st) {
+  raster_forward_kernel<K><<<grid, NTHREADS, 0, st>>>(P);
+}
+
+extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                  const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                                  const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (validate(s)) return -1;
+  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba || !topk_ids || !workspace)
+    return fail("dbw_render_forward: null pointer argument");
+  if (!s->verts_are_ndc && (!R || !T)) return fail("dbw_render_forward: R and T are required unless verts_are_ndc");
+  Workspace w = carve(*s, workspace);
+  if (workspace_bytes < w.total) return fail("dbw_render_forward: workspace too small (see dbw_workspace_bytes)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->n_views, V = s->n_verts, F = s->n_faces;
+  const float* verts_ndc = verts;
+  if (!s->verts_are_ndc) {
+    project_verts_kernel<<<(B * V + 255) / 256, 256, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V, w.verts_ndc);
+    LAUNCH_CK("project_verts_kernel");
+    verts_ndc = w.verts_ndc;
+  }
+  CK(cudaMemsetAsync(w.view_flags, 0, B * sizeof(int), st));
+  face_setup_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
+                                                         sqrtf(s->blur_radius), w.bbox, w.rec, w.conv, w.view_flags);
+  LAUNCH_CK("face_setup_kernel");
+  RasterParams P = make_params(*s, w, faces_uvs, face_map, maps, map_table, faces_alpha);
+  P.out_rgba = out_rgba; P.topk = topk_ids;
+  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
+  const int K = s->faces_per_pixel;
+  if (K <= 1) launch_forward<1>(P, grid, st);
+  else if (K <= 4) launch_forward<4>(P, grid, st);
+  else if (K <= 10) launch_forward<10>(P, grid, st);
+  else if (K <= 16) launch_forward<16>(P, grid, st);
+  else if (K <= 25) launch_forward<25>(P, grid, st);
+  else if (K <= 32) launch_forward<32>(P, grid, st);
+  else launch_forward<64>(P, grid, st);
+  LAUNCH_CK("raster_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                   const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                                   const float* T, const float* faces_alpha, const int32_t* topk_ids, const void* workspace,
+                                   size_t workspace_bytes, const float* grad_rgba, float* g_verts, float* g_faces_alpha,
+                                   float* g_maps, void* bwd_scratch, size_t bwd_scratch_bytes, void* stream) {
+  if (validate(s)) return -1;
+  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !topk_ids || !workspace || !grad_rgba || !bwd_scratch)
+    return fail("dbw_render_backward: null pointer argument");
+  Workspace w = carve(*s, (void*)workspace);
+  BwdScratch g = carve_bwd(*s, bwd_scratch);
+  if (workspace_bytes < w.total || bwd_scratch_bytes < g.total) return fail("dbw_render_backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = s->n_views, V = s->n_verts, F = s->n_faces;
+  const bool need_geom = g_verts != nullptr;
+  CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
+  RasterParams P = make_params(*s, w, faces_uvs, face_map, maps, map_table, faces_alpha);
+  P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
+  P.g_faces_alpha = g_faces_alpha; P.g_maps = g_maps;
+  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
+  const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(raster_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  raster_backward_kernel<<<grid, NTHREADS, smem, st>>>(P);
+  LAUNCH_CK("raster_backward_kernel");
+  if (need_geom) {
+    const float* verts_ndc = s->verts_are_ndc ? verts : w.verts_ndc;
+    float* g_ndc = s->verts_are_ndc ? g_verts : g.g_verts_ndc;
+    face_setup_backward_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
+                                                                    g.g_tri, g.g_conv, g_ndc);
+    LAUNCH_CK("face_setup_backward_kernel");
+    if (!s->verts_are_ndc) {
+      if (!R || !T) return fail("dbw_render_backward: R and T are required unless verts_are_ndc");
+      project_verts_backward_kernel<<<(V + 127) / 128, 128, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V,
+                                                                     g.g_verts_ndc, g_verts);
+      LAUNCH_CK("project_verts_backward_kernel");
+    }
+  }
+  return 0;
+}
+
+extern "C" int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
+                                 const float* imgs, float inv_count, float* rec, float* loss_sum, float* g_fg, float* g_env,
+                                 void* stream) {
+  if (!fg || !env || !imgs || !loss_sum) return fail("dbw_composite_mse: null pointer argument");
+  if (n_views <= 0 || height <= 0 || width <= 0) return fail("dbw_composite_mse: bad sizes");
+  const int plane = height * width;
+  const long long total = (long long)n_views * plane;
+  if (total > 0x7fffffffLL) return fail("dbw_composite_mse: too many pixels for one call");
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  composite_mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((int)total, plane, fg, env, imgs, inv_count, rec, loss_sum, g_fg, g_env);
+  LAUNCH_CK("composite_mse_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer entry point
+static struct { char* base; size_t cap; } g_arena = {nullptr, 0};
+
+static int arena_reserve(size_t bytes) {
+  if (bytes <= g_arena.cap) return 0;
+  if (g_arena.base) cudaFree(g_arena.base);
+  g_arena.base = nullptr; g_arena.cap = 0;
+  CK(cudaMalloc((void**)&g_arena.base, bytes));
+  g_arena.cap = bytes;
+  return 0;
+}
+extern "C" void dbw_host_arena_release(void) {
+  if (g_arena.base) cudaFree(g_arena.base);
+  g_arena.base = nullptr; g_arena.cap = 0;
+}
+
+extern "C" int dbw_render_forward_host(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                       const int32_t* face_map, const float* maps, size_t maps_floats, const DbwMapDesc* map_table,
+                                       const float* R, const float* T, const float* faces_alpha, float* out_rgba, void* stream) {
+  if (validate(s)) return -1;
+  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba) return fail("dbw_render_forward_host: null pointer argument");
+  const size_t B = s->n_views, V = s->n_verts, F = s->n_faces, M = s->n_maps, HW = (size_t)s->height * s->width, K = s->faces_per_pixel;
+  size_t fwd = 0; dbw_workspace_bytes(s, &fwd, nullptr);
+  const size_t n_verts_f = (s->verts_are_ndc ? B : 1) * V * 3;
+  const size_t n_alpha = faces_alpha ? (s->alpha_view_stride ? B * F : F) : 0;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_verts = take(n_verts_f * 4), o_faces = take(F * 3 * 4), o_fuv = take(F * 6 * 4), o_fmap = take(F * 4);
+  const size_t o_maps = take(maps_floats * 4), o_tab = take(M * sizeof(DbwMapDesc)), o_R = take(B * 9 * 4), o_T = take(B * 3 * 4);
+  const size_t o_alpha = take(n_alpha * 4 + 4), o_out = take(B * 4 * HW * 4), o_ids = take(B * K * HW * 4), o_ws = take(fwd);
+  if (arena_reserve(off)) return -1;
+  char* d = g_arena.base;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(d + o_verts, verts, n_verts_f * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_faces, faces, F * 3 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_fuv, faces_uvs, F * 6 * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_fmap, face_map, F * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_maps, maps, maps_floats * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_tab, map_table, M * sizeof(DbwMapDesc), cudaMemcpyHostToDevice, st));
+  if (R) CK(cudaMemcpyAsync(d + o_R, R, B * 9 * 4, cudaMemcpyHostToDevice, st));
+  if (T) CK(cudaMemcpyAsync(d + o_T, T, B * 3 * 4, cudaMemcpyHostToDevice, st));
+  if (faces_alpha) CK(cudaMemcpyAsync(d + o_alpha, faces_alpha, n_alpha * 4, cudaMemcpyHostToDevice, st));
+  const int rc = dbw_render_forward(s, (float*)(d + o_verts), (int32_t*)(d + o_faces), (float*)(d + o_fuv), (int32_t*)(d + o_fmap),
+                                    (float*)(d + o_maps), (DbwMapDesc*)(d + o_tab), R ? (float*)(d + o_R) : nullptr,
+                                    T ? (float*)(d + o_T) : nullptr, faces_alpha ? (float*)(d + o_alpha) : nullptr,
+                                    (float*)(d + o_out), (int32_t*)(d + o_ids), d + o_ws, fwd, stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_rgba, d + o_out, B * 4 * HW * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,206 @@
+"""Drop-in for the reference's `Renderer` (src/model/renderer.py:24-132): same constructor kwargs, same
+`forward(meshes, R, T, viz_purpose=False, **kwargs) -> (B,4,H,W)`, same `update_cameras(device=, K=)` /
+`.cameras.K` probe (src/model/dbw.py:204-208) -- but the whole MeshRasterizer + LayeredShader + layered_rgb_blend
+stack behind it is ONE pair of hand-written sm_100a kernels reached through the C-ABI of include/dbw_render.h.
+There is no CPU / PyTorch fallback: a missing library or a non-CUDA tensor raises."""
+import ctypes
+from copy import deepcopy
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import DbwMapDesc, DbwRenderSettings, DbwError
+
+LAYERED_SHADER = True
+SHADING_TYPE = 'raw'
+EPS = 1e-8          # renderer.py:20
+
+
+class _Cameras:
+    """The subset of PyTorch3D's PerspectiveCameras / FoVPerspectiveCameras state the hot path reads."""
+
+    def __init__(self, name='fov', device=None, K=None, fov=60.0, **unused):
+        self.name, self.K, self.device, self.fov = name, K, device, fov
+
+    def to(self, device):
+        self.device = device
+        if self.K is not None:
+            self.K = self.K.to(device)
+        return self
+
+    def intrinsics(self):
+        """(fx, fy, px, py) of the NDC projection x_ndc = fx X/Z + px."""
+        if self.K is not None:
+            K = self.K.reshape(-1, 4, 4)[0].detach().cpu()
+            return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+        if self.name == 'perspective':
+            return 1.0, 1.0, 0.0, 0.0                   # PerspectiveCameras defaults: focal_length=1, principal_point=0
+        f = 1.0 / np.tan(np.deg2rad(self.fov) / 2)      # FoVPerspectiveCameras, aspect 1
+        return f, f, 0.0, 0.0
+
+
+def _c(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _RenderFn(torch.autograd.Function):
+    """autograd seam over dbw_render_forward / dbw_render_backward (include/dbw_render.h)."""
+
+    @staticmethod
+    def forward(ctx, verts, maps, faces_alpha, R, T, faces, faces_uvs, face_map, map_table, cfg):
+        if not verts.is_cuda:
+            raise DbwError('the B200 renderer needs CUDA tensors (there is no CPU fallback)')
+        s = cfg
+        B, H, W, K = s.n_views, s.height, s.width, s.faces_per_pixel
+        L = _lib.lib()
+        verts, maps = verts.detach().contiguous().float(), maps.detach().contiguous().float()
+        fa = faces_alpha.detach().contiguous().float() if faces_alpha is not None else None
+        R, T = R.detach().contiguous().float(), T.detach().contiguous().float()
+        fwd, bwd = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        _lib.check(L.dbw_workspace_bytes(ctypes.byref(s), ctypes.byref(fwd), ctypes.byref(bwd)), 'dbw_workspace_bytes')
+        ws = torch.empty(fwd.value, dtype=torch.uint8, device=verts.device)
+        out = torch.empty(B, 4, H, W, dtype=torch.float32, device=verts.device)
+        ids = torch.empty(B, K, H, W, dtype=torch.int32, device=verts.device)
+        _lib.check(L.dbw_render_forward(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
+                                        _c(map_table), _c(R), _c(T), _c(fa), _c(out), _c(ids), _c(ws), fwd.value,
+                                        _stream()), 'dbw_render_forward')
+        ctx.save_for_backward(verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws)
+        ctx.cfg, ctx.bwd_bytes = s, bwd.value
+        ctx.mark_non_differentiable(ids)
+        return out, ids
+
+    @staticmethod
+    def backward(ctx, g_out, _g_ids):
+        verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws = ctx.saved_tensors
+        s = ctx.cfg
+        L = _lib.lib()
+        g_out = g_out.contiguous().float()
+        need_v, need_m, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and fa is not None
+        g_verts = torch.zeros_like(verts) if need_v else None
+        g_maps = torch.zeros_like(maps) if need_m else None
+        g_fa = torch.zeros_like(fa) if need_a else None
+        scratch = torch.empty(ctx.bwd_bytes, dtype=torch.uint8, device=verts.device)
+        _lib.check(L.dbw_render_backward(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
+                                         _c(map_table), _c(R), _c(T), _c(fa), _c(ids), _c(ws), ws.numel(), _c(g_out),
+                                         _c(g_verts), _c(g_fa), _c(g_maps), _c(scratch), scratch.numel(), _stream()),
+                   'dbw_render_backward')
+        return g_verts, g_maps, g_fa, None, None, None, None, None, None, None
+
+
+def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
+                  perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS):
+    s = DbwRenderSettings()
+    s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
+    s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
+    s.fx, s.fy, s.px, s.py = intr
+    s.sigma, s.blur_radius = float(sigma), float(blur_radius)
+    s.z_clip = float(z_clip) if z_clip is not None else -1.0
+    s.proj_eps = float(eps)
+    s.background = (ctypes.c_float * 3)(*[float(c) for c in background])
+    s.clip_inside, s.perspective_correct = int(clip_inside), int(perspective_correct)
+    s.clip_barycentric, s.detach_bary, s.verts_are_ndc = int(clip_barycentric), int(detach_bary), int(verts_are_ndc)
+    return s
+
+
+def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
+                 z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
+                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False):
+    """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
+    verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
+    map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,)."""
+    H, W = image_size
+    B = R.shape[0] if R is not None else verts.shape[0]
+    V = verts.shape[-2]
+    Fn = faces.shape[0]
+    dev = verts.device
+    table = (DbwMapDesc * len(map_table_host))(*[DbwMapDesc(int(o), int(h), int(w), 0) for o, h, w in map_table_host])
+    map_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.int32).to(dev)
+    alpha_stride = 0
+    if faces_alpha is not None:
+        if faces_alpha.numel() == B * Fn and B > 1:
+            alpha_stride = Fn
+        elif faces_alpha.numel() != Fn:
+            raise DbwError(f'faces_alpha must have F={Fn} or B*F={B * Fn} entries, got {faces_alpha.numel()}')
+    if blur_radius is None:
+        blur_radius = np.log(1. / 1e-4 - 1.) * sigma            # renderer.py:51
+    cfg = make_settings(B, H, W, faces_per_pixel, V, Fn, len(map_table_host), alpha_stride, intr, sigma, blur_radius,
+                        z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc)
+    if R is None:
+        R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
+        T = torch.zeros(B, 3, device=dev)
+    out, ids = _RenderFn.apply(verts, maps, faces_alpha, R, T, faces.to(torch.int32).contiguous(),
+                               faces_uvs.contiguous().float(), face_map.to(torch.int32).contiguous(), map_table, cfg)
+    return (out, ids) if return_ids else out
+
+
+class Renderer(nn.Module):
+    def __init__(self, img_size, **kwargs):
+        super().__init__()
+        self.img_size = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
+        self._init_kwargs = deepcopy(kwargs)
+        self.init_cameras(**kwargs.pop('cameras', {}))
+        self.init_lights(**kwargs.pop('lights', {}))
+        self.sigma = kwargs.pop('sigma', 1e-4)
+        self.background_color = tuple(kwargs.pop('background_color', (0, 0, 0)))
+        self.faces_per_pixel = kwargs.pop('faces_per_pixel', 25)
+        p_correct = kwargs.pop('perspective_correct', None)
+        self.perspective_correct = True if p_correct is None else bool(p_correct)   # None -> True for perspective cams
+        self.z_clip = kwargs.pop('z_clip', None)
+        kwargs.pop('debug', False)
+        if not kwargs.pop('layered_shader', LAYERED_SHADER):
+            raise NotImplementedError('only the LayeredShader path of the reference is implemented')
+        self.clip_inside = kwargs.pop('clip_inside', True)
+        self.shading_type = kwargs.pop('shading_type', SHADING_TYPE)
+        self.detach_bary = kwargs.pop('detach_bary', False)
+        assert len(kwargs) == 0, kwargs
+        self.blur_radius = float(np.log(1. / 1e-4 - 1.) * self.sigma)                # renderer.py:51
+
+    def init_cameras(self, **kwargs):
+        kwargs = deepcopy(kwargs)
+        self.cam_kwargs = kwargs
+        self.cameras = _Cameras(**kwargs)
+
+    def init_lights(self, **kwargs):
+        self.light_kwargs = deepcopy(kwargs)
+
+    @property
+    def init_kwargs(self):
+        return deepcopy(self._init_kwargs)
+
+    def update_cameras(self, **kwargs):
+        merged = deepcopy(self.cam_kwargs)
+        merged.update(kwargs)
+        self.cameras = _Cameras(**merged)
+
+    def to(self, device):
+        super().to(device)
+        self.cameras = self.cameras.to(device)
+        return self
+
+    def forward(self, meshes, R, T, viz_purpose=False, **kwargs):
+        if self.shading_type != 'raw' or self.light_kwargs.get('name', 'ambient') != 'ambient':
+            raise NotImplementedError('lit shading (renderer_light) is a visualisation-only path: not in the B200 hot path yet')
+        faces_alpha = kwargs.get('faces_alpha')
+        verts, faces = meshes.get_mesh_verts_faces(0)
+        txt = meshes.textures
+        fvu, fmap = txt.scene_arrays()
+        maps, table = txt.packed_maps()
+        H, W = self.img_size
+        intr = self.cameras.intrinsics()
+        if viz_purpose:
+            # VizMeshRenderer (renderer.py:56-60,178-183): hard 4x supersampled render, box-filtered, no gradient
+            with torch.no_grad():
+                out = render_scene(verts, faces, fvu, fmap, maps, table, R, T, intr, (H * 4, W * 4), 0.0, 1, self.z_clip,
+                                   self.detach_bary, self.clip_inside, self.background_color, faces_alpha,
+                                   self.perspective_correct)
+                return F.avg_pool2d(out, kernel_size=4, stride=4)
+        return render_scene(verts, faces, fvu, fmap, maps, table, R, T, intr, (H, W), self.sigma, self.faces_per_pixel,
+                            self.z_clip, self.detach_bary, self.clip_inside, self.background_color, faces_alpha,
+                            self.perspective_correct, blur_radius=self.blur_radius)

@@ -1,0 +1,129 @@
+/*
+ * include/dbw_render.h -- C-ABI of the B200-native differentiable primitive renderer.
+ *
+ * The reference (monniert/differentiable-blocksworld) has no FFI: its render hot path is a Python-level seam,
+ *     Renderer.forward(meshes, R, T, viz_purpose=False, **kwargs) -> (B,4,H,W)      src/model/renderer.py:84-98
+ * behind which PyTorch3D's MeshRasterizer (_C.rasterize_meshes / _C.rasterize_meshes_backward) and the
+ * reference's LayeredShader + layered_rgb_blend (src/model/renderer.py:219-273) run.  This header is what a
+ * binding for that seam loads instead: plain pointers and sizes, no torch types.  Each entry point cites the
+ * reference interface it replaces.  INTEGRATION.md shows the ctypes stub on the reference side.
+ *
+ * Conventions
+ *  - every pointer except `settings` is a DEVICE pointer on the current CUDA device (the *_host entry points
+ *    take HOST pointers and do the copies themselves);
+ *  - the caller owns every buffer; the library never allocates or frees device memory (the *_host entry
+ *    points keep one grow-only per-process scratch arena, released by dbw_host_arena_release());
+ *  - all work is ordered on `stream` (a cudaStream_t passed as void*); no implicit synchronisation;
+ *  - gradient outputs ACCUMULATE (atomics): the caller zero-fills them;
+ *  - return value 0 = success, negative = error (message via dbw_last_error(), thread-local); never throws;
+ *  - dtype is float32 throughout; ids are int32.
+ */
+#ifndef DBW_RENDER_H
+#define DBW_RENDER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBW_ABI_VERSION 1
+#define DBW_MAX_FACES_PER_PIXEL 64
+
+/*
+ * Mirrors RasterizationSettings + BlendParams + the LayeredShader flags the reference configures at
+ * src/model/renderer.py:29-54 and the camera it installs at src/model/dbw.py:204-208.
+ */
+typedef struct DbwRenderSettings {
+  int32_t n_views;            /* B: cameras / images in this call (Meshes.extend(B), src/model/dbw.py:215,220)      */
+  int32_t height, width;      /* img_size (H, W)                                                                    */
+  int32_t faces_per_pixel;    /* K  (renderer.py:33)                                                                */
+  int32_t n_verts, n_faces;   /* V, F of the (single) scene mesh shared by all views                                 */
+  int32_t n_maps;             /* M texture maps (join_meshes_as_scene keeps one per sub-mesh)                        */
+  int32_t alpha_view_stride;  /* faces_alpha layout: 0 = (F,) shared by all views; F = (B*F,) batch-packed (dbw.py:219) */
+  float fx, fy, px, py;       /* PerspectiveCameras K in NDC (src/dataset/dtu.py:102-106): K[0,0], K[1,1], K[0,2], K[1,2] */
+  float sigma;                /* BlendParams.sigma (renderer.py:31); 0 = hard                                        */
+  float blur_radius;          /* log(1/1e-4 - 1) * sigma (renderer.py:51)                                            */
+  float z_clip;               /* z_clip_value (renderer.py:35,46); < 0 disables clipping                             */
+  float proj_eps;             /* eps passed to the cameras (renderer.py:20,94) = 1e-8                                 */
+  float background[3];        /* BlendParams.background_color (renderer.py:32)                                       */
+  int32_t clip_inside;        /* LayeredShader clip_inside (renderer.py:41)                                          */
+  int32_t perspective_correct;/* renderer.py:34,46 (None -> True for perspective cameras)                            */
+  int32_t clip_barycentric;   /* clip_barycentric_coords=True (renderer.py:46)                                       */
+  int32_t detach_bary;        /* LayeredShader detach_bary (renderer.py:43,222-223): no gradient through barycentrics */
+  int32_t verts_are_ndc;      /* 1: `verts` is (B,V,3) = (x_ndc, y_ndc, z_view) and R/T/K are ignored                 */
+} DbwRenderSettings;
+
+/* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */
+typedef struct DbwMapDesc { int32_t offset, height, width, reserved; } DbwMapDesc;
+
+int dbw_abi_version(void);
+const char* dbw_last_error(void);
+
+/* Bytes of the two caller-provided device scratch buffers:
+ *   *fwd_bytes: workspace written by dbw_render_forward and read again by dbw_render_backward (keep it alive);
+ *   *bwd_bytes: scratch used only inside dbw_render_backward. */
+int dbw_workspace_bytes(const DbwRenderSettings* settings, size_t* fwd_bytes, size_t* bwd_bytes);
+
+/*
+ * Forward of Renderer.forward (src/model/renderer.py:84-98): projection -> z-clip -> rasterize (top-K nearest
+ * faces per pixel within the blur halo) -> UV interpolation + bilinear texture fetch -> layered soft blend.
+ *   verts        (V,3) world-space vertices   [or (B,V,3) NDC when settings->verts_are_ndc]
+ *   faces        (F,3) int32 vertex ids
+ *   faces_uvs    (F,3,2) per-face-vertex UVs = verts_uvs[faces_uvs] of TexturesUV (src/model/dbw.py:280,295,342)
+ *   face_map     (F) int32 texture map of each face
+ *   maps, map_table  packed maps + (M) DbwMapDesc (device)
+ *   R (B,3,3), T (B,3)  row-vector convention X_view = X_world @ R + T (src/dataset/dtu.py:75-124)
+ *   faces_alpha  NULL, or per-face opacity (src/model/dbw.py:219, renderer.py:258-260), see alpha_view_stride
+ *   out_rgba     (B,4,H,W)  RGB + coverage, NCHW (renderer.py:268)
+ *   topk_ids     (B,K,H,W) int32: z-sorted face slots kept per pixel (-1 = empty); needed by backward
+ */
+int dbw_render_forward(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                       const float* faces_uvs, const int32_t* face_map, const float* maps,
+                       const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                       float* out_rgba, int32_t* topk_ids, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Backward of the same (replaces autograd through layered_rgb_blend, grid_sample, interpolate_face_attributes
+ * and _C.rasterize_meshes_backward).  grad_rgba (B,4,H,W).  Outputs accumulate:
+ *   g_verts        (V,3)  [or (B,V,3) when verts_are_ndc]
+ *   g_faces_alpha  same shape as faces_alpha (may be NULL when faces_alpha is NULL)
+ *   g_maps         same packing as maps (may be NULL: no texture gradient)
+ */
+int dbw_render_backward(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                        const float* faces_uvs, const int32_t* face_map, const float* maps,
+                        const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                        const int32_t* topk_ids, const void* workspace, size_t workspace_bytes,
+                        const float* grad_rgba, float* g_verts, float* g_faces_alpha, float* g_maps,
+                        void* bwd_scratch, size_t bwd_scratch_bytes, void* stream);
+
+/*
+ * Fused compositing + RGB loss of the decoupled scene (src/model/dbw.py:223 and :366-367):
+ *   rec = rgb_fg * a_fg + (1 - a_fg) * rgb_env ;  loss = weight * mean((imgs - rec)^2)
+ * fg, env: (B,4,H,W) outputs of dbw_render_forward; imgs (B,3,H,W).  Writes rec (B,3,H,W) (may be NULL), adds
+ * the loss into *loss_sum (device scalar, caller zero-fills), and -- when g_fg / g_env are not NULL -- writes the
+ * gradients of `loss` w.r.t. fg and env ((B,4,H,W), overwritten).  `inv_count` = weight / (B_total*3*H*W).
+ */
+int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
+                      const float* imgs, float inv_count, float* rec, float* loss_sum, float* g_fg, float* g_env,
+                      void* stream);
+
+/*
+ * Host-buffer variants (the end-to-end call a reference-side binding makes with numpy / CPU tensors): every
+ * pointer is a HOST pointer; the library stages through its own device arena on the current device, runs the
+ * device entry points above on `stream`, copies results back and synchronises the stream before returning.
+ */
+int dbw_render_forward_host(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                            const float* faces_uvs, const int32_t* face_map, const float* maps, size_t maps_floats,
+                            const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                            float* out_rgba, void* stream);
+void dbw_host_arena_release(void);
+
+/* Number of kernel launches issued by this library since process start (for bench.py's gpu_launches). */
+uint64_t dbw_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBW_RENDER_H */

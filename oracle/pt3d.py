@@ -103,7 +103,7 @@ def clip_faces(face_verts, mesh_first, mesh_nfaces, z_clip, perspective_correct)
     n_behind = behind.sum(1)
     if int(n_behind.sum()) == 0:
         return SimpleNamespace(face_verts=face_verts, mesh_first=mesh_first, mesh_nfaces=mesh_nfaces,
-                               to_unclipped=None, conversion=None, neighbor=None)
+                               to_unclipped=None, conversion=None, neighbor=None, u2c=None)
     case1 = n_behind == 0            # untouched
     case2 = n_behind == 3            # culled
     case3 = n_behind == 2            # -> one smaller triangle
@@ -149,7 +149,7 @@ def clip_faces(face_verts, mesh_first, mesh_nfaces, z_clip, perspective_correct)
         fv_c = fv_c.index_put((order,), torch.cat(pieces_v))
         conv = conv.index_put((order,), torch.cat(pieces_c))
     return SimpleNamespace(face_verts=fv_c, mesh_first=new_first, mesh_nfaces=new_nfaces,
-                           to_unclipped=c2u, conversion=conv, neighbor=neighbor)
+                           to_unclipped=c2u, conversion=conv, neighbor=neighbor, u2c=u2c)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -200,12 +200,13 @@ def rasterize_meshes(verts_ndc, faces, image_size, blur_radius=0.0, faces_per_pi
     mesh_first = torch.arange(N, dtype=torch.long) * Fn
     mesh_nfaces = torch.full((N,), Fn, dtype=torch.long)
     clipped = SimpleNamespace(face_verts=face_verts, mesh_first=mesh_first, mesh_nfaces=mesh_nfaces,
-                              to_unclipped=None, conversion=None, neighbor=None)
+                              to_unclipped=None, conversion=None, neighbor=None, u2c=None)
     if z_clip_value is not None:
         clipped = clip_faces(face_verts, mesh_first, mesh_nfaces, z_clip_value, perspective_correct)
     p2f, zbuf, bary, dists = _RasterizeFaceVerts.apply(
         clipped.face_verts, clipped.mesh_first, clipped.mesh_nfaces, clipped.neighbor, tuple(image_size),
         float(blur_radius), int(faces_per_pixel), perspective_correct, clip_barycentric_coords, cull_backfaces)
+    clipped_idx = p2f            # face index in the CLIPPED face list (test diagnostics: which half of a split quad)
     if clipped.to_unclipped is not None:
         # convert_clipped_rasterization_to_original_faces
         valid = p2f >= 0
@@ -214,7 +215,8 @@ def rasterize_meshes(verts_ndc, faces, image_size, blur_radius=0.0, faces_per_pi
         bary_u = (bary[..., :, None] * conv).sum(-2)                       # row-vector times matrix
         bary = torch.where(valid[..., None], bary_u, bary)
         p2f = torch.where(valid, clipped.to_unclipped[idx], p2f)
-    return SimpleNamespace(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists)
+    return SimpleNamespace(pix_to_face=p2f, zbuf=zbuf, bary_coords=bary, dists=dists, clipped_idx=clipped_idx,
+                           unclipped_to_clipped=clipped.u2c)
 
 
 # --------------------------------------------------------------------------------------------------------------

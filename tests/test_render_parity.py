@@ -1,0 +1,177 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): rendered RGB / silhouette within 1e-4 abs, gradients within 1e-3 rel.
+Gradients are compared with the float64 oracle (the reference's own fp32 cumprod backward is
+noisy where 1 - alpha is tiny), as relative L2 error per tensor plus an element-wise bound scaled by the tensor's
+max magnitude."""
+import pytest
+import torch
+
+from oracle import dbw_path as D
+from tests.helpers import scene_to_device, render_product, split_map_grads, decision_mask
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+GRAD_REL = 1e-3
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _check_image(out, ref, max_bad_frac=0.0):
+    err = (out - ref).abs()
+    bad = (err > IMG_TOL).float().mean().item()
+    assert bad <= max_bad_frac, f'max err {err.max().item():.3e}, {bad * 100:.4f}% of values above {IMG_TOL}'
+
+
+def _setup(n_blocks=4, txt=32, n_views=2, seed=3, boxy=False, dtype=torch.float32, dist=2.75):
+    tpl = D.SceneTemplate(n_blocks=n_blocks, txt_size=txt)
+    p = D.init_params(n_blocks, txt, seed=seed, boxy=boxy, dtype=dtype)
+    R, T, K = D.ring_cameras(n_views, dtype=dtype, jitter=0.3, seed=seed, dist=dist)
+    return tpl, p, R, T, K
+
+
+@pytest.mark.parametrize('size', [(64, 64), (48, 80), (70, 50)])
+@pytest.mark.parametrize('mode', ['coarse', 'fine', 'sigmoid'])
+def test_blocks_forward(size, mode):
+    dev = _dev()
+    tpl, p, R, T, K = _setup(boxy=(mode == 'fine'))
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF) if mode != 'fine' else None
+    sigma = {'coarse': 1e-4, 'fine': 5e-6, 'sigmoid': 1e-4}[mode]
+    clip_inside = mode != 'sigmoid'
+    ref = D.render(blocks, R, T, K, size, sigma=sigma, faces_per_pixel=10, z_clip=0.001, detach_bary=True,
+                   faces_alpha=fa, clip_inside=clip_inside, background=(0.1, 0.2, 0.3))
+    sc = scene_to_device(blocks, dev)
+    out = render_product(sc, R.to(dev), T.to(dev), K, size, sigma, 10, z_clip=0.001, detach_bary=True,
+                         faces_alpha=None if fa is None else fa.to(dev), clip_inside=clip_inside,
+                         background=(0.1, 0.2, 0.3))
+    _check_image(out.cpu(), ref)
+
+
+@pytest.mark.parametrize('K_', [1, 3, 10, 25, 40])
+def test_blocks_forward_faces_per_pixel(K_):
+    dev = _dev()
+    tpl, p, R, T, K = _setup(n_blocks=6)
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF).repeat(R.shape[0])          # batch-packed (B*F,) as dbw.py:219
+    ref = D.render(blocks, R, T, K, (64, 64), sigma=1e-4, faces_per_pixel=K_, z_clip=0.001, detach_bary=True, faces_alpha=fa)
+    sc = scene_to_device(blocks, dev)
+    out = render_product(sc, R.to(dev), T.to(dev), K, (64, 64), 1e-4, K_, z_clip=0.001, detach_bary=True, faces_alpha=fa.to(dev))
+    _check_image(out.cpu(), ref)
+
+
+def test_topk_ids_match_oracle():
+    """bit-exact integer parity: the per-pixel z-sorted face ids equal the oracle's pix_to_face."""
+    dev = _dev()
+    tpl, p, R, T, K = _setup(n_blocks=5)
+    blocks, alpha = tpl.build_blocks(p)
+    _, frags = D.render(blocks, R, T, K, (64, 64), sigma=1e-4, faces_per_pixel=10, z_clip=0.001, return_fragments=True)
+    sc = scene_to_device(blocks, dev)
+    _, ids = render_product(sc, R.to(dev), T.to(dev), K, (64, 64), 1e-4, 10, z_clip=0.001, return_ids=True)
+    Fn = blocks['faces'].shape[0]
+    ref_ids = torch.where(frags.pix_to_face >= 0, frags.pix_to_face % Fn, frags.pix_to_face).permute(0, 3, 1, 2)
+    mism = (ids.cpu().long() != ref_ids).float().mean().item()
+    assert mism <= 1e-4, f'{mism * 100:.4f}% of top-K ids differ'
+
+
+def _grad_parity(scene, R, T, K, size, sigma, Kf, z_clip, detach, fa, clip_inside, seed, max_ambiguous=2e-3):
+    """forward+backward of the CUDA path vs the FLOAT64 oracle.  A few pixels take a different discrete decision in
+    fp32 than in fp64 (inside test / halo cut-off / K-th face / which half of a z-clipped quad); they are identified by
+    comparing the kept face ids, excluded from the loss on BOTH sides, counted and bounded -- everything else must
+    agree to 1e-4 (image) and 1e-3 relative (gradients)."""
+    dev = _dev()
+    B = R.shape[0]
+    ref, frags = D.render(scene, R, T, K, size, sigma=sigma, faces_per_pixel=Kf, z_clip=z_clip, detach_bary=detach,
+                          faces_alpha=fa, clip_inside=clip_inside, return_fragments=True)
+    sc = scene_to_device(scene, dev, requires_grad=True)
+    fa_d = None if fa is None else fa.detach().float().to(dev).requires_grad_(True)
+    out, ids = render_product(sc, R.to(dev), T.to(dev), K, size, sigma, Kf, z_clip=z_clip, detach_bary=detach,
+                              faces_alpha=fa_d, clip_inside=clip_inside, return_ids=True)
+    mask = decision_mask(ids, frags, scene['faces'].shape[0])
+    ambiguous = 1 - mask.mean().item()
+    assert ambiguous <= max_ambiguous, f'{ambiguous * 100:.3f}% of pixels take a different discrete decision'
+    _check_image(out.detach().cpu().double() * mask, ref.detach() * mask)
+    gen = torch.Generator().manual_seed(seed)
+    wgt = torch.rand(B, 4, *size, generator=gen, dtype=torch.float64) * mask
+    scene['verts'].retain_grad()
+    for m in scene['maps']:
+        m.retain_grad()
+    if fa is not None:
+        fa.retain_grad()
+    (ref * wgt).sum().backward()
+    (out * wgt.to(dev).float()).sum().backward()
+    gv, gv_ref = sc['verts'].grad.cpu().double(), scene['verts'].grad
+    assert _rel(gv, gv_ref) < GRAD_REL, f'verts grad rel err {_rel(gv, gv_ref):.3e}'
+    assert (gv - gv_ref).abs().max() <= 2e-3 * gv_ref.abs().max()
+    for g, m in zip(split_map_grads(sc['maps'].grad.cpu().double(), sc['table']), scene['maps']):
+        if m.grad is None:
+            assert g.abs().max() == 0
+        else:
+            assert _rel(g, m.grad) < GRAD_REL, f'map grad rel err {_rel(g, m.grad):.3e}'
+    if fa is not None:
+        assert _rel(fa_d.grad.cpu().double(), fa.grad) < GRAD_REL, f'faces_alpha grad rel err {_rel(fa_d.grad.cpu().double(), fa.grad):.3e}'
+    return ambiguous
+
+
+def test_env_forward_backward():
+    """sigma = 0, K = 1, gradient through barycentrics to the ground pose and both env textures (dbw.py:135-138)."""
+    tpl, p, R, T, K = _setup(dtype=torch.float64)
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    env = tpl.build_env(p)
+    _grad_parity(env, R, T, K, (64, 64), 0.0, 1, 0.001, False, None, True, seed=0)
+
+
+@pytest.mark.parametrize('mode', ['coarse', 'fine', 'sigmoid', 'bary'])
+def test_blocks_backward(mode):
+    tpl, p, R, T, K = _setup(n_blocks=4, dtype=torch.float64, boxy=(mode == 'fine'))
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF) if mode != 'fine' else None
+    sigma = 5e-6 if mode == 'fine' else 1e-4
+    _grad_parity(blocks, R, T, K, (64, 64), sigma, 10, 0.001, mode != 'bary', fa, mode != 'sigmoid', seed=1)
+
+
+def test_blocks_backward_batch_packed_alpha():
+    """faces_alpha of length B*F exactly as the reference builds it (dbw.py:219)."""
+    tpl, p, R, T, K = _setup(n_blocks=3, dtype=torch.float64, n_views=3)
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF).repeat(3)
+    _grad_parity(blocks, R, T, K, (40, 56), 1e-4, 10, 0.001, True, fa, True, seed=4)
+
+
+def test_z_clipped_faces_forward_backward():
+    """camera inside the geometry so that faces straddle z = z_clip and are split: forward parity and the
+    gradient through the clipped vertices / barycentric conversion.  Pixels in the Voronoi cell of a vertex shared by
+    the two halves of a split quad have mathematically tied distances to both halves, so which half is kept is decided
+    by rounding (in PyTorch3D too): those are the 'ambiguous' pixels here."""
+    tpl, p, R, T, K = _setup(n_blocks=3, dtype=torch.float64, dist=0.45, n_views=3)
+    K = K.clone(); K[0, 0] = K[1, 1] = 1.2            # wide field of view so that clipped faces are visible
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    blocks, alpha = tpl.build_blocks(p)
+    env = tpl.build_env(p)
+    scene = D.join_scenes([env, blocks])
+    amb = _grad_parity(scene, R, T, K, (48, 48), 1e-4, 8, 0.05, False, None, True, seed=2, max_ambiguous=1e-2)
+    print(f'ambiguous pixels: {amb * 100:.3f}%')
+
+
+def test_verts_are_ndc_entry():
+    """the kernel's differentiable input can be NDC vertices directly (SURVEY 8b recommended split)."""
+    dev = _dev()
+    tpl, p, R, T, K = _setup()
+    blocks, alpha = tpl.build_blocks(p)
+    from oracle import pt3d
+    ndc = pt3d.world_to_ndc(blocks['verts'], R, T, K)
+    ref = D.render(blocks, R, T, K, (64, 64), sigma=1e-4, faces_per_pixel=10, z_clip=0.001)
+    sc = scene_to_device(blocks, dev)
+    sc['verts'] = ndc.to(dev).contiguous()
+    out = render_product(sc, None, None, K, (64, 64), 1e-4, 10, z_clip=0.001, verts_are_ndc=True)
+    _check_image(out.cpu(), ref)
