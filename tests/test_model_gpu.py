@@ -1,0 +1,95 @@
+"""GPU parity of the scene model (DifferentiableBlocksWorld drop-in) against the oracle's restatement of
+src/model/dbw.py: predict(), the RGB loss and its gradients down to the leaf parameters."""
+import pytest
+import torch
+
+from oracle import dbw_path as D
+
+pytestmark = pytest.mark.gpu
+
+CFG = {
+    'mesh': {'n_blocks': 5, 'S_world': 0.5, 'R_world': [115, 0, 0], 'txt_size': 32},
+    'renderer': {'faces_per_pixel': 10, 'cameras': {'name': 'perspective'}, 'detach_bary': True, 'z_clip': 0.001},
+    'rend_optim': {'coarse_learning': 1500, 'decimate_txt': 750, 'decimate_factor': 8, 'kill_blocks': True,
+                   'decouple_rendering': True, 'opacity_noise': False},
+    'loss': {'rgb_weight': 1, 'parsimony_weight': 0.01, 'tv_weight': 0.1, 'overlap_weight': 1},
+}
+
+
+def _model_and_oracle(dtype=torch.float64, fine=False, seed=5):
+    import dbw_b200
+    from dbw_b200.dbw import DifferentiableBlocksWorld
+    from copy import deepcopy
+    torch.manual_seed(seed)
+    dev = torch.device('cuda:0')
+    model = DifferentiableBlocksWorld((48, 64), **deepcopy(CFG)).to(dev)
+    model.train()
+    if fine:
+        model.set_cur_epoch(2000)
+        with torch.no_grad():
+            model.alpha_logit.copy_(torch.tensor([2., -2., 1., 3., -1.]))
+    tpl = D.SceneTemplate(n_blocks=5, txt_size=32)
+    p = {k: v.detach().cpu().to(dtype).clone().requires_grad_(True) for k, v in model.named_parameters()}
+    return model, tpl, p, dev
+
+
+def _inputs(dev, B=3, size=(48, 64), dtype=torch.float64, seed=7):
+    R, T, K = D.ring_cameras(B, dtype=dtype, jitter=0.3, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.rand(B, 3, *size, generator=g, dtype=dtype)
+    inp = {'imgs': imgs.float().to(dev), 'R': R.float().to(dev), 'T': T.float().to(dev), 'K': K.float()[None].expand(B, -1, -1).to(dev)}
+    return inp, imgs, R, T, K
+
+
+def test_buffers_match_oracle_template():
+    model, tpl, p, dev = _model_and_oracle()
+    assert torch.equal(model.sq_eta.cpu(), tpl.sq_eta) and torch.equal(model.sq_omega.cpu(), tpl.sq_omega)
+    assert torch.equal(model.block_faces_uvs.cpu(), tpl.block_faces_uvs)
+    assert torch.allclose(model.block_verts_uvs.cpu(), tpl.block_verts_uvs, atol=0)
+    assert torch.allclose(model.R_world.cpu(), tpl.R_world, atol=1e-7)
+    assert torch.equal(model.bkg_verts_uvs.cpu(), tpl.bkg_verts_uvs) and torch.equal(model.ground_verts_uvs.cpu(), tpl.ground_verts_uvs)
+    assert model.txt_padding == tpl.txt_padding and model.BNF == tpl.BNF
+
+
+@pytest.mark.parametrize('fine', [False, True])
+def test_predict_and_rgb_gradients(fine):
+    model, tpl, p, dev = _model_and_oracle(fine=fine)
+    inp, imgs, R, T, K = _inputs(dev)
+    decim = 8 if not fine else 0                          # decimate_txt is live below epoch 750 in training mode
+    keep = None
+    if fine:
+        keep = torch.sigmoid(p['alpha_logit'].detach()) > 0.5
+    elif CFG['rend_optim']['kill_blocks']:
+        keep = torch.sigmoid(p['alpha_logit'].detach()) > 0.01
+    sigma = 5e-6 if fine else 1e-4
+    rec_ref = D.predict(tpl, p, R, T, K, (48, 64), sigma=sigma, faces_per_pixel=10, z_clip=0.001, fine=fine, keep=keep,
+                        decimate=decim)
+    rec = model.predict(inp)
+    err = (rec.detach().cpu().double() - rec_ref.detach()).abs()
+    assert (err > 1e-4).float().mean().item() < 1e-3, f'max err {err.max().item():.3e}'
+    # loss + gradients: only the rgb term (the regularisers are plain torch on parameters)
+    model.loss_weights = {'rgb': 1.0}
+    losses = model(inp, None)
+    loss_ref = D.mse_loss(imgs, rec_ref)
+    assert abs(losses['rgb'].item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    losses['total'].backward()
+    loss_ref.backward()
+    for name, prm in model.named_parameters():
+        g_ref = p[name].grad
+        g = prm.grad
+        if g_ref is None or g_ref.abs().max() == 0:
+            assert g is None or g.abs().max().item() < 1e-12, name
+            continue
+        rel = ((g.cpu().double() - g_ref).norm() / g_ref.norm()).item()
+        # a few pixels take a different discrete decision in fp32 than in the fp64 oracle (see test_render_parity)
+        assert rel < 2e-2, f'{name}: rel grad err {rel:.3e}'
+
+
+def test_full_loss_dict_runs_and_is_finite():
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    losses = model(inp, None)
+    assert set(losses) == {'rgb', 'parsimony', 'tv', 'overlap', 'total'}
+    losses['total'].backward()
+    for n, prm in model.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), n
