@@ -28,7 +28,8 @@ class DbwMapDesc(ctypes.Structure):
 
 
 EXPORTS = ['dbw_abi_version', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_backward',
-           'dbw_composite_mse', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count']
+           'dbw_composite_mse', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
+           'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset']
 
 _lib = None
 
@@ -54,6 +55,9 @@ def lib():
         L.dbw_composite_mse.argtypes = [ctypes.c_int32] * 3 + [vp] * 3 + [ctypes.c_float] + [vp] * 5
         L.dbw_render_forward_host.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 5 + [sz] + [vp] * 6
         L.dbw_host_arena_release.restype = None
+        L.dbw_timing_enable.restype = None
+        L.dbw_timing_reset.restype = None
+        L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
         if L.dbw_abi_version() != ABI_VERSION:
             raise DbwError(f'ABI mismatch: library {L.dbw_abi_version()} != binding {ABI_VERSION}')
         _lib = L
@@ -67,3 +71,10 @@ def check(rc, what):
 
 def launch_count():
     return int(lib().dbw_launch_count())
+
+
+def kernel_time_ms(kind, K=0):
+    """(total ms, launches) of the raster kernel `kind` (0 forward, 1 backward) recorded since the last reset."""
+    tot, n = ctypes.c_double(0), ctypes.c_int(0)
+    check(lib().dbw_timing_read(kind, K, ctypes.byref(tot), ctypes.byref(n)), 'dbw_timing_read')
+    return tot.value, n.value

@@ -32,13 +32,17 @@ struct TriGeom {
   int face;      // original face id
   int neighbor;  // slot of the other half of a z-clipped quad, or -1
   int flags;     // bit0: clipped (barycentric conversion matrix present)
+  float inv_area;            // 1 / (edge(v2; v0, v1) + kEpsilon)
+  float il01, il02, il12;    // 1 / |b - a|^2 of the three edges, or -1 when |b - a|^2 <= kEpsilon (degenerate)
 };
 
-__device__ __forceinline__ TriGeom unpack_tri(float4 r0, float4 r1, float4 r2) {
+// record = 4 x float4: [v0xy v1xy] [v2xy z0 z1] [z2 face neighbor flags] [inv_area il01 il02 il12]
+__device__ __forceinline__ TriGeom unpack_tri(float4 r0, float4 r1, float4 r2, float4 r3) {
   TriGeom t;
   t.v0 = {r0.x, r0.y}; t.v1 = {r0.z, r0.w}; t.v2 = {r1.x, r1.y};
   t.z0 = r1.z; t.z1 = r1.w; t.z2 = r2.x;
   t.face = __float_as_int(r2.y); t.neighbor = __float_as_int(r2.z); t.flags = __float_as_int(r2.w);
+  t.inv_area = r3.x; t.il01 = r3.y; t.il02 = r3.z; t.il12 = r3.w;
   return t;
 }
 
@@ -50,46 +54,64 @@ struct Bary {
   float pz;
 };
 
+// The three edge functions (exact, non-contracted) and the inside test.  inside <=> every barycentric > 0
+// <=> every edge function has the sign of the (eps-shifted) area; this is the DISCRETE decision and is bit-identical
+// to the IEEE evaluation of SURVEY A4 (z > 0 after clipping, so perspective correction keeps the signs).
+struct Edges { float e0, e1, e2; bool inside; };
+__device__ __forceinline__ Edges eval_edges(f2 p, const TriGeom& t) {
+  Edges e;
+  e.e0 = edge_nc(p, t.v1, t.v2); e.e1 = edge_nc(p, t.v2, t.v0); e.e2 = edge_nc(p, t.v0, t.v1);
+  const float s = t.inv_area;
+  e.inside = (e.e0 * s > 0.f) && (e.e1 * s > 0.f) && (e.e2 * s > 0.f);
+  return e;
+}
+
 __device__ __forceinline__ f3 persp_forward(f3 b, float z0, float z1, float z2) {
   const float t0 = b.x * z1 * z2, t1 = z0 * b.y * z2, t2 = z0 * z1 * b.z;
-  const float denom = fmaxf(t0 + t1 + t2, DBW_KEPS);
-  return {t0 / denom, t1 / denom, t2 / denom};
+  const float inv = 1.f / fmaxf(t0 + t1 + t2, DBW_KEPS);
+  return {t0 * inv, t1 * inv, t2 * inv};
 }
 
 __device__ __forceinline__ f3 clip_forward(f3 b) {
   f3 w = {fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f)};
-  const float s = fmaxf(w.x + w.y + w.z, 1e-5f);
-  return {w.x / s, w.y / s, w.z / s};
+  const float sum = fmaxf(w.x + w.y + w.z, 1e-5f);
+  const float inv = 1.f / sum;
+  // Beyond a vertex two barycentrics are negative, the third is renormalised to EXACTLY 1 by a true division, and
+  // every face sharing that vertex then ties at pz = z_vertex (broken by face index).  w * (1/w) is not
+  // always 1, so keep that case exact; elsewhere one reciprocal replaces three divisions.
+  return {w.x == sum ? 1.f : w.x * inv, w.y == sum ? 1.f : w.y * inv, w.z == sum ? 1.f : w.z * inv};
 }
 
-__device__ __forceinline__ Bary eval_bary(f2 p, const TriGeom& t, bool persp, bool clipb) {
+// continuous part: barycentrics (one reciprocal per normalisation instead of three IEEE divisions) and depth
+__device__ __forceinline__ Bary bary_from_edges(const Edges& e, const TriGeom& t, bool persp, bool clipb) {
   Bary r;
-  const float area = __fadd_rn(edge_nc(t.v2, t.v0, t.v1), DBW_KEPS);
-  r.b0 = {edge_nc(p, t.v1, t.v2) / area, edge_nc(p, t.v2, t.v0) / area, edge_nc(p, t.v0, t.v1) / area};
+  r.b0 = {e.e0 * t.inv_area, e.e1 * t.inv_area, e.e2 * t.inv_area};
   r.bp = persp ? persp_forward(r.b0, t.z0, t.z1, t.z2) : r.b0;
-  r.inside = r.bp.x > 0.f && r.bp.y > 0.f && r.bp.z > 0.f;
+  r.inside = e.inside;
   r.bc = clipb ? clip_forward(r.bp) : r.bp;
   r.pz = r.bc.x * t.z0 + r.bc.y * t.z1 + r.bc.z * t.z2;
   return r;
 }
 
-// squared distance from p to the segment a-b; also returns the clamped parameter t and whether the degenerate
-// (|ba|^2 <= eps) branch was taken
-__device__ __forceinline__ float seg_dist2(f2 p, f2 a, f2 b) {
+__device__ __forceinline__ Bary eval_bary(f2 p, const TriGeom& t, bool persp, bool clipb) {
+  return bary_from_edges(eval_edges(p, t), t, persp, clipb);
+}
+
+// squared distance from p to the segment a-b, il = 1/|b-a|^2 (or -1: degenerate -> distance to b)
+__device__ __forceinline__ float seg_dist2(f2 p, f2 a, f2 b, float il) {
   const float bax = b.x - a.x, bay = b.y - a.y;
-  const float l2 = bax * bax + bay * bay;
-  if (l2 <= DBW_KEPS) {
+  if (il < 0.f) {
     const float dx = p.x - b.x, dy = p.y - b.y;
     return dx * dx + dy * dy;
   }
-  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) / l2;
+  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) * il;
   tt = fminf(fmaxf(tt, 0.f), 1.f);
   const float dx = a.x + tt * bax - p.x, dy = a.y + tt * bay - p.y;
   return dx * dx + dy * dy;
 }
 
 __device__ __forceinline__ float tri_dist2(f2 p, const TriGeom& t) {
-  const float e01 = seg_dist2(p, t.v0, t.v1), e02 = seg_dist2(p, t.v0, t.v2), e12 = seg_dist2(p, t.v1, t.v2);
+  const float e01 = seg_dist2(p, t.v0, t.v1, t.il01), e02 = seg_dist2(p, t.v0, t.v2, t.il02), e12 = seg_dist2(p, t.v1, t.v2, t.il12);
   return fminf(fminf(e01, e02), e12);
 }
 
@@ -101,9 +123,8 @@ __device__ __forceinline__ void edge_backward(f2 p, f2 a, f2 b, float g, f2& ga,
 }
 
 __device__ __forceinline__ void bary_backward(f2 p, const TriGeom& t, f3 g, f2& g0, f2& g1, f2& g2) {
-  const float area = __fadd_rn(edge_nc(t.v2, t.v0, t.v1), DBW_KEPS);
   const float e0 = edge_nc(p, t.v1, t.v2), e1 = edge_nc(p, t.v2, t.v0), e2 = edge_nc(p, t.v0, t.v1);
-  const float inv = 1.f / area;
+  const float inv = t.inv_area;
   const float garea = -(g.x * e0 + g.y * e1 + g.z * e2) * inv * inv;
   edge_backward(p, t.v1, t.v2, g.x * inv, g1, g2);
   edge_backward(p, t.v2, t.v0, g.y * inv, g2, g0);
@@ -137,14 +158,13 @@ __device__ __forceinline__ f3 clip_backward(f3 b, f3 g) {
 }
 
 // gradient of seg_dist2 w.r.t. a and b (the closest point's parameter is treated as a constant)
-__device__ __forceinline__ void seg_backward(f2 p, f2 a, f2 b, float g, f2& ga, f2& gb) {
+__device__ __forceinline__ void seg_backward(f2 p, f2 a, f2 b, float il, float g, f2& ga, f2& gb) {
   const float bax = b.x - a.x, bay = b.y - a.y;
-  const float l2 = bax * bax + bay * bay;
-  if (l2 <= DBW_KEPS) {
+  if (il < 0.f) {
     gb.x += g * 2.f * (b.x - p.x); gb.y += g * 2.f * (b.y - p.y);
     return;
   }
-  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) / l2;
+  float tt = (bax * (p.x - a.x) + bay * (p.y - a.y)) * il;
   tt = fminf(fmaxf(tt, 0.f), 1.f);
   const float dx = a.x + tt * bax - p.x, dy = a.y + tt * bay - p.y;
   ga.x += g * (1.f - tt) * 2.f * dx; ga.y += g * (1.f - tt) * 2.f * dy;
@@ -152,10 +172,10 @@ __device__ __forceinline__ void seg_backward(f2 p, f2 a, f2 b, float g, f2& ga, 
 }
 
 __device__ __forceinline__ void tri_dist_backward(f2 p, const TriGeom& t, float g, f2& g0, f2& g1, f2& g2) {
-  const float e01 = seg_dist2(p, t.v0, t.v1), e02 = seg_dist2(p, t.v0, t.v2), e12 = seg_dist2(p, t.v1, t.v2);
-  if (e01 <= e02 && e01 <= e12) seg_backward(p, t.v0, t.v1, g, g0, g1);
-  else if (e02 <= e01 && e02 <= e12) seg_backward(p, t.v0, t.v2, g, g0, g2);
-  else seg_backward(p, t.v1, t.v2, g, g1, g2);
+  const float e01 = seg_dist2(p, t.v0, t.v1, t.il01), e02 = seg_dist2(p, t.v0, t.v2, t.il02), e12 = seg_dist2(p, t.v1, t.v2, t.il12);
+  if (e01 <= e02 && e01 <= e12) seg_backward(p, t.v0, t.v1, t.il01, g, g0, g1);
+  else if (e02 <= e01 && e02 <= e12) seg_backward(p, t.v0, t.v2, t.il02, g, g0, g2);
+  else seg_backward(p, t.v1, t.v2, t.il12, g, g1, g2);
 }
 
 // ------------------------------------------------------------------ texture fetch

@@ -10,7 +10,7 @@
 // Layout in HBM (all fp32 / int32):
 //   verts_ndc  (B,V,3)            projected vertices (x_ndc, y_ndc, z_view)
 //   bbox       (B,2F) float4      blur-expanded NDC bbox of each face slot (xmin,xmax,ymin,ymax); xmin=+inf: empty
-//   rec        (B,2F,3) float4    v0xy v1xy | v2xy z0 z1 | z2 face neighbor flags
+//   rec        (B,2F,4) float4    v0xy v1xy | v2xy z0 z1 | z2 face neighbor flags | 1/area, 1/|e01|^2, 1/|e02|^2, 1/|e12|^2
 //   conv       (B,2F,9)           barycentric conversion (clipped -> original face), only for clipped slots
 //   slots [0,F) hold each face's (first) triangle, slots [F,2F) the second triangle of a z-clipped quad.
 //   out_rgba   (B,4,H,W), topk_ids (B,K,H,W) planar so that every warp store is a run of full 32 B sectors.
@@ -41,6 +41,37 @@ extern "C" uint64_t dbw_launch_count(void) { return g_launches; }
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+// ------------------------------------------------------------------------------------------------ optional per-kernel timing
+// CUDA events recorded on the launch stream around the two raster kernels (bench.py's live roofline measurement).
+#include <vector>
+struct TimedLaunch { int kind, K; cudaEvent_t a, b; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+struct ScopedTimer {
+  cudaStream_t st; bool on; TimedLaunch t;
+  ScopedTimer(int kind, int K, cudaStream_t s) : st(s), on(g_timing) {
+    if (!on) return;
+    t.kind = kind; t.K = K; cudaEventCreate(&t.a); cudaEventCreate(&t.b); cudaEventRecord(t.a, st);
+  }
+  ~ScopedTimer() { if (on) { cudaEventRecord(t.b, st); g_timed.push_back(t); } }
+};
+extern "C" void dbw_timing_enable(int on) { g_timing = on != 0; }
+extern "C" int dbw_timing_read(int kind, int K, double* total_ms, int* count) {
+  double tot = 0; int n = 0;
+  for (auto& t : g_timed) {
+    if (t.kind != kind || (K > 0 && t.K != K)) continue;
+    if (cudaEventSynchronize(t.b) != cudaSuccess) return fail("dbw_timing_read: event sync failed");
+    float ms = 0.f; cudaEventElapsedTime(&ms, t.a, t.b); tot += ms; ++n;
+  }
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return 0;
+}
+extern "C" void dbw_timing_reset(void) {
+  for (auto& t : g_timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  g_timed.clear();
+}
+
 struct Workspace {
   float* verts_ndc; float4* bbox; float4* rec; float* conv; int* view_flags; size_t total;
 };
@@ -49,7 +80,7 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   const size_t B = s.n_views, V = s.n_verts, S = 2 * (size_t)s.n_faces;
   w.verts_ndc = (float*)(p + off); off += align_up(B * V * 3 * sizeof(float));
   w.bbox = (float4*)(p + off);     off += align_up(B * S * sizeof(float4));
-  w.rec = (float4*)(p + off);      off += align_up(B * S * 3 * sizeof(float4));
+  w.rec = (float4*)(p + off);      off += align_up(B * S * 4 * sizeof(float4));
   w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
   w.total = off; return w;
@@ -206,9 +237,13 @@ __device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float* con
     bb.x = INFINITY; bb.y = -INFINITY; bb.z = INFINITY; bb.w = -INFINITY;
   }
   bbox[slot] = bb;
-  rec[slot * 3 + 0] = make_float4(x0, y0, x1, y1);
-  rec[slot * 3 + 1] = make_float4(x2, y2, z0, z1);
-  rec[slot * 3 + 2] = make_float4(z2, __int_as_float(face), __int_as_float(neighbor), __int_as_float(clipped ? 1 : 0));
+  rec[slot * 4 + 0] = make_float4(x0, y0, x1, y1);
+  rec[slot * 4 + 1] = make_float4(x2, y2, z0, z1);
+  rec[slot * 4 + 2] = make_float4(z2, __int_as_float(face), __int_as_float(neighbor), __int_as_float(clipped ? 1 : 0));
+  const float l01 = (x1 - x0) * (x1 - x0) + (y1 - y0) * (y1 - y0), l02 = (x2 - x0) * (x2 - x0) + (y2 - y0) * (y2 - y0);
+  const float l12 = (x2 - x1) * (x2 - x1) + (y2 - y1) * (y2 - y1);
+  rec[slot * 4 + 3] = make_float4(1.f / __fadd_rn(area, DBW_KEPS), l01 <= DBW_KEPS ? -1.f : 1.f / l01,
+                                  l02 <= DBW_KEPS ? -1.f : 1.f / l02, l12 <= DBW_KEPS ? -1.f : 1.f / l12);
   if (clipped) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) conv[slot * 9 + i] = cv[i];
@@ -274,7 +309,7 @@ struct Shade {
 
 __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
   const size_t gs = (size_t)view * 2 * P.F + slot;
-  s.t = unpack_tri(__ldg(&P.rec[gs * 3]), __ldg(&P.rec[gs * 3 + 1]), __ldg(&P.rec[gs * 3 + 2]));
+  s.t = unpack_tri(__ldg(&P.rec[gs * 4]), __ldg(&P.rec[gs * 4 + 1]), __ldg(&P.rec[gs * 4 + 2]), __ldg(&P.rec[gs * 4 + 3]));
   s.b = eval_bary(p, s.t, P.persp, P.clipb);
   s.bu = s.b.bc;
   if (s.t.flags & 1) {
@@ -299,7 +334,7 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
 template <int K>
 __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterParams P) {
   __shared__ float4 s_bbox[LIST_CAP];
-  __shared__ float4 s_rec[LIST_CAP * 3];
+  __shared__ float4 s_rec[LIST_CAP * 4];
   __shared__ int s_slot[LIST_CAP];
   __shared__ int s_count;
 
@@ -323,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
 
   const int nslots = (P.view_flags[view] & 1) ? 2 * P.F : P.F;
   const float4* bbox = P.bbox + (size_t)view * 2 * P.F;
-  const float4* rec = P.rec + (size_t)view * 2 * P.F * 3;
+  const float4* rec = P.rec + (size_t)view * 2 * P.F * 4;
   const bool dist_inside = (!P.clip_inside && P.sigma > 0.f);
 
   if (tid == 0) s_count = 0;
@@ -352,9 +387,10 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
       // ---- stage the records of the listed faces in shared memory
       for (int j = tid; j < cnt; j += NTHREADS) {
         const int sl = s_slot[j];
-        s_rec[j * 3 + 0] = __ldg(&rec[sl * 3 + 0]);
-        s_rec[j * 3 + 1] = __ldg(&rec[sl * 3 + 1]);
-        s_rec[j * 3 + 2] = __ldg(&rec[sl * 3 + 2]);
+        s_rec[j * 4 + 0] = __ldg(&rec[sl * 4 + 0]);
+        s_rec[j * 4 + 1] = __ldg(&rec[sl * 4 + 1]);
+        s_rec[j * 4 + 2] = __ldg(&rec[sl * 4 + 2]);
+        s_rec[j * 4 + 3] = __ldg(&rec[sl * 4 + 3]);
       }
       __syncthreads();
       // ---- per pixel: test every listed face, keep the K nearest
@@ -362,13 +398,15 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
         for (int j = 0; j < cnt; ++j) {
           const float4 b4 = s_bbox[j];
           if (p.x > b4.y || p.x < b4.x || p.y > b4.w || p.y < b4.z) continue;
-          const TriGeom t = unpack_tri(s_rec[j * 3], s_rec[j * 3 + 1], s_rec[j * 3 + 2]);
-          const Bary b = eval_bary(p, t, P.persp, P.clipb);
-          if (b.pz < 0.f) continue;
+          const TriGeom t = unpack_tri(s_rec[j * 4], s_rec[j * 4 + 1], s_rec[j * 4 + 2], s_rec[j * 4 + 3]);
+          // cheap, exact part first: edge functions -> inside; pixels outside the face and beyond the halo leave here
+          const Edges ed = eval_edges(p, t);
           float dist = 1.f;
-          const bool need_dist = !b.inside || dist_inside || t.neighbor >= 0;
+          const bool need_dist = !ed.inside || dist_inside || t.neighbor >= 0;
           if (need_dist) dist = tri_dist2(p, t);
-          if (!b.inside && dist >= P.blur) continue;
+          if (!ed.inside && dist >= P.blur) continue;
+          const Bary b = bary_from_edges(ed, t, P.persp, P.clipb);
+          if (b.pz < 0.f) continue;
           const float sd = b.inside ? -dist : dist;
           const int slot = s_slot[j];
           if (t.neighbor >= 0) {
@@ -435,129 +473,230 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// Warp-aggregated accumulation: lanes of a warp that hold a contribution for the same key (face slot) are summed with
+// shuffles and ONE lane issues the atomics -- a 16x16 tile typically sees 1-3 distinct faces per layer, so this
+// removes the same-address contention that otherwise serialises the L2 atomic units (every pixel of a big face hitting
+// the same 9 floats).  Must be called by all 32 lanes (key < 0: nothing to add).
+// all N butterflies advance level by level so that the N shuffles of a level are independent (latency overlapped)
+template <int N>
+__device__ __forceinline__ void warp_sum(float (&x)[N]) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] += __shfl_xor_sync(0xffffffffu, x[i], o);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride, int key, const float (&v)[N], int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = (key == lk);
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    if (__popc(grp) <= 2) {              // (almost) alone: plain atomics are cheaper than a reduction
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (v[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, v[i]);
+      }
+    } else {
+      float x[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = mine ? v[i] : 0.f;
+      warp_sum<N>(x);
+      if (lane == leader) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (x[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, x[i]);
+      }
+    }
+    todo &= ~grp;
+  }
+}
+
+// Texture-gradient scatter of one fragment: 4 bilinear taps x RGB.  Under magnification (the environment maps seen
+// through a narrow field of view: hundreds of pixels per texel) whole warps hit the same 2x2 texel footprint, so
+// lanes that share the footprint with >= 8 others are reduced with shuffles first; the rest issue plain atomics.
+// Coherence is probed from the first pending lane only (no match.any): an incoherent warp pays two ballots.
+__device__ __forceinline__ void warp_tex_scatter(float* __restrict__ gm, int key, int i01, int i10, int i11,
+                                                 const float (&v)[12], int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  bool done = key < 0;
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = !done && key == lk;
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    if (__popc(grp) < 8) break;
+    float x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = mine ? v[i] : 0.f;
+    warp_sum<12>(x);
+    if (lane == leader) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (x[c] != 0.f) atomicAdd(gm + key + c, x[c]);
+        if (i01 >= 0 && x[3 + c] != 0.f) atomicAdd(gm + i01 + c, x[3 + c]);
+        if (i10 >= 0 && x[6 + c] != 0.f) atomicAdd(gm + i10 + c, x[6 + c]);
+        if (i11 >= 0 && x[9 + c] != 0.f) atomicAdd(gm + i11 + c, x[9 + c]);
+      }
+    }
+    done = done || mine;
+    todo &= ~grp;
+  }
+  if (!done) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(gm + key + c, v[c]);
+      if (i01 >= 0) atomicAdd(gm + i01 + c, v[3 + c]);
+      if (i10 >= 0) atomicAdd(gm + i10 + c, v[6 + c]);
+      if (i11 >= 0) atomicAdd(gm + i11 + c, v[9 + c]);
+    }
+  }
+}
+
 // One thread per pixel.  Pass 1 walks the K saved fragments front to back, recomputes colour/opacity, scatters the
 // texture gradient and (unless detach_bary) the barycentric-path vertex gradient; pass 2 walks back to front with the
 // division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
-__global__ void __launch_bounds__(NTHREADS) raster_backward_kernel(const RasterParams P) {
+// Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
+__global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
   const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
   const int yi = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
-  if (xi >= P.W || yi >= P.H) return;
+  const bool live = xi < P.W && yi < P.H;
   const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
   const size_t plane = (size_t)P.H * P.W;
-  const size_t pix = (size_t)yi * P.W + xi;
+  const size_t pix = live ? (size_t)yi * P.W + xi : 0;
   const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
-  const float gr = go[0], gg = go[plane], gb = go[2 * plane], ga = go[3 * plane];
+  float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+  if (live) { gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane]; }
   const int* ids = P.topk + (size_t)view * P.K * plane + pix;
   float* s_alpha = s_store;
   float* s_cdot = s_store + (size_t)P.K * NTHREADS;
   float* s_e = s_store + 2 * (size_t)P.K * NTHREADS;
   float* s_occ = s_store + 3 * (size_t)P.K * NTHREADS;
-  const bool any_grad = (gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f);
+  const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
+  const size_t slot_base = (size_t)view * 2 * P.F;
+
+  // number of fragments of this pixel; warp-uniform trip count
+  int n = 0;
+  if (any_grad) { while (n < P.K && ids[(size_t)n * plane] >= 0) ++n; }
+  const int n_warp = __reduce_max_sync(0xffffffffu, n);
 
   float occ = 1.f;
-  int n = 0;
-  for (int k = 0; k < P.K; ++k) {
-    const int slot = ids[(size_t)k * plane];
-    if (slot < 0) break;
-    ++n;
-    Shade s;
-    shade_fragment(P, view, slot, p, s);
-    float d;
-    if (s.b.inside && P.clip_inside) d = -1.f;
-    else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
-    const float e = frag_alpha(d, P.sigma, P.clip_inside);
-    const float fa = P.faces_alpha ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
-    const float a = e * fa;
-    const float cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
-    s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
-    s_occ[k * NTHREADS + tid] = occ;
-    const float w = occ * a;                 // d RGB / d colour_k
-    if (w != 0.f && any_grad) {
-      const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
-      if (P.g_maps) {
-        float* gm = P.g_maps;
-        atomicAdd(gm + s.tap.i00, gcx * s.tap.w00); atomicAdd(gm + s.tap.i00 + 1, gcy * s.tap.w00); atomicAdd(gm + s.tap.i00 + 2, gcz * s.tap.w00);
-        if (s.tap.i01 >= 0) { atomicAdd(gm + s.tap.i01, gcx * s.tap.w01); atomicAdd(gm + s.tap.i01 + 1, gcy * s.tap.w01); atomicAdd(gm + s.tap.i01 + 2, gcz * s.tap.w01); }
-        if (s.tap.i10 >= 0) { atomicAdd(gm + s.tap.i10, gcx * s.tap.w10); atomicAdd(gm + s.tap.i10 + 1, gcy * s.tap.w10); atomicAdd(gm + s.tap.i10 + 2, gcz * s.tap.w10); }
-        if (s.tap.i11 >= 0) { atomicAdd(gm + s.tap.i11, gcx * s.tap.w11); atomicAdd(gm + s.tap.i11 + 1, gcy * s.tap.w11); atomicAdd(gm + s.tap.i11 + 2, gcz * s.tap.w11); }
-      }
-      if (!P.detach_bary) {
-        // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
-        const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
-        const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
-        const float d00 = s.c00.x * gcx + s.c00.y * gcy + s.c00.z * gcz, d01 = s.c01.x * gcx + s.c01.y * gcy + s.c01.z * gcz;
-        const float d10 = s.c10.x * gcx + s.c10.y * gcy + s.c10.z * gcz, d11 = s.c11.x * gcx + s.c11.y * gcy + s.c11.z * gcz;
-        const float gix = (d01 - d00) * ey + (d11 - d10) * wy;
-        const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
-        const float gu = gix * s.tap.mx, gv = giy * s.tap.my;
-        const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
-        f3 gbu = {gu * __ldg(fu) + gv * __ldg(fu + 1), gu * __ldg(fu + 2) + gv * __ldg(fu + 3), gu * __ldg(fu + 4) + gv * __ldg(fu + 5)};
-        const size_t gs = (size_t)view * 2 * P.F + slot;
-        f3 gbc = gbu;
-        if (s.t.flags & 1) {
-          const float* cv = P.conv + gs * 9;
-          gbc.x = cv[0] * gbu.x + cv[1] * gbu.y + cv[2] * gbu.z;
-          gbc.y = cv[3] * gbu.x + cv[4] * gbu.y + cv[5] * gbu.z;
-          gbc.z = cv[6] * gbu.x + cv[7] * gbu.y + cv[8] * gbu.z;
-          float* gc = P.g_conv + gs * 9;
-          const float bcv[3] = {s.b.bc.x, s.b.bc.y, s.b.bc.z}; const float gv3[3] = {gbu.x, gbu.y, gbu.z};
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) atomicAdd(gc + i * 3 + j, bcv[i] * gv3[j]);
+  for (int k = 0; k < n_warp; ++k) {
+    int key = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
+    float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float tv[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k < n) {
+      const int slot = ids[(size_t)k * plane];
+      Shade s;
+      shade_fragment(P, view, slot, p, s);
+      float d;
+      if (s.b.inside && P.clip_inside) d = -1.f;
+      else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
+      const float e = frag_alpha(d, P.sigma, P.clip_inside);
+      const float fa = P.faces_alpha ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
+      const float a = e * fa;
+      const float cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
+      s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
+      s_occ[k * NTHREADS + tid] = occ;
+      const float w = occ * a;                 // d RGB / d colour_k
+      if (w != 0.f) {
+        const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
+        if (P.g_maps) {
+          tkey = s.tap.i00; t01 = s.tap.i01; t10 = s.tap.i10; t11 = s.tap.i11;
+          tv[0] = gcx * s.tap.w00; tv[1] = gcy * s.tap.w00; tv[2] = gcz * s.tap.w00;
+          tv[3] = gcx * s.tap.w01; tv[4] = gcy * s.tap.w01; tv[5] = gcz * s.tap.w01;
+          tv[6] = gcx * s.tap.w10; tv[7] = gcy * s.tap.w10; tv[8] = gcz * s.tap.w10;
+          tv[9] = gcx * s.tap.w11; tv[10] = gcy * s.tap.w11; tv[11] = gcz * s.tap.w11;
         }
-        float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
-        f3 gb_ = gbc;
-        if (P.clipb) gb_ = clip_backward(s.b.bp, gb_);
-        if (P.persp) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
-        f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
-        bary_backward(p, s.t, gb_, g0, g1, g2);
-        float* gt = P.g_tri + gs * 9;
-        atomicAdd(gt + 0, g0.x); atomicAdd(gt + 1, g0.y); atomicAdd(gt + 2, gz0);
-        atomicAdd(gt + 3, g1.x); atomicAdd(gt + 4, g1.y); atomicAdd(gt + 5, gz1);
-        atomicAdd(gt + 6, g2.x); atomicAdd(gt + 7, g2.y); atomicAdd(gt + 8, gz2);
+        if (!P.detach_bary) {
+          // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
+          const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
+          const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
+          const float d00 = s.c00.x * gcx + s.c00.y * gcy + s.c00.z * gcz, d01 = s.c01.x * gcx + s.c01.y * gcy + s.c01.z * gcz;
+          const float d10 = s.c10.x * gcx + s.c10.y * gcy + s.c10.z * gcz, d11 = s.c11.x * gcx + s.c11.y * gcy + s.c11.z * gcz;
+          const float gix = (d01 - d00) * ey + (d11 - d10) * wy;
+          const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
+          const float gu = gix * s.tap.mx, gv = giy * s.tap.my;
+          const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
+          f3 gbu = {gu * __ldg(fu) + gv * __ldg(fu + 1), gu * __ldg(fu + 2) + gv * __ldg(fu + 3), gu * __ldg(fu + 4) + gv * __ldg(fu + 5)};
+          const size_t gs = slot_base + slot;
+          f3 gbc = gbu;
+          if (s.t.flags & 1) {               // rare: z-clipped face, plain atomics
+            const float* cv = P.conv + gs * 9;
+            gbc.x = cv[0] * gbu.x + cv[1] * gbu.y + cv[2] * gbu.z;
+            gbc.y = cv[3] * gbu.x + cv[4] * gbu.y + cv[5] * gbu.z;
+            gbc.z = cv[6] * gbu.x + cv[7] * gbu.y + cv[8] * gbu.z;
+            float* gc = P.g_conv + gs * 9;
+            const float bcv[3] = {s.b.bc.x, s.b.bc.y, s.b.bc.z}; const float gv3[3] = {gbu.x, gbu.y, gbu.z};
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) atomicAdd(gc + i * 3 + j, bcv[i] * gv3[j]);
+          }
+          float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
+          f3 gb_ = gbc;
+          if (P.clipb) gb_ = clip_backward(s.b.bp, gb_);
+          if (P.persp) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
+          f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
+          bary_backward(p, s.t, gb_, g0, g1, g2);
+          key = slot;
+          gv9[0] = g0.x; gv9[1] = g0.y; gv9[2] = gz0; gv9[3] = g1.x; gv9[4] = g1.y; gv9[5] = gz1; gv9[6] = g2.x; gv9[7] = g2.y; gv9[8] = gz2;
+        }
       }
+      occ *= (1.f - a);
     }
-    occ *= (1.f - a);
+    if (P.g_maps) warp_tex_scatter(P.g_maps, tkey, t01, t10, t11, tv, lane);
+    if (!P.detach_bary) warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
   }
-  if (!any_grad || n == 0) return;
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
-  for (int k = n - 1; k >= 0; --k) {
-    const float a = s_alpha[k * NTHREADS + tid], cdot = s_cdot[k * NTHREADS + tid], e = s_e[k * NTHREADS + tid];
-    const float occ_k = s_occ[k * NTHREADS + tid];
-    const float g_alpha = occ_k * (cdot - Tacc);
-    Tacc = a * cdot + (1.f - a) * Tacc;
-    if (g_alpha == 0.f) continue;
-    const int slot = ids[(size_t)k * plane];
-    const size_t gs = (size_t)view * 2 * P.F + slot;
-    const TriGeom t = unpack_tri(__ldg(&P.rec[gs * 3]), __ldg(&P.rec[gs * 3 + 1]), __ldg(&P.rec[gs * 3 + 2]));
-    float fa = 1.f;
-    if (P.faces_alpha) {
-      fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
-      if (P.g_faces_alpha) atomicAdd(P.g_faces_alpha + (size_t)view * P.alpha_stride + t.face, g_alpha * e);
-    }
-    if (P.sigma > 0.f) {
-      const Bary b = eval_bary(p, t, P.persp, P.clipb);
-      float g_sd;           // gradient w.r.t. the SIGNED squared distance
-      if (P.clip_inside) {
-        if (b.inside) continue;                        // clamp(d, 0): flat inside the face
-        g_sd = g_alpha * fa * (-e / P.sigma);
-      } else {
-        g_sd = g_alpha * fa * (-e * (1.f - e) / P.sigma);
+  for (int k = n_warp - 1; k >= 0; --k) {
+    int akey = -1, vkey = -1;
+    float ga1[1] = {0.f};
+    float gv6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k < n) {
+      const float a = s_alpha[k * NTHREADS + tid], cdot = s_cdot[k * NTHREADS + tid], e = s_e[k * NTHREADS + tid];
+      const float occ_k = s_occ[k * NTHREADS + tid];
+      const float g_alpha = occ_k * (cdot - Tacc);
+      Tacc = a * cdot + (1.f - a) * Tacc;
+      if (g_alpha != 0.f) {
+        const int slot = ids[(size_t)k * plane];
+        const size_t gs = slot_base + slot;
+        const TriGeom t = unpack_tri(__ldg(&P.rec[gs * 4]), __ldg(&P.rec[gs * 4 + 1]), __ldg(&P.rec[gs * 4 + 2]), __ldg(&P.rec[gs * 4 + 3]));
+        float fa = 1.f;
+        if (P.faces_alpha) {
+          fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
+          if (P.g_faces_alpha) { akey = t.face; ga1[0] = g_alpha * e; }
+        }
+        if (P.sigma > 0.f && P.g_tri) {
+          const Bary b = eval_bary(p, t, P.persp, P.clipb);
+          float g_sd = 0.f;           // gradient w.r.t. the SIGNED squared distance
+          if (P.clip_inside) { if (!b.inside) g_sd = g_alpha * fa * (-e / P.sigma); }   // clamp(d, 0): flat inside the face
+          else g_sd = g_alpha * fa * (-e * (1.f - e) / P.sigma);
+          const float g_dist = b.inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
+          if (g_dist != 0.f) {
+            f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
+            tri_dist_backward(p, t, g_dist, g0, g1, g2);
+            vkey = slot;
+            gv6[0] = g0.x; gv6[1] = g0.y; gv6[2] = g1.x; gv6[3] = g1.y; gv6[4] = g2.x; gv6[5] = g2.y;
+          }
+        }
       }
-      const float g_dist = b.inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
-      if (g_dist == 0.f) continue;
-      f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
-      tri_dist_backward(p, t, g_dist, g0, g1, g2);
-      float* gt = P.g_tri + gs * 9;
-      if (g0.x != 0.f || g0.y != 0.f) { atomicAdd(gt + 0, g0.x); atomicAdd(gt + 1, g0.y); }
-      if (g1.x != 0.f || g1.y != 0.f) { atomicAdd(gt + 3, g1.x); atomicAdd(gt + 4, g1.y); }
-      if (g2.x != 0.f || g2.y != 0.f) { atomicAdd(gt + 6, g2.x); atomicAdd(gt + 7, g2.y); }
+    }
+    if (P.g_faces_alpha) warp_agg_add<1>(P.g_faces_alpha + (size_t)view * P.alpha_stride, 1, akey, ga1, lane);
+    if (P.sigma > 0.f) {
+      // (x, y) of the three vertices live at offsets 0,1, 3,4, 6,7 of the slot's 9 floats
+      const unsigned any_v = __ballot_sync(0xffffffffu, vkey >= 0);
+      if (any_v) {
+        float gv9[9] = {gv6[0], gv6[1], 0.f, gv6[2], gv6[3], 0.f, gv6[4], gv6[5], 0.f};
+        warp_agg_add<9>(P.g_tri + slot_base * 9, 9, vkey, gv9, lane);
+      }
     }
   }
 }
@@ -735,6 +874,7 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
   P.out_rgba = out_rgba; P.topk = topk_ids;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const int K = s->faces_per_pixel;
+  ScopedTimer timer(0, K, st);
   if (K <= 1) launch_forward<1>(P, grid, st);
   else if (K <= 4) launch_forward<4>(P, grid, st);
   else if (K <= 10) launch_forward<10>(P, grid, st);
@@ -767,7 +907,10 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
   if (smem > 48 * 1024) CK(cudaFuncSetAttribute(raster_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  raster_backward_kernel<<<grid, NTHREADS, smem, st>>>(P);
+  {
+    ScopedTimer timer(1, s->faces_per_pixel, st);
+    raster_backward_kernel<<<grid, NTHREADS, smem, st>>>(P);
+  }
   LAUNCH_CK("raster_backward_kernel");
   if (need_geom) {
     const float* verts_ndc = s->verts_are_ndc ? verts : w.verts_ndc;

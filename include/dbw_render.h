@@ -123,6 +123,13 @@ void dbw_host_arena_release(void);
 /* Number of kernel launches issued by this library since process start (for bench.py's gpu_launches). */
 uint64_t dbw_launch_count(void);
 
+/* Optional live timing of the two rasterization kernels with CUDA events on the launch stream (bench.py's roofline):
+ * kind 0 = raster forward, 1 = raster backward; K filters by faces_per_pixel (0 = any).  dbw_timing_read synchronises
+ * on the recorded events and returns their summed duration and count; dbw_timing_reset frees them. */
+void dbw_timing_enable(int on);
+int dbw_timing_read(int kind, int K, double* total_ms, int* count);
+void dbw_timing_reset(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,10 +25,19 @@ def _rel(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def _check_image(out, ref, max_bad_frac=0.0):
+# Faces that share an edge or a vertex can reach a halo pixel with depths equal to ~1e-7 relative (their clamped
+# barycentrics land on the same point of the shared edge); which of them sorts first is then decided by the last bit
+# of pz -- in PyTorch3D too (its CPU and CUDA kernels need not agree there).  Such near-tie flips are the only
+# tolerated deviation: at most NEAR_TIE_FRAC of the values may exceed IMG_TOL, and never by more than NEAR_TIE_MAX.
+NEAR_TIE_FRAC = 1e-4
+NEAR_TIE_MAX = 2e-2
+
+
+def _check_image(out, ref, max_bad_frac=NEAR_TIE_FRAC, max_err=NEAR_TIE_MAX):
     err = (out - ref).abs()
     bad = (err > IMG_TOL).float().mean().item()
-    assert bad <= max_bad_frac, f'max err {err.max().item():.3e}, {bad * 100:.4f}% of values above {IMG_TOL}'
+    assert bad <= max_bad_frac and err.max().item() <= max(max_err, IMG_TOL), \
+        f'max err {err.max().item():.3e}, {bad * 100:.4f}% of values above {IMG_TOL}'
 
 
 def _setup(n_blocks=4, txt=32, n_views=2, seed=3, boxy=False, dtype=torch.float32, dist=2.75):
@@ -98,7 +107,7 @@ def _grad_parity(scene, R, T, K, size, sigma, Kf, z_clip, detach, fa, clip_insid
     mask = decision_mask(ids, frags, scene['faces'].shape[0])
     ambiguous = 1 - mask.mean().item()
     assert ambiguous <= max_ambiguous, f'{ambiguous * 100:.3f}% of pixels take a different discrete decision'
-    _check_image(out.detach().cpu().double() * mask, ref.detach() * mask)
+    _check_image(out.detach().cpu().double() * mask, ref.detach() * mask, max_bad_frac=0.0, max_err=IMG_TOL)
     gen = torch.Generator().manual_seed(seed)
     wgt = torch.rand(B, 4, *size, generator=gen, dtype=torch.float64) * mask
     scene['verts'].retain_grad()
