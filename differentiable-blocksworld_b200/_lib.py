@@ -27,7 +27,7 @@ class DbwMapDesc(ctypes.Structure):
                 ('reserved', ctypes.c_int32)]
 
 
-EXPORTS = ['dbw_abi_version', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_backward',
+EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_backward',
            'dbw_composite_mse', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset']
 
@@ -47,6 +47,7 @@ def lib():
         L = ctypes.CDLL(LIB_PATH)
         vp, sz = ctypes.c_void_p, ctypes.c_size_t
         L.dbw_abi_version.restype = ctypes.c_int
+        L.dbw_sizeof_settings.restype = ctypes.c_size_t
         L.dbw_last_error.restype = ctypes.c_char_p
         L.dbw_launch_count.restype = ctypes.c_uint64
         L.dbw_workspace_bytes.argtypes = [ctypes.POINTER(DbwRenderSettings), ctypes.POINTER(sz), ctypes.POINTER(sz)]
@@ -58,6 +59,8 @@ def lib():
         L.dbw_timing_enable.restype = None
         L.dbw_timing_reset.restype = None
         L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]
+        if L.dbw_sizeof_settings() != ctypes.sizeof(DbwRenderSettings):
+            raise DbwError('DbwRenderSettings layout mismatch between the library and its ctypes mirror')
         if L.dbw_abi_version() != ABI_VERSION:
             raise DbwError(f'ABI mismatch: library {L.dbw_abi_version()} != binding {ABI_VERSION}')
         _lib = L

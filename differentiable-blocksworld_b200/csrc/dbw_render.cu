@@ -36,6 +36,7 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
 #define LAUNCH_CK(name) do { ++g_launches; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail(name, _e); } while (0)
 
 extern "C" int dbw_abi_version(void) { return DBW_ABI_VERSION; }
+extern "C" size_t dbw_sizeof_settings(void) { return sizeof(DbwRenderSettings); }
 extern "C" const char* dbw_last_error(void) { return g_err; }
 extern "C" uint64_t dbw_launch_count(void) { return g_launches; }
 

@@ -59,6 +59,8 @@ typedef struct DbwRenderSettings {
 typedef struct DbwMapDesc { int32_t offset, height, width, reserved; } DbwMapDesc;
 
 int dbw_abi_version(void);
+/* sizeof(DbwRenderSettings) as compiled into the library: lets a binding verify its mirror of the struct. */
+size_t dbw_sizeof_settings(void);
 const char* dbw_last_error(void);
 
 /* Bytes of the two caller-provided device scratch buffers:

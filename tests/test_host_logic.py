@@ -1,0 +1,202 @@
+"""CPU: host-side logic of the product (no kernels are launched): topology/UV builders vs the oracle, the Meshes /
+TexturesUV stand-ins, model construction from the reference's configs, view sharding, and the N>1 gradient
+all-reduce path on the gloo backend (world_size 2)."""
+import os
+from copy import deepcopy
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dbw_path as D, pt3d
+
+REF_CFG = '/root/reference/configs'
+
+DTU_DEFAULT_MODEL = {          # restated values of configs/dtu/default.yml:1-26
+    'name': 'dbw',
+    'mesh': {'n_blocks': 10, 'S_world': 0.5, 'R_world': [115, 0, 0], 'txt_size': 256},
+    'renderer': {'faces_per_pixel': 10, 'cameras': {'name': 'perspective'}, 'detach_bary': True, 'z_clip': 0.001},
+    'rend_optim': {'coarse_learning': 1500, 'decimate_txt': 750, 'decimate_factor': 8, 'kill_blocks': True,
+                   'decouple_rendering': True, 'opacity_noise': True},
+    'loss': {'rgb_weight': 1, 'perceptual_weight': 0.1, 'parsimony_weight': 0.01, 'tv_weight': 0.1, 'overlap_weight': 1},
+}
+
+
+def test_geometry_builders_match_oracle():
+    from dbw_b200 import geometry as G
+    for lvl in (0, 1, 2):
+        v, f = G.ico_sphere(lvl)
+        vo, fo = pt3d.ico_sphere(lvl)
+        assert torch.equal(f, fo) and torch.equal(v, vo)
+    for lvl in (1, 2):
+        f, uv = G.icosphere_uvs(lvl)
+        fo, uvo = D.get_icosphere_uvs(lvl)
+        assert torch.equal(f, fo) and torch.equal(uv, uvo)
+    gv, gf = G.unit_plane()
+    ov, of = D.get_plane()
+    for _ in range(3):
+        gv, gf = G.subdivide_mesh(gv, gf)
+        ov, of = pt3d.subdivide(ov, of)
+    assert torch.equal(gf, of) and torch.equal(gv, ov)
+    assert torch.allclose(G.euler_world_rotation(115, 20, -30), D.world_rotation(115, 20, -30), atol=1e-7)
+    d6 = torch.randn(5, 6)
+    assert torch.allclose(G.rotation_6d_to_matrix(d6), pt3d.rotation_6d_to_matrix(d6), atol=1e-7)
+    Rm = G.random_rotations(7)
+    assert torch.allclose(Rm @ Rm.transpose(1, 2), torch.eye(3).expand(7, -1, -1), atol=1e-5)
+    assert torch.allclose(torch.det(Rm), torch.ones(7), atol=1e-5)
+    eta, om = torch.rand(3, 42) * 3 - 1.5, torch.rand(3, 42) * 6 - 3
+    e1, e2 = torch.rand(3, 1) * 1.8 + 0.1, torch.rand(3, 1) * 1.8 + 0.1
+    assert torch.equal(G.superquadric_points(eta, om, e1, e2), D.parametric_sq(eta, om, e1, e2))
+    X = torch.randn(50, 3)
+    assert torch.equal(G.spherical_uv(X), D.point_to_uv_sphericalmap(X))
+
+
+def test_synthetic_cameras_match_oracle_and_look_at_origin():
+    from dbw_b200.synthetic import ring_cameras
+    R, T, K = ring_cameras(5, jitter=0.2, seed=3)
+    Ro, To, Ko = D.ring_cameras(5, jitter=0.2, seed=3)
+    assert torch.equal(R, Ro) and torch.equal(T, To) and torch.equal(K, Ko)
+    origin_cam = (torch.zeros(5, 1, 3) @ R)[:, 0] + T          # X_cam = X_world @ R + T
+    assert torch.allclose(origin_cam[:, :2], torch.zeros(5, 2), atol=1e-6) and (origin_cam[:, 2] > 2).all()
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(5, -1, -1), atol=1e-6)
+
+
+def test_meshes_and_textures_join_scene():
+    from dbw_b200 import Meshes, TexturesUV, join_meshes_as_scene
+    v = torch.rand(2, 4, 3)
+    f = torch.tensor([[[0, 1, 2], [0, 2, 3]]]).expand(2, -1, -1)
+    maps = torch.rand(2, 5, 7, 3)
+    fu = torch.tensor([[[0, 1, 2], [0, 2, 3]]]).expand(2, -1, -1)
+    vu = torch.rand(2, 4, 2)
+    a = Meshes(v, f, TexturesUV(maps, fu, vu))
+    extra = Meshes(torch.rand(1, 3, 3), torch.tensor([[[0, 1, 2]]]), TexturesUV(torch.rand(1, 4, 4, 3), torch.tensor([[[0, 1, 2]]]), torch.rand(1, 3, 2)))
+    scene = join_meshes_as_scene([a, extra])
+    assert len(scene) == 1 and len(scene.extend(6)) == 6
+    sv, sf = scene.get_mesh_verts_faces(0)
+    assert sv.shape == (11, 3) and sf.shape == (5, 3) and sf.max() == 10
+    assert torch.equal(sf[2:4], f[1] + 4) and torch.equal(sf[4], torch.tensor([8, 9, 10]))
+    fvu, fmap = scene.textures.scene_arrays()
+    assert fvu.shape == (5, 3, 2) and fmap.tolist() == [0, 0, 1, 1, 2]
+    assert torch.equal(fvu[2], vu[1][fu[1][0]])
+    flat, table = scene.textures.packed_maps()
+    assert table == [(0, 5, 7), (105, 5, 7), (210, 4, 4)] and flat.numel() == 210 + 48
+    assert torch.equal(flat[105:210].reshape(5, 7, 3), maps[1])
+
+
+def _param_shapes(model):
+    return {n: tuple(p.shape) for n, p in model.named_parameters()}
+
+
+def test_model_constructs_with_reference_parameter_names():
+    from dbw_b200.dbw import create_model
+    cfg = {'model': deepcopy(DTU_DEFAULT_MODEL)}
+    cfg['model']['mesh']['txt_size'] = 64
+    model = create_model(cfg, (300, 400))
+    assert _param_shapes(model) == {
+        'sq_eps': (10, 2), 'R_6d_ground': (1, 6), 'T_ground': (1, 3), 'S': (10, 3), 'R_6d': (10, 6), 'T': (10, 3),
+        'alpha_logit': (10,), 'texture_bkg': (1, 64, 64, 3), 'texture_ground': (1, 64, 64, 3), 'textures': (10, 64, 64, 3)}
+    bufs = dict(model.named_buffers())
+    assert set(bufs) == {'R_world', 'T_world', 'bkg_verts_uvs', 'ground_verts_uvs', 'sq_eta', 'sq_omega',
+                         'block_faces_uvs', 'block_verts_uvs'}
+    assert bufs['sq_eta'].shape == (10, 42) and bufs['block_faces_uvs'].shape == (80, 3) and bufs['block_verts_uvs'].shape == (63, 2)
+    assert model.bkg_n_faces == 320 and model.ground_n_faces == 128 and model.blocks_n_faces == 800
+    assert model.loss_names == ['loss_rgb', 'loss_perceptual', 'loss_parsimony', 'loss_tv', 'loss_overlap', 'loss_total']
+    assert model.renderer.sigma == 1e-4 and model.renderer_fine.sigma == 5e-6 and model.renderer_env.faces_per_pixel == 1
+    assert abs(model.renderer.blur_radius - 9.2102e-4) < 1e-7
+    # the texture-prefixed Adam group of src/optimizer.py:9-14
+    assert sorted(n for n, _ in model.named_parameters() if n.startswith('texture')) == ['texture_bkg', 'texture_ground', 'textures']
+    # milestones
+    assert model.is_live('coarse_learning') and model.is_live('decimate_txt')
+    model.set_cur_epoch(1600)
+    assert not model.is_live('coarse_learning')
+    # checkpoint round trip incl. the spq_ -> sq_ rename of dbw.py:444-445
+    sd = {k.replace('sq_', 'spq_'): v.clone() + 1 for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)
+    assert torch.allclose(model.state_dict()['sq_eps'], sd['spq_eps'])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason='needs the reference checkout (/root/reference)')
+def test_every_reference_config_parses_unmodified():
+    import yaml
+    from dbw_b200.dbw import create_model
+    n = 0
+    for ds in sorted(os.listdir(REF_CFG)):
+        dpath = os.path.join(REF_CFG, ds, 'default.yml')       # load_yaml overlays on the directory's default.yml if any
+        default = yaml.safe_load(open(dpath)) if os.path.exists(dpath) else {}
+        for fn in sorted(os.listdir(os.path.join(REF_CFG, ds))):
+            cfg = deepcopy(default)
+
+            def overlay(dst, src):
+                for k, v in (src or {}).items():
+                    if isinstance(v, dict) and isinstance(dst.get(k), dict):
+                        overlay(dst[k], v)
+                    else:
+                        dst[k] = v
+            overlay(cfg, yaml.safe_load(open(os.path.join(REF_CFG, ds, fn))))
+            cfg['model']['mesh']['txt_size'] = 16           # keep the CPU test light; every other key untouched
+            model = create_model(cfg, (32, 48))
+            assert model.n_blocks == cfg['model']['mesh']['n_blocks']
+            n += 1
+    assert n >= 18
+
+
+def test_shard_views_is_a_balanced_partition():
+    from dbw_b200.parallel import shard_views
+    for B, W in [(49, 8), (49, 1), (64, 8), (5, 8), (256, 3)]:
+        parts = [shard_views(B, W, r) for r in range(W)]
+        assert parts[0].start == 0 and parts[-1].stop == B
+        assert all(parts[i].stop == parts[i + 1].start for i in range(W - 1))
+        sizes = [p.stop - p.start for p in parts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert [p.stop - p.start for p in [shard_views(49, 8, r) for r in range(8)]] == [7, 6, 6, 6, 6, 6, 6, 6]
+
+
+class _ToyScene(torch.nn.Module):
+    """stands in for the scene model on CPU: per-view 'render' loss + a view-independent regulariser + opacity noise."""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.arange(6, dtype=torch.float32).reshape(2, 3) / 10)
+        self.textures = torch.nn.Parameter(torch.ones(4))
+        self.n_total_views, self.noise_generator = None, None
+
+    def forward(self, inp, labels=None):
+        noise = torch.randn(4, generator=self.noise_generator)
+        pred = inp['imgs'] * self.w.sum() + (self.textures * (1 + 0.1 * noise)).sum()
+        rgb = ((pred - inp['R'].sum((1, 2))[:, None]) ** 2).sum() / (self.n_total_views * pred.shape[1])
+        reg = (self.w ** 2).sum() + self.textures.abs().sum()
+        return {'rgb': rgb, 'tv': reg, 'total': rgb + reg}
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from dbw_b200.parallel import ViewParallel
+    torch.manual_seed(0)
+    model = _ToyScene()
+    vp = ViewParallel(model, seed=123)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(7, 5, generator=g), 'R': torch.rand(7, 3, 3, generator=g), 'T': torch.rand(7, 3, generator=g)}
+    vp.forward_backward(inp)
+    out[rank] = vp.bucket.flat.clone()
+    dist.destroy_process_group()
+
+
+def test_view_parallel_gradients_equal_single_process_gloo():
+    """world_size-2 gloo run: sharded views + ONE all-reduce == the single-process gradient of the same step."""
+    from dbw_b200.parallel import ViewParallel
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29000 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    torch.manual_seed(0)
+    model = _ToyScene()
+    vp = ViewParallel(model, seed=123)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(7, 5, generator=g), 'R': torch.rand(7, 3, 3, generator=g), 'T': torch.rand(7, 3, generator=g)}
+    vp.forward_backward(inp)
+    ref = vp.bucket.flat
+    assert torch.allclose(out[0], out[1], atol=0)                 # every rank holds the same reduced gradient
+    assert torch.allclose(out[0], ref, rtol=1e-5, atol=1e-6)
+    assert vp.bucket.flat.data_ptr() == model.w.grad.data_ptr()   # grads are views into the single bucket
