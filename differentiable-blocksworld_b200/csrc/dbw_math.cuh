@@ -182,7 +182,7 @@ __device__ __forceinline__ void tri_dist_backward(f2 p, const TriGeom& t, float 
 // TexturesUV.sample_textures: grid = 2*uv - 1 on the map flipped along H, F.grid_sample(bilinear,
 // align_corners=True, padding_mode='border').  Row r of the flipped map is row H-1-r of the stored map.
 struct TexTap {
-  int i00, i01, i10, i11;   // float offsets (within the packed maps buffer) of the 4 texels, or -1 if out of bounds
+  int i00, i01, i10, i11;   // texel indices (within the packed float4 texel buffer) of the 4 taps, or -1 if out of bounds
   float w00, w01, w10, w11; // nw, ne, sw, se weights
   float ix, iy;             // un-normalised (clipped) coordinates in the flipped map
   float mx, my;             // d(ix)/du, d(iy)/dv incl. the border-clip mask
@@ -207,15 +207,21 @@ __device__ __forceinline__ TexTap tex_tap(float u, float v, int off, int H, int 
   t.w11 = (ix - fx0) * (iy - fy0);
   const bool x1ok = x1 <= W - 1, y1ok = y1 <= H - 1;
   const int r0 = (H - 1 - y0) * W, r1 = (H - 1 - y1) * W;
-  t.i00 = off + (r0 + x0) * 3;
-  t.i01 = x1ok ? off + (r0 + x1) * 3 : -1;
-  t.i10 = y1ok ? off + (r1 + x0) * 3 : -1;
-  t.i11 = (x1ok && y1ok) ? off + (r1 + x1) * 3 : -1;
+  t.i00 = off + r0 + x0;
+  t.i01 = x1ok ? off + r0 + x1 : -1;
+  t.i10 = y1ok ? off + r1 + x0 : -1;
+  t.i11 = (x1ok && y1ok) ? off + r1 + x1 : -1;
   t.ix = ix; t.iy = iy; t.x0 = x0; t.y0 = y0;
   return t;
 }
 
-__device__ __forceinline__ f3 ld3(const float* __restrict__ m, int i) {
+__device__ __forceinline__ f3 ld_texel(const float4* __restrict__ m, int i) {
   if (i < 0) return {0.f, 0.f, 0.f};
-  return {__ldg(m + i), __ldg(m + i + 1), __ldg(m + i + 2)};
+  const float4 t = __ldg(m + i);          // one 128-bit load per tap (RGB + pad)
+  return {t.x, t.y, t.z};
+}
+
+// vector reduction: one RED.128 per tap instead of three RED.32 (sm_90+)
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }

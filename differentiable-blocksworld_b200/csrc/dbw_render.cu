@@ -11,6 +11,9 @@
 //   verts_ndc  (B,V,3)            projected vertices (x_ndc, y_ndc, z_view)
 //   bbox       (B,2F) float4      blur-expanded NDC bbox of each face slot (xmin,xmax,ymin,ymax); xmin=+inf: empty
 //   rec        (B,2F,4) float4    v0xy v1xy | v2xy z0 z1 | z2 face neighbor flags | 1/area, 1/|e01|^2, 1/|e02|^2, 1/|e12|^2
+//   rec2       (B,2F,2) float4    u0 v0 u1 v1 | u2 v2 map_texel_offset (H<<16|W)   (static per face, replicated per view so
+//                                 that shading needs ONE dependent load level after the face id)
+//   maps4      (sum H*W) float4   the caller's (H,W,3) maps re-packed as RGB+pad texels: one 128-bit load per bilinear tap
 //   conv       (B,2F,9)           barycentric conversion (clipped -> original face), only for clipped slots
 //   slots [0,F) hold each face's (first) triangle, slots [F,2F) the second triangle of a z-clipped quad.
 //   out_rgba   (B,4,H,W), topk_ids (B,K,H,W) planar so that every warp store is a run of full 32 B sectors.
@@ -19,6 +22,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "../../include/dbw_render.h"
 #include "dbw_math.cuh"
@@ -74,7 +78,7 @@ extern "C" void dbw_timing_reset(void) {
 }
 
 struct Workspace {
-  float* verts_ndc; float4* bbox; float4* rec; float* conv; int* view_flags; size_t total;
+  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; float4* maps4; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
   Workspace w; char* p = (char*)base; size_t off = 0;
@@ -82,17 +86,20 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.verts_ndc = (float*)(p + off); off += align_up(B * V * 3 * sizeof(float));
   w.bbox = (float4*)(p + off);     off += align_up(B * S * sizeof(float4));
   w.rec = (float4*)(p + off);      off += align_up(B * S * 4 * sizeof(float4));
+  w.rec2 = (float4*)(p + off);     off += align_up(B * S * 2 * sizeof(float4));
   w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
+  w.maps4 = (float4*)(p + off);    off += align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   w.total = off; return w;
 }
-struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; size_t total; };
+struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; float4* g_maps4; size_t total; };
 static BwdScratch carve_bwd(const DbwRenderSettings& s, void* base) {
   BwdScratch w; char* p = (char*)base; size_t off = 0;
   const size_t B = s.n_views, V = s.n_verts, S = 2 * (size_t)s.n_faces;
   w.g_tri = (float*)(p + off);        off += align_up(B * S * 9 * sizeof(float));
   w.g_conv = (float*)(p + off);       off += align_up(B * S * 9 * sizeof(float));
   w.g_verts_ndc = (float*)(p + off);  off += align_up(B * V * 3 * sizeof(float));
+  w.g_maps4 = (float4*)(p + off);     off += align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   w.total = off; return w;
 }
 
@@ -110,7 +117,20 @@ static int validate(const DbwRenderSettings* s) {
   if (s->n_verts <= 0 || s->n_faces <= 0 || s->n_maps <= 0) return fail("n_verts, n_faces, n_maps must be positive");
   if (s->alpha_view_stride != 0 && s->alpha_view_stride != s->n_faces) return fail("alpha_view_stride must be 0 or n_faces");
   if (s->sigma < 0.f || s->blur_radius < 0.f) return fail("sigma and blur_radius must be >= 0");
+  if (s->n_map_floats <= 0 || s->n_map_floats % 3 != 0) return fail("n_map_floats must be a positive multiple of 3");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ texel repack
+__global__ void maps_to_float4_kernel(const float* __restrict__ maps, float4* __restrict__ maps4, int n_texels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_texels; i += gridDim.x * blockDim.x)
+    maps4[i] = make_float4(maps[3 * i], maps[3 * i + 1], maps[3 * i + 2], 0.f);
+}
+__global__ void fold_gmaps_kernel(const float4* __restrict__ g4, float* __restrict__ g_maps, int n_texels) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_texels; i += gridDim.x * blockDim.x) {
+    const float4 g = g4[i];
+    g_maps[3 * i] += g.x; g_maps[3 * i + 1] += g.y; g_maps[3 * i + 2] += g.z;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ projection (A1)
@@ -222,8 +242,10 @@ __device__ void clip_face(const float a[3][3], float z_clip, bool persp, ClipRes
   }
 }
 
-__device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float* conv, size_t slot, const float* tri,
-                                           const float* cv, bool clipped, int face, int neighbor, float sqrt_blur) {
+__device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float4* rec2, float* conv, size_t slot, const float* tri,
+                                           const float* cv, bool clipped, int face, int neighbor, float sqrt_blur,
+                                           float4 uv01, float4 uv2m) {
+  rec2[slot * 2] = uv01; rec2[slot * 2 + 1] = uv2m;
   const float x0 = tri[0], y0 = tri[1], z0 = tri[2], x1 = tri[3], y1 = tri[4], z1 = tri[5], x2 = tri[6], y2 = tri[7], z2 = tri[8];
   const float zmin = fminf(fminf(z0, z1), z2);
   const f2 a = {x0, y0}, b = {x1, y1}, c = {x2, y2};
@@ -252,7 +274,9 @@ __device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float* con
 }
 
 __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
-                                  float z_clip, int persp, float sqrt_blur, float4* __restrict__ bbox, float4* __restrict__ rec,
+                                  float z_clip, int persp, float sqrt_blur, const float* __restrict__ faces_uvs,
+                                  const int* __restrict__ face_map, const DbwMapDesc* __restrict__ map_table,
+                                  float4* __restrict__ bbox, float4* __restrict__ rec, float4* __restrict__ rec2,
                                   float* __restrict__ conv, int* __restrict__ view_flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * F) return;
@@ -267,8 +291,12 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   clip_face(a, z_clip, persp != 0, r);
   const size_t s0 = (size_t)b * 2 * F + f, s1 = s0 + F;
   const float inval[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // zmin = 0 < eps -> marked empty
-  write_slot(bbox, rec, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur);
-  write_slot(bbox, rec, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur);
+  const float* fu = faces_uvs + (size_t)f * 6;
+  const DbwMapDesc md = map_table[face_map[f]];
+  const float4 uv01 = make_float4(fu[0], fu[1], fu[2], fu[3]);
+  const float4 uv2m = make_float4(fu[4], fu[5], __int_as_float(md.offset / 3), __int_as_float((md.height << 16) | md.width));
+  write_slot(bbox, rec, rec2, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur, uv01, uv2m);
+  write_slot(bbox, rec, rec2, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur, uv01, uv2m);
   if (r.ntri == 2) atomicOr(&view_flags[b], 1);
 }
 
@@ -278,12 +306,14 @@ struct RasterParams {
   int alpha_stride;
   float sigma, blur, bg0, bg1, bg2;
   int clip_inside, persp, clipb, detach_bary;
-  const float4* bbox; const float4* rec; const float* conv; const int* view_flags;
-  const float* faces_uvs; const int* face_map; const float* maps; const DbwMapDesc* map_table;
+  const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags;
+  const float4* maps4;
   const float* faces_alpha;
   float* out_rgba; int* topk;
   // backward only
-  const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float* g_maps;
+  const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
+  int debug_skip;   // experiments only (env DBW_DEBUG_SKIP): 1 = no texture scatter, 2 = no vertex-gradient accumulation, 4 = no pass 2,
+                    // 8 = return after the per-pixel loads, 16 = no gradient work in pass 1, 32 = no barycentric-path math
 };
 
 #define TILE_W 16
@@ -305,12 +335,16 @@ __device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_insid
 // shared by forward shading and backward: colour of fragment (slot) at pixel p
 struct Shade {
   TriGeom t; Bary b; f3 bu;       // bu: barycentrics w.r.t. the ORIGINAL face (after un-clipping)
-  float u, v; int m_off, mH, mW; TexTap tap; f3 c00, c01, c10, c11, color;
+  float4 uv01; float u2, v2;      // per-face-vertex UVs
+  float u, v; TexTap tap; f3 c00, c01, c10, c11, color;
 };
 
 __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
   const size_t gs = (size_t)view * 2 * P.F + slot;
-  s.t = unpack_tri(__ldg(&P.rec[gs * 4]), __ldg(&P.rec[gs * 4 + 1]), __ldg(&P.rec[gs * 4 + 2]), __ldg(&P.rec[gs * 4 + 3]));
+  // one level of dependent loads after the face id: geometry record + UV / map record (6 x LDG.128)
+  const float4 r0 = __ldg(&P.rec[gs * 4]), r1 = __ldg(&P.rec[gs * 4 + 1]), r2 = __ldg(&P.rec[gs * 4 + 2]), r3 = __ldg(&P.rec[gs * 4 + 3]);
+  const float4 q0 = __ldg(&P.rec2[gs * 2]), q1 = __ldg(&P.rec2[gs * 2 + 1]);
+  s.t = unpack_tri(r0, r1, r2, r3);
   s.b = eval_bary(p, s.t, P.persp, P.clipb);
   s.bu = s.b.bc;
   if (s.t.flags & 1) {
@@ -319,14 +353,13 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
     s.bu.y = s.b.bc.x * cv[1] + s.b.bc.y * cv[4] + s.b.bc.z * cv[7];
     s.bu.z = s.b.bc.x * cv[2] + s.b.bc.y * cv[5] + s.b.bc.z * cv[8];
   }
-  const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
-  s.u = s.bu.x * __ldg(fu) + s.bu.y * __ldg(fu + 2) + s.bu.z * __ldg(fu + 4);
-  s.v = s.bu.x * __ldg(fu + 1) + s.bu.y * __ldg(fu + 3) + s.bu.z * __ldg(fu + 5);
-  const DbwMapDesc md = P.map_table[__ldg(&P.face_map[s.t.face])];
-  s.m_off = md.offset; s.mH = md.height; s.mW = md.width;
-  s.tap = tex_tap(s.u, s.v, md.offset, md.height, md.width);
-  s.c00 = ld3(P.maps, s.tap.i00); s.c01 = ld3(P.maps, s.tap.i01);
-  s.c10 = ld3(P.maps, s.tap.i10); s.c11 = ld3(P.maps, s.tap.i11);
+  s.uv01 = q0; s.u2 = q1.x; s.v2 = q1.y;
+  s.u = s.bu.x * q0.x + s.bu.y * q0.z + s.bu.z * q1.x;
+  s.v = s.bu.x * q0.y + s.bu.y * q0.w + s.bu.z * q1.y;
+  const int hw = __float_as_int(q1.w);
+  s.tap = tex_tap(s.u, s.v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
+  s.c00 = ld_texel(P.maps4, s.tap.i00); s.c01 = ld_texel(P.maps4, s.tap.i01);
+  s.c10 = ld_texel(P.maps4, s.tap.i10); s.c11 = ld_texel(P.maps4, s.tap.i11);
   s.color.x = s.c00.x * s.tap.w00 + s.c01.x * s.tap.w01 + s.c10.x * s.tap.w10 + s.c11.x * s.tap.w11;
   s.color.y = s.c00.y * s.tap.w00 + s.c01.y * s.tap.w01 + s.c10.y * s.tap.w10 + s.c11.y * s.tap.w11;
   s.color.z = s.c00.z * s.tap.w00 + s.c01.z * s.tap.w01 + s.c10.z * s.tap.w10 + s.c11.z * s.tap.w11;
@@ -519,7 +552,7 @@ __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride
 // through a narrow field of view: hundreds of pixels per texel) whole warps hit the same 2x2 texel footprint, so
 // lanes that share the footprint with >= 8 others are reduced with shuffles first; the rest issue plain atomics.
 // Coherence is probed from the first pending lane only (no match.any): an incoherent warp pays two ballots.
-__device__ __forceinline__ void warp_tex_scatter(float* __restrict__ gm, int key, int i01, int i10, int i11,
+__device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int key, int i01, int i10, int i11,
                                                  const float (&v)[12], int lane) {
   unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
   bool done = key < 0;
@@ -534,25 +567,19 @@ __device__ __forceinline__ void warp_tex_scatter(float* __restrict__ gm, int key
     for (int i = 0; i < 12; ++i) x[i] = mine ? v[i] : 0.f;
     warp_sum<12>(x);
     if (lane == leader) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (x[c] != 0.f) atomicAdd(gm + key + c, x[c]);
-        if (i01 >= 0 && x[3 + c] != 0.f) atomicAdd(gm + i01 + c, x[3 + c]);
-        if (i10 >= 0 && x[6 + c] != 0.f) atomicAdd(gm + i10 + c, x[6 + c]);
-        if (i11 >= 0 && x[9 + c] != 0.f) atomicAdd(gm + i11 + c, x[9 + c]);
-      }
+      red_add_v4(gm + key, x[0], x[1], x[2]);
+      if (i01 >= 0) red_add_v4(gm + i01, x[3], x[4], x[5]);
+      if (i10 >= 0) red_add_v4(gm + i10, x[6], x[7], x[8]);
+      if (i11 >= 0) red_add_v4(gm + i11, x[9], x[10], x[11]);
     }
     done = done || mine;
     todo &= ~grp;
   }
   if (!done) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      atomicAdd(gm + key + c, v[c]);
-      if (i01 >= 0) atomicAdd(gm + i01 + c, v[3 + c]);
-      if (i10 >= 0) atomicAdd(gm + i10 + c, v[6 + c]);
-      if (i11 >= 0) atomicAdd(gm + i11 + c, v[9 + c]);
-    }
+    red_add_v4(gm + key, v[0], v[1], v[2]);
+    if (i01 >= 0) red_add_v4(gm + i01, v[3], v[4], v[5]);
+    if (i10 >= 0) red_add_v4(gm + i10, v[6], v[7], v[8]);
+    if (i11 >= 0) red_add_v4(gm + i11, v[9], v[10], v[11]);
   }
 }
 
@@ -560,6 +587,7 @@ __device__ __forceinline__ void warp_tex_scatter(float* __restrict__ gm, int key
 // texture gradient and (unless detach_bary) the barycentric-path vertex gradient; pass 2 walks back to front with the
 // division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
 // Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
+template <bool DETACH, bool ALPHA>
 __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -585,11 +613,13 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
   int n = 0;
   if (any_grad) { while (n < P.K && ids[(size_t)n * plane] >= 0) ++n; }
   const int n_warp = __reduce_max_sync(0xffffffffu, n);
+  if (P.debug_skip & 8) { if (gr + gg + gb + ga + (float)n == 12345.f) P.g_tri[0] = 1.f; return; }
 
   float occ = 1.f;
   for (int k = 0; k < n_warp; ++k) {
-    int key = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
+    int key = -1, ckey = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
     float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float gc9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tv[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (k < n) {
       const int slot = ids[(size_t)k * plane];
@@ -599,22 +629,22 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
       if (s.b.inside && P.clip_inside) d = -1.f;
       else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
       const float e = frag_alpha(d, P.sigma, P.clip_inside);
-      const float fa = P.faces_alpha ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
+      const float fa = ALPHA ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
       const float a = e * fa;
       const float cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
       s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
       s_occ[k * NTHREADS + tid] = occ;
       const float w = occ * a;                 // d RGB / d colour_k
-      if (w != 0.f) {
+      if (w != 0.f && !(P.debug_skip & 16)) {
         const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
-        if (P.g_maps) {
+        if (P.g_maps4) {
           tkey = s.tap.i00; t01 = s.tap.i01; t10 = s.tap.i10; t11 = s.tap.i11;
           tv[0] = gcx * s.tap.w00; tv[1] = gcy * s.tap.w00; tv[2] = gcz * s.tap.w00;
           tv[3] = gcx * s.tap.w01; tv[4] = gcy * s.tap.w01; tv[5] = gcz * s.tap.w01;
           tv[6] = gcx * s.tap.w10; tv[7] = gcy * s.tap.w10; tv[8] = gcz * s.tap.w10;
           tv[9] = gcx * s.tap.w11; tv[10] = gcy * s.tap.w11; tv[11] = gcz * s.tap.w11;
         }
-        if (!P.detach_bary) {
+        if (!DETACH && !(P.debug_skip & 32)) {
           // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
           const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
           const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
@@ -623,40 +653,43 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
           const float gix = (d01 - d00) * ey + (d11 - d10) * wy;
           const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
           const float gu = gix * s.tap.mx, gv = giy * s.tap.my;
-          const float* fu = P.faces_uvs + (size_t)s.t.face * 6;
-          f3 gbu = {gu * __ldg(fu) + gv * __ldg(fu + 1), gu * __ldg(fu + 2) + gv * __ldg(fu + 3), gu * __ldg(fu + 4) + gv * __ldg(fu + 5)};
+          f3 gbu = {gu * s.uv01.x + gv * s.uv01.y, gu * s.uv01.z + gv * s.uv01.w, gu * s.u2 + gv * s.v2};
           const size_t gs = slot_base + slot;
           f3 gbc = gbu;
-          if (s.t.flags & 1) {               // rare: z-clipped face, plain atomics
+          if (s.t.flags & 1) {
+            // z-clipped face (the ground plane under the camera is one): bu = bc @ conv, so the conversion matrix gets
+            // gradient too; it is accumulated per slot with the same warp aggregation as the vertex gradient below
             const float* cv = P.conv + gs * 9;
             gbc.x = cv[0] * gbu.x + cv[1] * gbu.y + cv[2] * gbu.z;
             gbc.y = cv[3] * gbu.x + cv[4] * gbu.y + cv[5] * gbu.z;
             gbc.z = cv[6] * gbu.x + cv[7] * gbu.y + cv[8] * gbu.z;
-            float* gc = P.g_conv + gs * 9;
-            const float bcv[3] = {s.b.bc.x, s.b.bc.y, s.b.bc.z}; const float gv3[3] = {gbu.x, gbu.y, gbu.z};
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) atomicAdd(gc + i * 3 + j, bcv[i] * gv3[j]);
+            ckey = slot;
+            gc9[0] = s.b.bc.x * gbu.x; gc9[1] = s.b.bc.x * gbu.y; gc9[2] = s.b.bc.x * gbu.z;
+            gc9[3] = s.b.bc.y * gbu.x; gc9[4] = s.b.bc.y * gbu.y; gc9[5] = s.b.bc.y * gbu.z;
+            gc9[6] = s.b.bc.z * gbu.x; gc9[7] = s.b.bc.z * gbu.y; gc9[8] = s.b.bc.z * gbu.z;
           }
           float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
           f3 gb_ = gbc;
-          if (P.clipb) gb_ = clip_backward(s.b.bp, gb_);
-          if (P.persp) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
+          if (P.clipb && !(P.debug_skip & 128)) gb_ = clip_backward(s.b.bp, gb_);
+          if (P.persp && !(P.debug_skip & 256)) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
           f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
-          bary_backward(p, s.t, gb_, g0, g1, g2);
+          if (!(P.debug_skip & 512)) bary_backward(p, s.t, gb_, g0, g1, g2);
           key = slot;
           gv9[0] = g0.x; gv9[1] = g0.y; gv9[2] = gz0; gv9[3] = g1.x; gv9[4] = g1.y; gv9[5] = gz1; gv9[6] = g2.x; gv9[7] = g2.y; gv9[8] = gz2;
         }
       }
       occ *= (1.f - a);
     }
-    if (P.g_maps) warp_tex_scatter(P.g_maps, tkey, t01, t10, t11, tv, lane);
-    if (!P.detach_bary) warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
+    if (P.g_maps4 && !(P.debug_skip & 1)) warp_tex_scatter(P.g_maps4, tkey, t01, t10, t11, tv, lane);
+    if (!DETACH && !(P.debug_skip & 2)) {
+      warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
+      if (__ballot_sync(0xffffffffu, ckey >= 0)) warp_agg_add<9>(P.g_conv + slot_base * 9, 9, ckey, gc9, lane);
+    }
   }
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
+  if (P.debug_skip & 4) return;
   for (int k = n_warp - 1; k >= 0; --k) {
     int akey = -1, vkey = -1;
     float ga1[1] = {0.f};
@@ -671,7 +704,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
         const size_t gs = slot_base + slot;
         const TriGeom t = unpack_tri(__ldg(&P.rec[gs * 4]), __ldg(&P.rec[gs * 4 + 1]), __ldg(&P.rec[gs * 4 + 2]), __ldg(&P.rec[gs * 4 + 3]));
         float fa = 1.f;
-        if (P.faces_alpha) {
+        if (ALPHA) {
           fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
           if (P.g_faces_alpha) { akey = t.face; ga1[0] = g_alpha * e; }
         }
@@ -690,7 +723,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
         }
       }
     }
-    if (P.g_faces_alpha) warp_agg_add<1>(P.g_faces_alpha + (size_t)view * P.alpha_stride, 1, akey, ga1, lane);
+    if (ALPHA && P.g_faces_alpha) warp_agg_add<1>(P.g_faces_alpha + (size_t)view * P.alpha_stride, 1, akey, ga1, lane);
     if (P.sigma > 0.f) {
       // (x, y) of the three vertices live at offsets 0,1, 3,4, 6,7 of the slot's 9 floats
       const unsigned any_v = __ballot_sync(0xffffffffu, vkey >= 0);
@@ -831,16 +864,15 @@ __global__ void composite_mse_kernel(int n_px_total, int plane, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, const float* faces_uvs, const int32_t* face_map,
-                                const float* maps, const DbwMapDesc* map_table, const float* faces_alpha) {
+static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, const float* faces_alpha) {
   RasterParams P;
   memset(&P, 0, sizeof(P));
   P.B = s.n_views; P.H = s.height; P.W = s.width; P.K = s.faces_per_pixel; P.V = s.n_verts; P.F = s.n_faces; P.M = s.n_maps;
   P.alpha_stride = s.alpha_view_stride;
   P.sigma = s.sigma; P.blur = s.blur_radius; P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
-  P.bbox = w.bbox; P.rec = w.rec; P.conv = w.conv; P.view_flags = w.view_flags;
-  P.faces_uvs = faces_uvs; P.face_map = face_map; P.maps = maps; P.map_table = map_table; P.faces_alpha = faces_alpha;
+  P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags;
+  P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
   return P;
 }
 
@@ -869,9 +901,16 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
   }
   CK(cudaMemsetAsync(w.view_flags, 0, B * sizeof(int), st));
   face_setup_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
-                                                         sqrtf(s->blur_radius), w.bbox, w.rec, w.conv, w.view_flags);
+                                                         sqrtf(s->blur_radius), faces_uvs, face_map, map_table, w.bbox, w.rec,
+                                                         w.rec2, w.conv, w.view_flags);
   LAUNCH_CK("face_setup_kernel");
-  RasterParams P = make_params(*s, w, faces_uvs, face_map, maps, map_table, faces_alpha);
+  {
+    const int n_texels = s->n_map_floats / 3;
+    int blocks = (n_texels + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    maps_to_float4_kernel<<<blocks, 256, 0, st>>>(maps, w.maps4, n_texels);
+    LAUNCH_CK("maps_to_float4_kernel");
+  }
+  RasterParams P = make_params(*s, w, faces_alpha);
   P.out_rgba = out_rgba; P.topk = topk_ids;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const int K = s->faces_per_pixel;
@@ -902,17 +941,31 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   const int B = s->n_views, V = s->n_verts, F = s->n_faces;
   const bool need_geom = g_verts != nullptr;
   CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
-  RasterParams P = make_params(*s, w, faces_uvs, face_map, maps, map_table, faces_alpha);
+  RasterParams P = make_params(*s, w, faces_alpha);
   P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
-  P.g_faces_alpha = g_faces_alpha; P.g_maps = g_maps;
+  P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? g.g_maps4 : nullptr;
+  { const char* e = getenv("DBW_DEBUG_SKIP"); P.debug_skip = e ? atoi(e) : 0; }
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
-  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(raster_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
-    ScopedTimer timer(1, s->faces_per_pixel, st);
-    raster_backward_kernel<<<grid, NTHREADS, smem, st>>>(P);
+    auto launch = [&](auto kern) -> cudaError_t {
+      if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+      ScopedTimer timer(1, s->faces_per_pixel, st);
+      kern<<<grid, NTHREADS, smem, st>>>(P);
+      return cudaSuccess;
+    };
+    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr;
+    cudaError_t e = det ? (al ? launch(raster_backward_kernel<true, true>) : launch(raster_backward_kernel<true, false>))
+                        : (al ? launch(raster_backward_kernel<false, true>) : launch(raster_backward_kernel<false, false>));
+    if (e != cudaSuccess) return fail("raster_backward_kernel attribute", e);
   }
   LAUNCH_CK("raster_backward_kernel");
+  if (g_maps) {
+    const int n_texels = s->n_map_floats / 3;
+    int blocks = (n_texels + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
+    fold_gmaps_kernel<<<blocks, 256, 0, st>>>(g.g_maps4, g_maps, n_texels);
+    LAUNCH_CK("fold_gmaps_kernel");
+  }
   if (need_geom) {
     const float* verts_ndc = s->verts_are_ndc ? verts : w.verts_ndc;
     float* g_ndc = s->verts_are_ndc ? g_verts : g.g_verts_ndc;

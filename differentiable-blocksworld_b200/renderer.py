@@ -95,7 +95,8 @@ class _RenderFn(torch.autograd.Function):
 
 
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
-                  perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS):
+                  perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
+                  n_map_floats=0):
     s = DbwRenderSettings()
     s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
     s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
@@ -106,6 +107,7 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     s.background = (ctypes.c_float * 3)(*[float(c) for c in background])
     s.clip_inside, s.perspective_correct = int(clip_inside), int(perspective_correct)
     s.clip_barycentric, s.detach_bary, s.verts_are_ndc = int(clip_barycentric), int(detach_bary), int(verts_are_ndc)
+    s.n_map_floats = int(n_map_floats)
     return s
 
 
@@ -131,7 +133,8 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     if blur_radius is None:
         blur_radius = np.log(1. / 1e-4 - 1.) * sigma            # renderer.py:51
     cfg = make_settings(B, H, W, faces_per_pixel, V, Fn, len(map_table_host), alpha_stride, intr, sigma, blur_radius,
-                        z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc)
+                        z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc,
+                        n_map_floats=maps.numel())
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)

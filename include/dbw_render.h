@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 1
+#define DBW_ABI_VERSION 2
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -53,6 +53,7 @@ typedef struct DbwRenderSettings {
   int32_t clip_barycentric;   /* clip_barycentric_coords=True (renderer.py:46)                                       */
   int32_t detach_bary;        /* LayeredShader detach_bary (renderer.py:43,222-223): no gradient through barycentrics */
   int32_t verts_are_ndc;      /* 1: `verts` is (B,V,3) = (x_ndc, y_ndc, z_view) and R/T/K are ignored                 */
+  int32_t n_map_floats;       /* total floats in `maps` (= 3 * sum_m H_m*W_m): sizes the library's float4 texel scratch    */
 } DbwRenderSettings;
 
 /* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */

@@ -23,20 +23,21 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f'{n} declared in include/dbw_render.h but not exported'
     assert set(_lib.EXPORTS) == set(names)
-    assert L.dbw_abi_version() == 1
+    assert L.dbw_abi_version() == 2
 
 
 def test_settings_struct_layout_and_workspace_query():
     from dbw_b200 import _lib
     from dbw_b200.renderer import make_settings
-    assert ctypes.sizeof(_lib.DbwRenderSettings) == _lib.lib().dbw_sizeof_settings() == 24 * 4
+    assert ctypes.sizeof(_lib.DbwRenderSettings) == _lib.lib().dbw_sizeof_settings() == 25 * 4
     assert ctypes.sizeof(_lib.DbwMapDesc) == 16
-    s = make_settings(49, 400, 400, 10, 420, 800, 10, 0, (4.8, 4.8, 0., 0.), 1e-4, 9.21e-4, 0.001, (0, 0, 0))
+    s = make_settings(49, 400, 400, 10, 420, 800, 10, 0, (4.8, 4.8, 0., 0.), 1e-4, 9.21e-4, 0.001, (0, 0, 0),
+                      n_map_floats=10 * 256 * 279 * 3)
     fwd, bwd = ctypes.c_size_t(0), ctypes.c_size_t(0)
     assert _lib.lib().dbw_workspace_bytes(ctypes.byref(s), ctypes.byref(fwd), ctypes.byref(bwd)) == 0
     # verts_ndc + bbox (16 B) + rec (64 B) + conv (36 B) per slot, 2F slots per view
-    assert fwd.value >= 49 * (420 * 12 + 1600 * (16 + 64 + 36))
-    assert bwd.value >= 49 * (1600 * 72 + 420 * 12)
+    assert fwd.value >= 49 * (420 * 12 + 1600 * (16 + 96 + 36)) + 10 * 256 * 279 * 16
+    assert bwd.value >= 49 * (1600 * 72 + 420 * 12) + 10 * 256 * 279 * 16
 
 
 def test_invalid_arguments_fail_loudly_without_a_gpu():
