@@ -49,36 +49,43 @@ def algorithmic_bytes_per_view(K, H, W):
     return H * W * (32 + 8 * K)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line): one background
+    `nvidia-smi -lms 100` process, started before the region and stopped after it."""
+    QUERY = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.25)                      # let the first sample land before the timed region starts
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self._stop_evt.set()
-        self.join(timeout=3)
-        if not self.rows:
+        if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ''
+        rows = [[c.strip() for c in l.split(',')] for l in out.strip().splitlines() if l.count(',') >= 6]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+        num = lambda x: float(x) if x.replace('.', '', 1).isdigit() else None
+        sm = sorted(v for v in (num(r[0]) for r in rows) if v is not None)
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': float(self.rows[0][1]) if self.rows[0][1].replace('.', '').isdigit() else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in rows)]
+        pw = [v for v in (num(r[2]) for r in rows) if v is not None]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': num(rows[0][1]), 'reasons': reasons,
+                'samples': len(rows), 'power_w_max': max(pw) if pw else None}
 
 
 def synthetic_inputs(B, H, W, device=None, pin=False):
@@ -107,6 +114,7 @@ def run_ours(args):
     from dbw_b200 import _lib
     from dbw_b200.dbw import DifferentiableBlocksWorld
     from dbw_b200.parallel import ViewParallel, shard_views
+    from dbw_b200.graph import GraphedStep
     from copy import deepcopy
 
     B, H, W, K = WORKLOAD['n_views'], WORKLOAD['height'], WORKLOAD['width'], WORKLOAD['faces_per_pixel']
@@ -121,12 +129,20 @@ def run_ours(args):
     dev_local = {k: v.to(dev) for k, v in host_local.items()}
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
-    def step_resident():
+    def step_eager():
         return vp.forward_backward(dev_local, None, already_sharded=True, n_total_views=B)
 
+    graphed = None if args.no_graph else GraphedStep(vp, dev_local, B)
+
+    def step_resident():
+        return graphed.run() if graphed is not None else step_eager()
+
     def step_e2e():
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host_local.items()}     # H2D of this step's inputs (pinned)
-        losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B)
+        if graphed is not None:
+            losses = graphed.run(host_local)          # H2D of this step's inputs (pinned) into the graph's static buffers
+        else:
+            inp = {k: v.to(dev, non_blocking=True) for k, v in host_local.items()}
+            losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B)
         return float(losses['rgb'].item())                                        # D2H read of the step's result
 
     def barrier():
@@ -139,9 +155,10 @@ def run_ours(args):
     barrier()
 
     # ---- device-resident timing: per-step CUDA event pairs, L2 flushed between steps (outside the pairs)
-    _lib.lib().dbw_timing_reset()
-    _lib.lib().dbw_timing_enable(1)
     launches0 = _lib.launch_count()
+    step_eager()
+    launches_per_step = _lib.launch_count() - launches0      # our kernels per step (a graph replays exactly these)
+    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -155,10 +172,20 @@ def run_ours(args):
         b.record()
         evs.append((a, b))
     barrier()
-    launches = _lib.launch_count() - launches0
-    _lib.lib().dbw_timing_enable(0)
+    launches = launches_per_step * args.steps
     ms_local = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.summary() if sampler else None
+
+    # ---- per-kernel durations (roofline): the same steps run eagerly with CUDA events around the raster kernels on their
+    # launch stream (events cannot be read back from inside a replayed graph; kernel durations do not depend on how
+    # the launch was submitted)
+    _lib.lib().dbw_timing_reset()
+    _lib.lib().dbw_timing_enable(1)
+    for _ in range(args.steps):
+        flush.zero_()
+        step_eager()
+    barrier()
+    _lib.lib().dbw_timing_enable(0)
     kt = {(kind, kk): _lib.kernel_time_ms(kind, kk) for kind in (0, 1) for kk in (1, K)}
     _lib.lib().dbw_timing_reset()
 
@@ -205,7 +232,8 @@ def run_ours(args):
                                    'K=10, 256^2 textures, coarse phase (sigma=1e-4, per-face opacities); views sharded over ranks '
                                    '(7,6,6,..), one NCCL all-reduce of the flat gradient bucket',
                        'views_per_step': B, 'l2': 'flushed (256 MB memset) between steps, outside the per-step event pairs',
-                       'loss': 'rgb (MSE) only; LPIPS excluded (SURVEY 8d)', 'seed': SEED},
+                       'loss': 'rgb (MSE) only; LPIPS excluded (SURVEY 8d)', 'seed': SEED,
+                       'submission': 'eager' if graphed is None else 'whole step captured once in a CUDA graph and replayed'},
             'e2e': {'value': e2e_value, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
             'clocks': clocks,
@@ -276,10 +304,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='submit the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 5:

@@ -292,7 +292,9 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   const size_t s0 = (size_t)b * 2 * F + f, s1 = s0 + F;
   const float inval[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};     // zmin = 0 < eps -> marked empty
   const float* fu = faces_uvs + (size_t)f * 6;
-  const DbwMapDesc md = map_table[face_map[f]];
+  const int mid = face_map[f];
+  if (mid < 0) r.ntri = 0;                                 // face disabled by the caller (e.g. a killed block): never rasterized
+  const DbwMapDesc md = map_table[mid < 0 ? 0 : mid];
   const float4 uv01 = make_float4(fu[0], fu[1], fu[2], fu[3]);
   const float4 uv2m = make_float4(fu[4], fu[5], __int_as_float(md.offset / 3), __int_as_float((md.height << 16) | md.width));
   write_slot(bbox, rec, rec2, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur, uv01, uv2m);

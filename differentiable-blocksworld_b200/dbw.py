@@ -15,7 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, geometry as G
-from .renderer import Renderer, _c, _stream
+from .renderer import Renderer, render_scene, _c, _stream
 from .structures import Meshes, TexturesUV, join_meshes_as_scene, join_meshes_as_batch
 
 DECIMATE_FACTOR = 8
@@ -33,6 +33,7 @@ class _CompositeMSE(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, fg, env, imgs, n_total_views):
+        ctx.set_materialize_grads(False)          # g_rec arrives as None when `rec` is unused: no zero tensors, no sync
         B, _, H, W = fg.shape
         fg, env, imgs = fg.contiguous(), env.contiguous(), imgs.contiguous().float()
         rec = torch.empty(B, 3, H, W, device=fg.device, dtype=torch.float32)
@@ -47,8 +48,11 @@ class _CompositeMSE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rec, g_loss):
         g_fg, g_env, fg, env = ctx.saved_tensors
-        out_fg, out_env = g_fg * g_loss, g_env * g_loss
-        if g_rec is not None and bool((g_rec != 0).any()):
+        if g_loss is None:
+            out_fg, out_env = torch.zeros_like(g_fg), torch.zeros_like(g_env)
+        else:
+            out_fg, out_env = g_fg * g_loss, g_env * g_loss
+        if g_rec is not None:
             m = fg[:, 3:]
             extra_fg = torch.cat([g_rec * m, (g_rec * (fg[:, :3] - env[:, :3])).sum(1, keepdim=True)], 1)
             extra_env = torch.cat([g_rec * (1 - m), torch.zeros_like(m)], 1)
@@ -71,6 +75,12 @@ class DifferentiableBlocksWorld(nn.Module):
         # data-parallel context (parallel.py): this rank renders `len(inp['imgs'])` of `n_total_views` views
         self.n_total_views = None
         self.noise_generator = None
+        # static topology (default): blocks dropped by the opacity filters (dbw.py:316-328) keep their slot in the mesh
+        # and are DISABLED through face_map = -1 instead of being sliced out -> identical images and gradients, but no
+        # host sync and fixed shapes, so the whole step can be captured in a CUDA graph (graph.py)
+        self.static_topology = True
+        self.opacity_noise_buffer = None          # optional pre-drawn randn (N,) used instead of drawing inside forward
+        self._static_arrays = None
 
     @property
     def init_kwargs(self):
@@ -250,6 +260,16 @@ class DifferentiableBlocksWorld(nn.Module):
         fine_learning = not self.is_live('coarse_learning')
         filter_tsp = filter_transparent or fine_learning
         renderer = self.renderer_fine if fine_learning else self.renderer
+        if self.decouple_rendering and self.static_topology:
+            env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
+            out_env = self.renderer_env(env.extend(B), R=R_tgt, T=T_tgt)
+            verts, faces, fvu, fmap, maps, table = self._blocks_scene_static(filter_tsp)
+            alpha = None if filter_tsp else self._alpha.repeat_interleave(self.BNF)
+            r = renderer
+            out_fg = render_scene(verts, faces, fvu, fmap, maps, table, R_tgt, T_tgt, r.cameras.intrinsics(), r.img_size,
+                                  r.sigma, r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color,
+                                  alpha, r.perspective_correct, blur_radius=r.blur_radius)
+            return out_env, out_fg
         if self.decouple_rendering:
             env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
             out_env = self.renderer_env(env.extend(B), R=R_tgt, T=T_tgt)
@@ -325,13 +345,51 @@ class DifferentiableBlocksWorld(nn.Module):
             maps = self._decimate(maps)
         return Meshes(verts, faces, textures=TexturesUV(maps, faces, self.ground_verts_uvs[None], align_corners=True))
 
+    def _draw_opacity_noise(self):
+        if self.opacity_noise_buffer is not None:
+            return self.opacity_noise_buffer
+        if self.noise_generator is not None:
+            return torch.randn(self.alpha_logit.shape, generator=self.noise_generator, device=self.alpha_logit.device)
+        return torch.randn_like(self.alpha_logit)
+
+    def _blocks_scene_static(self, filter_transparent):
+        """build_blocks(as_scene=True) with fixed shapes: same vertices / maps / opacities, filtered blocks disabled via
+        face_map = -1 (see include/dbw_render.h) instead of removed.  No host synchronisation."""
+        N, dev = self.n_blocks, self.alpha_logit.device
+        coarse_learning = self.training and self.is_live('coarse_learning')
+        S, R, T = self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
+        alpha_logit = self.alpha_logit
+        if self.opacity_noise and coarse_learning:
+            alpha_logit = alpha_logit + self.opacity_noise * self._draw_opacity_noise()
+        self._alpha = torch.sigmoid(alpha_logit)
+        self._alpha_full = self._alpha.clone()
+        maps = torch.sigmoid(self.textures)
+        verts = (self.get_blocks_verts() * S[:, None]) @ R + T[:, None]
+        self._blocks_maps, self._blocks_SRT = maps, (S, R, T)
+        if self._static_arrays is None or self._static_arrays[0].device != dev:
+            faces = (self.blocks.faces_padded() + (torch.arange(N, device=dev) * verts.shape[1])[:, None, None]).reshape(-1, 3)
+            fvu = self.block_verts_uvs[self.block_faces_uvs][None].expand(N, -1, -1, -1).reshape(-1, 3, 2).contiguous()
+            fmap = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF)
+            self._static_arrays = (faces.to(torch.int32).contiguous(), fvu, fmap)
+        faces, fvu, fmap = self._static_arrays
+        if filter_transparent or self.kill_blocks:
+            mask = torch.sigmoid(self.alpha_logit) > (0.5 if filter_transparent else 0.01)
+            self._alpha_full = self._alpha_full * mask
+            fmap = torch.where(mask.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
+        if coarse_learning and self.is_live('decimate_txt'):
+            maps = self._decimate(maps)
+        p_left, p_right = self.txt_padding
+        maps = F.pad(maps.permute(0, 3, 1, 2), pad=(p_left, p_right, 0, 0), mode='circular').permute(0, 2, 3, 1).contiguous()
+        verts = self._to_world(verts).reshape(-1, 3)
+        Ht, Wt = maps.shape[1], maps.shape[2]
+        table = [(i * Ht * Wt * 3, Ht, Wt) for i in range(N)]
+        return verts, faces, fvu, fmap, maps.reshape(-1), table
+
     def build_blocks(self, filter_transparent=False, world_coord=False, as_scene=False):
         coarse_learning = self.training and self.is_live('coarse_learning')
         S, R, T = self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
         if self.opacity_noise and coarse_learning:
-            noise = torch.randn(self.alpha_logit.shape, generator=self.noise_generator, device=self.alpha_logit.device) \
-                if self.noise_generator is not None else torch.randn_like(self.alpha_logit)
-            alpha_logit = self.alpha_logit + self.opacity_noise * noise
+            alpha_logit = self.alpha_logit + self.opacity_noise * self._draw_opacity_noise()
         else:
             alpha_logit = self.alpha_logit
         self._alpha = torch.sigmoid(alpha_logit)
@@ -369,7 +427,7 @@ class DifferentiableBlocksWorld(nn.Module):
 
     # ------------------------------------------------------------------ losses (dbw.py:361-408)
     def compute_losses(self, imgs, rec, rgb_loss=None):
-        losses = {k: torch.tensor(0.0, device=imgs.device) for k in self.loss_weights}
+        losses = {k: torch.zeros((), device=imgs.device) for k in self.loss_weights}
         coarse_learning = self.is_live('coarse_learning')
         if 'rgb' in losses:
             losses['rgb'] = self.loss_weights['rgb'] * (rgb_loss if rgb_loss is not None else self.criterion(imgs, rec))

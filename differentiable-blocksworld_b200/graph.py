@@ -1,0 +1,47 @@
+"""Whole-step CUDA graph: zero the gradient bucket, build the scene, render both passes, composite + loss, and
+back-propagate to every leaf parameter -- captured once on static buffers and replayed per step.  The step is a few
+hundred kernel launches of 2-100 us each (scene construction, two rasterization passes, their backward, the
+reductions); replaying them as one graph removes the launch gaps and the Python/autograd dispatch that otherwise cost
+more than the kernels themselves.  Requires the model's static-topology mode (dbw.py): no host synchronisation and no
+shape that depends on parameter values inside forward()."""
+import torch
+
+
+class GraphedStep:
+    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3):
+        self.vp, self.model = view_parallel, view_parallel.model
+        self.n_total = n_total_views
+        dev = example_inp['imgs'].device
+        self.static_inp = {k: v.clone() for k, v in example_inp.items()}
+        self.model.n_total_views = n_total_views
+        self.model.opacity_noise_buffer = torch.zeros_like(self.model.alpha_logit)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(self.vp.seed)
+        self.model._install_cameras(self.static_inp)          # the one-off host read of the intrinsics happens here
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.losses = self._body()
+
+    def _body(self):
+        self.vp.bucket.zero_()
+        losses = self.model(self.static_inp, None)
+        total = self.vp.weighted_total(losses, len(self.static_inp['imgs']), self.n_total)
+        total.backward()
+        return losses
+
+    def run(self, inp=None, non_blocking=True):
+        """inp: optional dict of (host or device) tensors for this step, copied into the static buffers."""
+        if inp is not None:
+            for k, v in inp.items():
+                if k in self.static_inp:
+                    self.static_inp[k].copy_(v, non_blocking=non_blocking)
+        self.model.opacity_noise_buffer.normal_(generator=self.gen)     # identical on every rank (same seed, same count)
+        self.graph.replay()
+        self.vp.bucket.all_reduce(self.vp.group)
+        return self.losses

@@ -85,13 +85,16 @@ class ViewParallel:
         self._step += 1
         self.bucket.zero_()
         losses = self.model(inp, labels)
-        # view-independent terms are replicated on every rank: rescale so that the SUM over ranks counts them once
+        self.weighted_total(losses, len(inp['imgs']), n_total_views).backward()
+        self.bucket.all_reduce(self.group)
+        return losses
+
+    def weighted_total(self, losses, n_local_views, n_total_views):
+        """the scalar each rank back-propagates: its share of the per-view terms + 1/world of the replicated terms"""
         shared = [v for k, v in losses.items() if k not in ('rgb', 'perceptual', 'total')]
         total = losses['rgb'] if 'rgb' in losses else 0.
         if 'perceptual' in losses:
-            total = total + losses['perceptual'] * (len(inp['imgs']) / float(n_total_views))
+            total = total + losses['perceptual'] * (n_local_views / float(n_total_views))
         if shared:
             total = total + sum(shared) / self.world_size
-        total.backward()
-        self.bucket.all_reduce(self.group)
-        return losses
+        return total

@@ -24,6 +24,7 @@ class _Cameras:
 
     def __init__(self, name='fov', device=None, K=None, fov=60.0, **unused):
         self.name, self.K, self.device, self.fov = name, K, device, fov
+        self._intr = None          # host copy of (fx, fy, px, py): read once, so that forward() never syncs
 
     def to(self, device):
         self.device = device
@@ -33,9 +34,12 @@ class _Cameras:
 
     def intrinsics(self):
         """(fx, fy, px, py) of the NDC projection x_ndc = fx X/Z + px."""
+        if self._intr is not None:
+            return self._intr
         if self.K is not None:
             K = self.K.reshape(-1, 4, 4)[0].detach().cpu()
-            return float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2])
+            self._intr = (float(K[0, 0]), float(K[1, 1]), float(K[0, 2]), float(K[1, 2]))
+            return self._intr
         if self.name == 'perspective':
             return 1.0, 1.0, 0.0, 0.0                   # PerspectiveCameras defaults: focal_length=1, principal_point=0
         f = 1.0 / np.tan(np.deg2rad(self.fov) / 2)      # FoVPerspectiveCameras, aspect 1
@@ -94,6 +98,18 @@ class _RenderFn(torch.autograd.Function):
         return g_verts, g_maps, g_fa, None, None, None, None, None, None, None
 
 
+_TABLE_CACHE = {}
+
+
+def _device_map_table(table_host, dev):
+    """(M) DbwMapDesc on the device, cached per (layout, device): built once, so that steady-state calls do no H2D."""
+    key = (tuple(table_host), str(dev))
+    if key not in _TABLE_CACHE:
+        table = (DbwMapDesc * len(table_host))(*[DbwMapDesc(int(o), int(h), int(w), 0) for o, h, w in table_host])
+        _TABLE_CACHE[key] = torch.frombuffer(bytearray(bytes(table)), dtype=torch.int32).to(dev)
+    return _TABLE_CACHE[key]
+
+
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
                   perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
                   n_map_floats=0):
@@ -122,8 +138,7 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     V = verts.shape[-2]
     Fn = faces.shape[0]
     dev = verts.device
-    table = (DbwMapDesc * len(map_table_host))(*[DbwMapDesc(int(o), int(h), int(w), 0) for o, h, w in map_table_host])
-    map_table = torch.frombuffer(bytearray(bytes(table)), dtype=torch.int32).to(dev)
+    map_table = _device_map_table(map_table_host, dev)
     alpha_stride = 0
     if faces_alpha is not None:
         if faces_alpha.numel() == B * Fn and B > 1:

@@ -75,7 +75,8 @@ int dbw_workspace_bytes(const DbwRenderSettings* settings, size_t* fwd_bytes, si
  *   verts        (V,3) world-space vertices   [or (B,V,3) NDC when settings->verts_are_ndc]
  *   faces        (F,3) int32 vertex ids
  *   faces_uvs    (F,3,2) per-face-vertex UVs = verts_uvs[faces_uvs] of TexturesUV (src/model/dbw.py:280,295,342)
- *   face_map     (F) int32 texture map of each face
+ *   face_map     (F) int32 texture map of each face; a NEGATIVE entry disables the face (it is never rasterized and gets
+ *                no gradient) -- how a static-topology caller drops low-opacity blocks (src/model/dbw.py:316-328)
  *   maps, map_table  packed maps + (M) DbwMapDesc (device)
  *   R (B,3,3), T (B,3)  row-vector convention X_view = X_world @ R + T (src/dataset/dtu.py:75-124)
  *   faces_alpha  NULL, or per-face opacity (src/model/dbw.py:219, renderer.py:258-260), see alpha_view_stride

@@ -47,7 +47,7 @@ def test_invalid_arguments_fail_loudly_without_a_gpu():
     s = make_settings(1, 8, 8, 100, 3, 1, 1, 0, (1, 1, 0, 0), 0., 0., None, (0, 0, 0))      # K = 100 > 64
     rc = L.dbw_render_forward(ctypes.byref(s), *([None] * 12), 0, None)
     assert rc != 0 and b'faces_per_pixel' in L.dbw_last_error()
-    s = make_settings(1, 8, 8, 4, 3, 1, 1, 0, (1, 1, 0, 0), 0., 0., None, (0, 0, 0))
+    s = make_settings(1, 8, 8, 4, 3, 1, 1, 0, (1, 1, 0, 0), 0., 0., None, (0, 0, 0), n_map_floats=12)
     rc = L.dbw_render_forward(ctypes.byref(s), *([None] * 12), 0, None)
     assert rc != 0 and b'null pointer' in L.dbw_last_error()
 

@@ -93,3 +93,46 @@ def test_full_loss_dict_runs_and_is_finite():
     losses['total'].backward()
     for n, prm in model.named_parameters():
         assert prm.grad is not None and torch.isfinite(prm.grad).all(), n
+
+
+def test_static_topology_equals_filtered_meshes():
+    """blocks dropped by the opacity filters: disabling their faces (static shapes, no host sync) == removing them."""
+    model, tpl, p, dev = _model_and_oracle(fine=True)
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    outs = []
+    for static in (True, False):
+        model.static_topology = static
+        model.zero_grad(set_to_none=True)
+        losses = model(inp, None)
+        losses['total'].backward()
+        outs.append((losses['rgb'].item(), {n: prm.grad.clone() for n, prm in model.named_parameters() if prm.grad is not None}))
+    assert abs(outs[0][0] - outs[1][0]) < 1e-7
+    for n in outs[1][1]:
+        a, b = outs[0][1][n], outs[1][1][n]
+        assert (a - b).norm() <= 1e-4 * b.norm() + 1e-12, n
+
+
+def test_cuda_graph_step_equals_eager_step():
+    from dbw_b200.parallel import ViewParallel
+    from dbw_b200.graph import GraphedStep
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    vp = ViewParallel(model, seed=5)
+    graphed = GraphedStep(vp, inp, len(inp['imgs']))
+    losses = graphed.run()
+    g_graph = vp.bucket.flat.clone()
+    noise = model.opacity_noise_buffer.clone()
+    l_graph = losses['rgb'].item()
+    # eager step with the same noise
+    model.opacity_noise_buffer = noise
+    vp.bucket.zero_()
+    l = model(inp, None)
+    l['total'].backward()
+    assert abs(l['rgb'].item() - l_graph) < 1e-7
+    assert (vp.bucket.flat - g_graph).norm() <= 1e-4 * g_graph.norm()
+    # replay with new inputs changes the result, and is repeatable
+    inp2 = {k: (v.flip(0).contiguous() if k in ('imgs',) else v) for k, v in inp.items()}
+    l2 = graphed.run(inp2)['rgb'].item()
+    assert abs(l2 - l_graph) > 1e-9
