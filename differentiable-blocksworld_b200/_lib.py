@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdbw_render.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class DbwRenderSettings(ctypes.Structure):
@@ -19,8 +19,17 @@ class DbwRenderSettings(ctypes.Structure):
         ('proj_eps', ctypes.c_float), ('background', ctypes.c_float * 3),
         ('clip_inside', ctypes.c_int32), ('perspective_correct', ctypes.c_int32),
         ('clip_barycentric', ctypes.c_int32), ('detach_bary', ctypes.c_int32), ('verts_are_ndc', ctypes.c_int32),
-        ('n_map_floats', ctypes.c_int32),
+        ('n_map_floats', ctypes.c_int32), ('maps_are_texels4', ctypes.c_int32),
     ]
+
+
+class DbwSceneGeometry(ctypes.Structure):
+    _fields_ = [('n_blocks', ctypes.c_int32), ('verts_per_block', ctypes.c_int32), ('n_ground_verts', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)] \
+             + [(n, ctypes.c_void_p) for n in ('sq_eta', 'sq_omega', 'sq_eps', 'S', 'R_6d', 'T', 'ground_verts',
+                                               'R_6d_ground', 'T_ground')] \
+             + [('ratio_block_scene', ctypes.c_float), ('scale_min', ctypes.c_float), ('S_world', ctypes.c_float),
+                ('R_world', ctypes.c_float * 9), ('T_world', ctypes.c_float * 3)]
 
 
 class DbwMapDesc(ctypes.Structure):
@@ -30,7 +39,8 @@ class DbwMapDesc(ctypes.Structure):
 
 EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_backward',
            'dbw_composite_mse', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
-           'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset']
+           'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
+           'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward']
 
 _lib = None
 
@@ -57,6 +67,10 @@ def lib():
         L.dbw_composite_mse.argtypes = [ctypes.c_int32] * 3 + [vp] * 3 + [ctypes.c_float] + [vp] * 5
         L.dbw_render_forward_host.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 5 + [sz] + [vp] * 6
         L.dbw_host_arena_release.restype = None
+        L.dbw_scene_geometry_forward.argtypes = [ctypes.POINTER(DbwSceneGeometry), vp, vp]
+        L.dbw_scene_geometry_backward.argtypes = [ctypes.POINTER(DbwSceneGeometry)] + [vp] * 8
+        L.dbw_texture_prep_forward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp]
+        L.dbw_texture_prep_backward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp, vp]
         L.dbw_timing_enable.restype = None
         L.dbw_timing_reset.restype = None
         L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]

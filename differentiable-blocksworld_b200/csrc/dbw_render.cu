@@ -36,6 +36,9 @@ static int fail(const char* what, cudaError_t e = cudaSuccess) {
   else snprintf(g_err, sizeof(g_err), "%s", what);
   return -1;
 }
+// shared with dbw_scene.cu
+int dbw_fail_(const char* what, cudaError_t e) { return fail(what, e); }
+void dbw_count_launch_(void) { ++g_launches; }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(#call, _e); } while (0)
 #define LAUNCH_CK(name) do { ++g_launches; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail(name, _e); } while (0)
 
@@ -89,7 +92,7 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.rec2 = (float4*)(p + off);     off += align_up(B * S * 2 * sizeof(float4));
   w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
-  w.maps4 = (float4*)(p + off);    off += align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
+  w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   w.total = off; return w;
 }
 struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; float4* g_maps4; size_t total; };
@@ -99,7 +102,7 @@ static BwdScratch carve_bwd(const DbwRenderSettings& s, void* base) {
   w.g_tri = (float*)(p + off);        off += align_up(B * S * 9 * sizeof(float));
   w.g_conv = (float*)(p + off);       off += align_up(B * S * 9 * sizeof(float));
   w.g_verts_ndc = (float*)(p + off);  off += align_up(B * V * 3 * sizeof(float));
-  w.g_maps4 = (float4*)(p + off);     off += align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
+  w.g_maps4 = (float4*)(p + off);     off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   w.total = off; return w;
 }
 
@@ -906,13 +909,14 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
                                                          sqrtf(s->blur_radius), faces_uvs, face_map, map_table, w.bbox, w.rec,
                                                          w.rec2, w.conv, w.view_flags);
   LAUNCH_CK("face_setup_kernel");
-  {
+  if (!s->maps_are_texels4) {
     const int n_texels = s->n_map_floats / 3;
     int blocks = (n_texels + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
     maps_to_float4_kernel<<<blocks, 256, 0, st>>>(maps, w.maps4, n_texels);
     LAUNCH_CK("maps_to_float4_kernel");
   }
   RasterParams P = make_params(*s, w, faces_alpha);
+  if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.out_rgba = out_rgba; P.topk = topk_ids;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const int K = s->faces_per_pixel;
@@ -944,8 +948,9 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   const bool need_geom = g_verts != nullptr;
   CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
   RasterParams P = make_params(*s, w, faces_alpha);
+  if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
-  P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? g.g_maps4 : nullptr;
+  P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
   { const char* e = getenv("DBW_DEBUG_SKIP"); P.debug_skip = e ? atoi(e) : 0; }
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
@@ -962,7 +967,7 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
     if (e != cudaSuccess) return fail("raster_backward_kernel attribute", e);
   }
   LAUNCH_CK("raster_backward_kernel");
-  if (g_maps) {
+  if (g_maps && !s->maps_are_texels4) {
     const int n_texels = s->n_map_floats / 3;
     int blocks = (n_texels + 255) / 256; if (blocks > 148 * 8) blocks = 148 * 8;
     fold_gmaps_kernel<<<blocks, 256, 0, st>>>(g.g_maps4, g_maps, n_texels);

@@ -1,0 +1,329 @@
+// dbw_scene.cu -- fused scene construction of the DBW render hot path (include/dbw_render.h, "scene" entry points).
+//
+// Replaces the ~200 small eager kernels per step of the reference's build_blocks / build_ground / build_bkg
+// (src/model/dbw.py:267-352) and their autograd:
+//   * superquadric mesh build: sq_eps -> parametric superquadric (src/utils/superquadric.py:10-14) -> * ratio * (exp(S)+s_min)
+//     -> @ rot6d(R_6d) + T -> world transform (dbw.py:311,344), for the N blocks AND the ground plane, ONE launch;
+//     backward: one CTA per primitive reduces its vertices' gradients into (sq_eps, S, R_6d, T) without atomics;
+//   * texture prep: sigmoid -> optional 8x8 box decimation (avg_pool + nearest upsample, dbw.py:331-334) -> circular u
+//     padding (dbw.py:339-341) written straight into the float4 texel atlas the rasterizer samples; backward folds the
+//     atlas gradient through padding, decimation and the sigmoid.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/dbw_render.h"
+
+extern int dbw_fail_(const char* what, cudaError_t e);
+extern void dbw_count_launch_(void);
+#define SCENE_LAUNCH_CK(name) do { dbw_count_launch_(); cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return dbw_fail_(name, _e); } while (0)
+
+// ------------------------------------------------------------------------------------------------ geometry
+struct Mat3 { float m[9]; };
+
+__device__ __forceinline__ float spow(float x, float e) {        // sign(x) * |x|^e   (utils/pytorch.py:31-32)
+  const float a = fabsf(x);
+  if (a == 0.f) return 0.f;
+  return copysignf(powf(a, e), x);
+}
+
+// rotation_6d_to_matrix: rows b1 = a1/|a1|, b2 = normalize(a2 - (b1.a2) b1), b3 = b1 x b2
+__device__ __forceinline__ void rot6d(const float* d6, float* R) {
+  const float n1 = fmaxf(sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]), 1e-12f);
+  const float b1x = d6[0] / n1, b1y = d6[1] / n1, b1z = d6[2] / n1;
+  const float d = b1x * d6[3] + b1y * d6[4] + b1z * d6[5];
+  const float ux = d6[3] - d * b1x, uy = d6[4] - d * b1y, uz = d6[5] - d * b1z;
+  const float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+  const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+  R[0] = b1x; R[1] = b1y; R[2] = b1z; R[3] = b2x; R[4] = b2y; R[5] = b2z;
+  R[6] = b1y * b2z - b1z * b2y; R[7] = b1z * b2x - b1x * b2z; R[8] = b1x * b2y - b1y * b2x;
+}
+
+__device__ __forceinline__ void rot6d_backward(const float* d6, const float* gR, float* gd6) {
+  const float n1 = fmaxf(sqrtf(d6[0] * d6[0] + d6[1] * d6[1] + d6[2] * d6[2]), 1e-12f);
+  const float b1[3] = {d6[0] / n1, d6[1] / n1, d6[2] / n1};
+  const float d = b1[0] * d6[3] + b1[1] * d6[4] + b1[2] * d6[5];
+  const float u[3] = {d6[3] - d * b1[0], d6[4] - d * b1[1], d6[5] - d * b1[2]};
+  const float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+  const float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
+  float gb1[3] = {gR[0], gR[1], gR[2]}, gb2[3] = {gR[3], gR[4], gR[5]};
+  const float gb3[3] = {gR[6], gR[7], gR[8]};
+  // b3 = b1 x b2 :  d/db1 = b2 x g3 ,  d/db2 = g3 x b1
+  gb1[0] += b2[1] * gb3[2] - b2[2] * gb3[1]; gb1[1] += b2[2] * gb3[0] - b2[0] * gb3[2]; gb1[2] += b2[0] * gb3[1] - b2[1] * gb3[0];
+  gb2[0] += gb3[1] * b1[2] - gb3[2] * b1[1]; gb2[1] += gb3[2] * b1[0] - gb3[0] * b1[2]; gb2[2] += gb3[0] * b1[1] - gb3[1] * b1[0];
+  // b2 = u / |u|
+  const float gdot2 = gb2[0] * b2[0] + gb2[1] * b2[1] + gb2[2] * b2[2];
+  const float gu[3] = {(gb2[0] - gdot2 * b2[0]) / n2, (gb2[1] - gdot2 * b2[1]) / n2, (gb2[2] - gdot2 * b2[2]) / n2};
+  // u = a2 - (b1.a2) b1
+  const float gub1 = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
+  gd6[3] = gu[0] - gub1 * b1[0]; gd6[4] = gu[1] - gub1 * b1[1]; gd6[5] = gu[2] - gub1 * b1[2];
+  gb1[0] += -d * gu[0] - gub1 * d6[3]; gb1[1] += -d * gu[1] - gub1 * d6[4]; gb1[2] += -d * gu[2] - gub1 * d6[5];
+  // b1 = a1 / |a1|
+  const float gdot1 = gb1[0] * b1[0] + gb1[1] * b1[1] + gb1[2] * b1[2];
+  gd6[0] = (gb1[0] - gdot1 * b1[0]) / n1; gd6[1] = (gb1[1] - gdot1 * b1[1]) / n1; gd6[2] = (gb1[2] - gdot1 * b1[2]) / n1;
+}
+
+struct GeomParams {
+  int n_blocks, verts_per_block, n_ground_verts;
+  const float* sq_eta; const float* sq_omega;        // (N, Vb)
+  const float* sq_eps; const float* S; const float* R6; const float* T;   // (N,2) (N,3) (N,6) (N,3)
+  const float* ground_verts; const float* R6g; const float* Tg;          // (Vg,3) (6) (3)
+  float ratio, scale_min, S_world;
+  Mat3 R_world; float T_world[3];
+};
+
+// unit-scale vertex of primitive `prim` (block: parametric superquadric * ratio; ground: its static plane vertex)
+__device__ __forceinline__ void local_vertex(const GeomParams& P, int prim, int v, float* u, float* aux /*ce,se,co,so,e1,e2*/) {
+  if (prim < P.n_blocks) {
+    const float e1 = 1.8f / (1.f + expf(-P.sq_eps[prim * 2])) + 0.1f;
+    const float e2 = 1.8f / (1.f + expf(-P.sq_eps[prim * 2 + 1])) + 0.1f;
+    const float eta = P.sq_eta[prim * P.verts_per_block + v], om = P.sq_omega[prim * P.verts_per_block + v];
+    const float ce = spow(cosf(eta), e1), se = spow(sinf(eta), e1), co = spow(cosf(om), e2), so = spow(sinf(om), e2);
+    u[0] = ce * so * P.ratio; u[1] = se * P.ratio; u[2] = ce * co * P.ratio;
+    aux[0] = ce; aux[1] = se; aux[2] = co; aux[3] = so; aux[4] = e1; aux[5] = e2;
+  } else {
+    u[0] = P.ground_verts[v * 3]; u[1] = P.ground_verts[v * 3 + 1]; u[2] = P.ground_verts[v * 3 + 2];
+  }
+}
+
+// out: (N*Vb + Vg, 3) world-space vertices, blocks first then the ground
+__global__ void scene_geometry_forward_kernel(const GeomParams P, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = P.n_blocks * P.verts_per_block;
+  if (i >= nb + P.n_ground_verts) return;
+  const int prim = i < nb ? i / P.verts_per_block : P.n_blocks;
+  const int v = i < nb ? i - prim * P.verts_per_block : i - nb;
+  float u[3], aux[6], R[9], sc[3] = {1.f, 1.f, 1.f};
+  local_vertex(P, prim, v, u, aux);
+  const float* T;
+  if (prim < P.n_blocks) {
+    rot6d(P.R6 + prim * 6, R);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sc[c] = expf(P.S[prim * 3 + c]) + P.scale_min;
+    T = P.T + prim * 3;
+  } else { rot6d(P.R6g, R); T = P.Tg; }
+  const float x = u[0] * sc[0], y = u[1] * sc[1], z = u[2] * sc[2];
+  // row vector times matrix (dbw.py:311), then the world transform (dbw.py:344)
+  const float px = (x * R[0] + y * R[3] + z * R[6] + T[0]) * P.S_world;
+  const float py = (x * R[1] + y * R[4] + z * R[7] + T[1]) * P.S_world;
+  const float pz = (x * R[2] + y * R[5] + z * R[8] + T[2]) * P.S_world;
+  const float* W = P.R_world.m;
+  out[i * 3 + 0] = px * W[0] + py * W[3] + pz * W[6] + P.T_world[0];
+  out[i * 3 + 1] = px * W[1] + py * W[4] + pz * W[7] + P.T_world[1];
+  out[i * 3 + 2] = px * W[2] + py * W[5] + pz * W[8] + P.T_world[2];
+}
+
+// one CTA (64 threads) per primitive; outputs are WRITTEN (not accumulated)
+__global__ void __launch_bounds__(64) scene_geometry_backward_kernel(const GeomParams P, const float* __restrict__ g_out,
+                                                                     float* __restrict__ g_sq_eps, float* __restrict__ g_S,
+                                                                     float* __restrict__ g_R6, float* __restrict__ g_T,
+                                                                     float* __restrict__ g_R6g, float* __restrict__ g_Tg) {
+  const int prim = blockIdx.x, v = threadIdx.x;
+  const bool is_block = prim < P.n_blocks;
+  const int nv = is_block ? P.verts_per_block : P.n_ground_verts;
+  float R[9], sc[3] = {1.f, 1.f, 1.f};
+  rot6d(is_block ? P.R6 + prim * 6 : P.R6g, R);
+  if (is_block) for (int c = 0; c < 3; ++c) sc[c] = expf(P.S[prim * 3 + c]) + P.scale_min;
+  // per-thread partial sums: gT(3) gR(9) gS(3) ge(2)
+  float acc[17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) acc[k] = 0.f;
+  for (int vv = v; vv < nv; vv += 64) {
+    float u[3], aux[6] = {0, 0, 0, 0, 1, 1};
+    local_vertex(P, prim, vv, u, aux);
+    const int i = is_block ? prim * P.verts_per_block + vv : P.n_blocks * P.verts_per_block + vv;
+    const float gx = g_out[i * 3], gy = g_out[i * 3 + 1], gz = g_out[i * 3 + 2];
+    const float* W = P.R_world.m;
+    // world transform backward: g_p = S_world * (g @ R_world^T)
+    const float gp[3] = {(gx * W[0] + gy * W[1] + gz * W[2]) * P.S_world, (gx * W[3] + gy * W[4] + gz * W[5]) * P.S_world,
+                         (gx * W[6] + gy * W[7] + gz * W[8]) * P.S_world};
+    const float xs[3] = {u[0] * sc[0], u[1] * sc[1], u[2] * sc[2]};
+    acc[0] += gp[0]; acc[1] += gp[1]; acc[2] += gp[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) acc[3 + a * 3 + b] += xs[a] * gp[b];
+    if (is_block) {
+      // g wrt the scaled vertex, then scale and superquadric exponents
+      const float gxs[3] = {R[0] * gp[0] + R[1] * gp[1] + R[2] * gp[2], R[3] * gp[0] + R[4] * gp[1] + R[5] * gp[2],
+                            R[6] * gp[0] + R[7] * gp[1] + R[8] * gp[2]};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[12 + c] += gxs[c] * u[c] * (sc[c] - P.scale_min);       // d exp(S) = exp(S)
+      const float gu[3] = {gxs[0] * sc[0] * P.ratio, gxs[1] * sc[1] * P.ratio, gxs[2] * sc[2] * P.ratio};
+      const float ce = aux[0], se = aux[1], co = aux[2], so = aux[3];
+      const float g_ce = gu[0] * so + gu[2] * co, g_so = gu[0] * ce, g_se = gu[1], g_co = gu[2] * ce;
+      const float eta = P.sq_eta[prim * P.verts_per_block + vv], om = P.sq_omega[prim * P.verts_per_block + vv];
+      const float ace = fabsf(cosf(eta)), ase = fabsf(sinf(eta)), aco = fabsf(cosf(om)), aso = fabsf(sinf(om));
+      // d/de sign(x)|x|^e = sign(x)|x|^e ln|x|, with torch's convention 0 where |x| == 0
+      acc[15] += (ace > 0.f ? g_ce * ce * logf(ace) : 0.f) + (ase > 0.f ? g_se * se * logf(ase) : 0.f);
+      acc[16] += (aco > 0.f ? g_co * co * logf(aco) : 0.f) + (aso > 0.f ? g_so * so * logf(aso) : 0.f);
+    }
+  }
+  __shared__ float red[2][17];
+#pragma unroll
+  for (int k = 0; k < 17; ++k) {
+    float x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) t[k] = red[0][k] + red[1][k];
+    float gd6[6];
+    rot6d_backward(is_block ? P.R6 + prim * 6 : P.R6g, t + 3, gd6);
+    if (is_block) {
+      for (int c = 0; c < 3; ++c) { g_T[prim * 3 + c] = t[c]; g_S[prim * 3 + c] = t[12 + c]; }
+      for (int c = 0; c < 6; ++c) g_R6[prim * 6 + c] = gd6[c];
+      for (int c = 0; c < 2; ++c) {
+        const float sg = 1.f / (1.f + expf(-P.sq_eps[prim * 2 + c]));
+        g_sq_eps[prim * 2 + c] = t[15 + c] * 1.8f * sg * (1.f - sg);
+      }
+    } else {
+      for (int c = 0; c < 3; ++c) g_Tg[c] = t[c];
+      for (int c = 0; c < 6; ++c) g_R6g[c] = gd6[c];
+    }
+  }
+}
+
+static GeomParams make_geom(const DbwSceneGeometry* g) {
+  GeomParams P;
+  P.n_blocks = g->n_blocks; P.verts_per_block = g->verts_per_block; P.n_ground_verts = g->n_ground_verts;
+  P.sq_eta = g->sq_eta; P.sq_omega = g->sq_omega; P.sq_eps = g->sq_eps; P.S = g->S; P.R6 = g->R_6d; P.T = g->T;
+  P.ground_verts = g->ground_verts; P.R6g = g->R_6d_ground; P.Tg = g->T_ground;
+  P.ratio = g->ratio_block_scene; P.scale_min = g->scale_min; P.S_world = g->S_world;
+  for (int i = 0; i < 9; ++i) P.R_world.m[i] = g->R_world[i];
+  for (int i = 0; i < 3; ++i) P.T_world[i] = g->T_world[i];
+  return P;
+}
+
+extern "C" int dbw_scene_geometry_forward(const DbwSceneGeometry* g, float* verts_out, void* stream) {
+  if (!g || !verts_out) return dbw_fail_("dbw_scene_geometry_forward: null pointer argument", cudaSuccess);
+  if (g->n_blocks < 0 || g->verts_per_block <= 0 || g->n_ground_verts < 0 || g->verts_per_block > 4096)
+    return dbw_fail_("dbw_scene_geometry_forward: bad sizes", cudaSuccess);
+  const int n = g->n_blocks * g->verts_per_block + g->n_ground_verts;
+  if (n == 0) return 0;
+  scene_geometry_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_geom(g), verts_out);
+  SCENE_LAUNCH_CK("scene_geometry_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const float* g_verts, float* g_sq_eps, float* g_S,
+                                           float* g_R_6d, float* g_T, float* g_R_6d_ground, float* g_T_ground, void* stream) {
+  if (!g || !g_verts) return dbw_fail_("dbw_scene_geometry_backward: null pointer argument", cudaSuccess);
+  const int prims = g->n_blocks + (g->n_ground_verts > 0 ? 1 : 0);
+  if (prims == 0) return 0;
+  scene_geometry_backward_kernel<<<prims, 64, 0, (cudaStream_t)stream>>>(make_geom(g), g_verts, g_sq_eps, g_S, g_R_6d, g_T,
+                                                                         g_R_6d_ground, g_T_ground);
+  SCENE_LAUNCH_CK("scene_geometry_backward_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ textures
+// one thread per SOURCE texel (m, y, x); decimation cells are f x f (f = 1: none) and never straddle a warp row segment:
+// with f = 8 each run of 8 lanes shares a cell column, rows are combined through shared memory.
+__global__ void texture_prep_forward_kernel(const float* __restrict__ tex, int M, int TS, int p_left, int p_right, int f,
+                                            float4* __restrict__ atlas) {
+  // block = (32, 8): 32 texels along x, 8 rows -> with f = 8 a block holds 4 complete cells
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z;
+  __shared__ float s_sum[8][32][3];
+  float s[3] = {0.f, 0.f, 0.f};
+  const bool ok = x < TS && y < TS;
+  if (ok) {
+    const float* t = tex + (((size_t)m * TS + y) * TS + x) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s[c] = 1.f / (1.f + expf(-t[c]));
+  }
+  if (f == 8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = s[c];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      s_sum[threadIdx.y][threadIdx.x][c] = v;          // sum over the 8 lanes of this row segment
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += s_sum[r][threadIdx.x][c];
+      s[c] = v * (1.f / 64.f);
+    }
+  }
+  if (!ok) return;
+  const int Wp = TS + p_left + p_right;
+  float4* row = atlas + ((size_t)m * TS + y) * Wp;
+  const float4 val = make_float4(s[0], s[1], s[2], 0.f);
+  row[x + p_left] = val;
+  if (x < p_right) row[TS + p_left + x] = val;               // circular padding on the right: columns 0..p_right-1
+  if (x >= TS - p_left) row[x - (TS - p_left)] = val;        // and on the left: the last p_left columns
+}
+
+__global__ void texture_prep_backward_kernel(const float* __restrict__ tex, int M, int TS, int p_left, int p_right, int f,
+                                             const float4* __restrict__ g_atlas, float* __restrict__ g_tex) {
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z;
+  __shared__ float s_sum[8][32][3];
+  const bool ok = x < TS && y < TS;
+  float g[3] = {0.f, 0.f, 0.f};
+  if (ok) {
+    const int Wp = TS + p_left + p_right;
+    const float4* row = g_atlas + ((size_t)m * TS + y) * Wp;
+    float4 a = row[x + p_left];
+    g[0] = a.x; g[1] = a.y; g[2] = a.z;
+    if (x < p_right) { a = row[TS + p_left + x]; g[0] += a.x; g[1] += a.y; g[2] += a.z; }
+    if (x >= TS - p_left) { a = row[x - (TS - p_left)]; g[0] += a.x; g[1] += a.y; g[2] += a.z; }
+  }
+  if (f == 8) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = g[c];
+      v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+      s_sum[threadIdx.y][threadIdx.x][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v += s_sum[r][threadIdx.x][c];
+      g[c] = v * (1.f / 64.f);
+    }
+  }
+  if (!ok) return;
+  const size_t o = (((size_t)m * TS + y) * TS + x) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float sg = 1.f / (1.f + expf(-tex[o + c]));
+    g_tex[o + c] = g[c] * sg * (1.f - sg);
+  }
+}
+
+static int check_tex(const char* who, int M, int TS, int p_left, int p_right, int f) {
+  if (M <= 0 || TS <= 0 || p_left < 0 || p_right < 0 || p_left > TS || p_right > TS) return dbw_fail_(who, cudaSuccess);
+  if (f != 1 && f != 8) return dbw_fail_("texture prep: decimate factor must be 1 or 8", cudaSuccess);
+  if (f == 8 && TS % 8 != 0) return dbw_fail_("texture prep: txt_size must be a multiple of the decimation factor", cudaSuccess);
+  return 0;
+}
+
+extern "C" int dbw_texture_prep_forward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
+                                        int32_t decimate, float* atlas_out, void* stream) {
+  if (!textures || !atlas_out) return dbw_fail_("dbw_texture_prep_forward: null pointer argument", cudaSuccess);
+  if (check_tex("dbw_texture_prep_forward: bad sizes", n_maps, txt_size, p_left, p_right, decimate)) return -1;
+  dim3 grid((txt_size + 31) / 32, (txt_size + 7) / 8, n_maps), block(32, 8);
+  texture_prep_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(textures, n_maps, txt_size, p_left, p_right, decimate, (float4*)atlas_out);
+  SCENE_LAUNCH_CK("texture_prep_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_texture_prep_backward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
+                                         int32_t decimate, const float* g_atlas, float* g_textures, void* stream) {
+  if (!textures || !g_atlas || !g_textures) return dbw_fail_("dbw_texture_prep_backward: null pointer argument", cudaSuccess);
+  if (check_tex("dbw_texture_prep_backward: bad sizes", n_maps, txt_size, p_left, p_right, decimate)) return -1;
+  dim3 grid((txt_size + 31) / 32, (txt_size + 7) / 8, n_maps), block(32, 8);
+  texture_prep_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(textures, n_maps, txt_size, p_left, p_right, decimate,
+                                                                         (const float4*)g_atlas, g_textures);
+  SCENE_LAUNCH_CK("texture_prep_backward_kernel");
+  return 0;
+}

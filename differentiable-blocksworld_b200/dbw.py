@@ -16,6 +16,7 @@ import torch.nn.functional as F
 
 from . import _lib, geometry as G
 from .renderer import Renderer, render_scene, _c, _stream
+from .scene_ops import scene_geometry, texture_atlas
 from .structures import Meshes, TexturesUV, join_meshes_as_scene, join_meshes_as_batch
 
 DECIMATE_FACTOR = 8
@@ -81,6 +82,9 @@ class DifferentiableBlocksWorld(nn.Module):
         self.static_topology = True
         self.opacity_noise_buffer = None          # optional pre-drawn randn (N,) used instead of drawing inside forward
         self._static_arrays = None
+        # fused scene construction (scene_ops.py): mesh build + texture prep as one kernel each way
+        self.fused_scene = True
+        self._fused_static = None
 
     @property
     def init_kwargs(self):
@@ -260,6 +264,8 @@ class DifferentiableBlocksWorld(nn.Module):
         fine_learning = not self.is_live('coarse_learning')
         filter_tsp = filter_transparent or fine_learning
         renderer = self.renderer_fine if fine_learning else self.renderer
+        if self.decouple_rendering and self.static_topology and self.fused_scene and R_tgt.is_cuda:
+            return self._render_layers_fused(B, R_tgt, T_tgt, filter_tsp, renderer)
         if self.decouple_rendering and self.static_topology:
             env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
             out_env = self.renderer_env(env.extend(B), R=R_tgt, T=T_tgt)
@@ -345,6 +351,81 @@ class DifferentiableBlocksWorld(nn.Module):
             maps = self._decimate(maps)
         return Meshes(verts, faces, textures=TexturesUV(maps, faces, self.ground_verts_uvs[None], align_corners=True))
 
+    def _fused_arrays(self):
+        dev = self.alpha_logit.device
+        if self._fused_static is None or self._fused_static['dev'] != dev:
+            N, Vb = self.n_blocks, self.sq_eta.shape[1]
+            gv, gf = self.ground.get_mesh_verts_faces(0)
+            bv, bf = self.bkg.get_mesh_verts_faces(0)
+            geom = {'n_blocks': N, 'verts_per_block': Vb, 'n_ground_verts': gv.shape[0], 'sq_eta': self.sq_eta.contiguous(),
+                    'sq_omega': self.sq_omega.contiguous(), 'ground_verts': gv.contiguous().float(),
+                    'ratio': float(self.ratio_block_scene), 'scale_min': float(self.scale_min), 'S_world': float(self.S_world),
+                    'R_world': [float(x) for x in self.R_world.reshape(-1).cpu()], 'T_world': [float(x) for x in self.T_world.reshape(-1).cpu()]}
+            bkg_world = self._to_world(bv[None])[0].contiguous()             # static: no learnable pose
+            faces_b = (self.blocks.faces_padded() + (torch.arange(N, device=dev) * Vb)[:, None, None]).reshape(-1, 3)
+            fvu_b = self.block_verts_uvs[self.block_faces_uvs][None].expand(N, -1, -1, -1).reshape(-1, 3, 2).contiguous()
+            fmap_b = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF)
+            faces_e = torch.cat([bf, gf + bv.shape[0]]).to(torch.int32).contiguous()
+            fvu_e = torch.cat([self.bkg_verts_uvs[bf], self.ground_verts_uvs[gf]]).contiguous()
+            fmap_e = torch.cat([torch.zeros(len(bf)), torch.ones(len(gf))]).to(dev).to(torch.int32)
+            self._fused_static = {'dev': dev, 'geom': geom, 'bkg_world': bkg_world, 'faces_b': faces_b.to(torch.int32).contiguous(),
+                                  'fvu_b': fvu_b, 'fmap_b': fmap_b, 'faces_e': faces_e, 'fvu_e': fvu_e, 'fmap_e': fmap_e}
+        return self._fused_static
+
+    def _render_layers_fused(self, B, R_tgt, T_tgt, filter_tsp, renderer):
+        """decoupled rendering with the fused scene kernels: leaf parameters -> 2 scene kernels -> 2 render passes."""
+        st = self._fused_arrays()
+        N, Vb = self.n_blocks, st['geom']['verts_per_block']
+        coarse_learning = self.training and self.is_live('coarse_learning')
+        decim = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
+        verts = scene_geometry(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground, st['geom'])
+        # ---- environment pass (bkg sphere is static, the ground follows R_6d_ground / T_ground)
+        env_verts = torch.cat([st['bkg_world'], verts[N * Vb:]])
+        tb, tg = texture_atlas(self.texture_bkg, 0, 0, decim), texture_atlas(self.texture_ground, 0, 0, decim)
+        env_atlas = torch.cat([tb.reshape(-1, 4), tg.reshape(-1, 4)])
+        Hb = self.texture_bkg.shape[1]
+        table_e = [(0, Hb, Hb), (Hb * Hb * 3, Hb, Hb)]
+        re = self.renderer_env
+        out_env = render_scene(env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, table_e, R_tgt, T_tgt,
+                               re.cameras.intrinsics(), re.img_size, re.sigma, re.faces_per_pixel, re.z_clip, re.detach_bary,
+                               re.clip_inside, re.background_color, None, re.perspective_correct, blur_radius=re.blur_radius,
+                               maps_are_texels4=True)
+        # ---- blocks pass
+        alpha_logit = self.alpha_logit
+        if self.opacity_noise and coarse_learning:
+            alpha_logit = alpha_logit + self.opacity_noise * self._draw_opacity_noise()
+        self._alpha = torch.sigmoid(alpha_logit)
+        self._alpha_full = self._alpha.clone()
+        fmap = st['fmap_b']
+        if filter_tsp or self.kill_blocks:
+            mask = torch.sigmoid(self.alpha_logit) > (0.5 if filter_tsp else 0.01)
+            self._alpha_full = self._alpha_full * mask
+            fmap = torch.where(mask.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
+        p_left, p_right = self.txt_padding
+        atlas = texture_atlas(self.textures, p_left, p_right, self.decim_factor if (coarse_learning and self.is_live('decimate_txt')) else 1)
+        Ht, Wt = atlas.shape[1], atlas.shape[2]
+        table_b = [(i * Ht * Wt * 3, Ht, Wt) for i in range(N)]
+        alpha = None if filter_tsp else self._alpha.repeat_interleave(self.BNF)
+        r = renderer
+        out_fg = render_scene(verts[:N * Vb], st['faces_b'], st['fvu_b'], fmap, atlas.reshape(-1, 4), table_b, R_tgt, T_tgt,
+                              r.cameras.intrinsics(), r.img_size, r.sigma, r.faces_per_pixel, r.z_clip, r.detach_bary,
+                              r.clip_inside, r.background_color, alpha, r.perspective_correct, blur_radius=r.blur_radius,
+                              maps_are_texels4=True)
+        # the regularisers of compute_losses() read these (plain torch on parameters, only built when they are used)
+        self._blocks_SRT = None
+        self._needs_reg_state = True
+        return out_env, out_fg
+
+    def _ensure_reg_state(self):
+        """state the parameter-only regularisers read (dbw.py:313,349-351); the fused path builds it lazily."""
+        if getattr(self, '_needs_reg_state', False):
+            self._blocks_maps = torch.sigmoid(self.textures)
+            self._bkg_maps, self._ground_maps = torch.sigmoid(self.texture_bkg), torch.sigmoid(self.texture_ground)
+            self._blocks_SRT = (self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T)
+            eps1, eps2 = (self.sq_eps.sigmoid() * 1.8 + 0.1).split([1, 1], dim=-1)
+            self._blocks_eps = eps1, eps2
+            self._needs_reg_state = False
+
     def _draw_opacity_noise(self):
         if self.opacity_noise_buffer is not None:
             return self.opacity_noise_buffer
@@ -429,6 +510,8 @@ class DifferentiableBlocksWorld(nn.Module):
     def compute_losses(self, imgs, rec, rgb_loss=None):
         losses = {k: torch.zeros((), device=imgs.device) for k in self.loss_weights}
         coarse_learning = self.is_live('coarse_learning')
+        if any(k in self.loss_weights for k in ('tv', 'overlap')):
+            self._ensure_reg_state()
         if 'rgb' in losses:
             losses['rgb'] = self.loss_weights['rgb'] * (rgb_loss if rgb_loss is not None else self.criterion(imgs, rec))
         if 'perceptual' in losses and self.perceptual_loss is not None:

@@ -112,7 +112,7 @@ def _device_map_table(table_host, dev):
 
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
                   perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
-                  n_map_floats=0):
+                  n_map_floats=0, maps_are_texels4=False):
     s = DbwRenderSettings()
     s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
     s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
@@ -124,15 +124,17 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     s.clip_inside, s.perspective_correct = int(clip_inside), int(perspective_correct)
     s.clip_barycentric, s.detach_bary, s.verts_are_ndc = int(clip_barycentric), int(detach_bary), int(verts_are_ndc)
     s.n_map_floats = int(n_map_floats)
+    s.maps_are_texels4 = int(maps_are_texels4)
     return s
 
 
 def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
                  z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
-                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False):
+                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False):
     """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
     verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
-    map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,)."""
+    map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
+    maps_are_texels4: `maps` is a float4 (RGB+pad) texel atlas from scene_ops.texture_atlas (offsets stay 3*texel)."""
     H, W = image_size
     B = R.shape[0] if R is not None else verts.shape[0]
     V = verts.shape[-2]
@@ -149,7 +151,8 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
         blur_radius = np.log(1. / 1e-4 - 1.) * sigma            # renderer.py:51
     cfg = make_settings(B, H, W, faces_per_pixel, V, Fn, len(map_table_host), alpha_stride, intr, sigma, blur_radius,
                         z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc,
-                        n_map_floats=maps.numel())
+                        n_map_floats=(maps.numel() // 4 * 3) if maps_are_texels4 else maps.numel(),
+                        maps_are_texels4=maps_are_texels4)
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)

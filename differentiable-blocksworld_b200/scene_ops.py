@@ -1,0 +1,79 @@
+"""autograd seams over the fused scene-construction kernels (dbw_scene_geometry_*, dbw_texture_prep_*): the
+superquadric mesh build and the texture preparation of src/model/dbw.py:267-352 as ONE kernel each way instead of
+~200 eager ops, with no host synchronisation (CUDA-graph friendly)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DbwSceneGeometry
+from .renderer import _c, _stream
+
+
+def _geom_struct(static, sq_eps, S, R6, T, R6g, Tg):
+    g = DbwSceneGeometry()
+    g.n_blocks, g.verts_per_block, g.n_ground_verts = static['n_blocks'], static['verts_per_block'], static['n_ground_verts']
+    g.sq_eta, g.sq_omega = static['sq_eta'].data_ptr(), static['sq_omega'].data_ptr()
+    g.sq_eps, g.S, g.R_6d, g.T = sq_eps.data_ptr(), S.data_ptr(), R6.data_ptr(), T.data_ptr()
+    g.ground_verts = static['ground_verts'].data_ptr()
+    g.R_6d_ground, g.T_ground = R6g.data_ptr(), Tg.data_ptr()
+    g.ratio_block_scene, g.scale_min, g.S_world = static['ratio'], static['scale_min'], static['S_world']
+    g.R_world = (ctypes.c_float * 9)(*static['R_world'])
+    g.T_world = (ctypes.c_float * 3)(*static['T_world'])
+    return g
+
+
+class _SceneGeometryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sq_eps, S, R6, T, R6g, Tg, static):
+        args = [t.detach().contiguous().float() for t in (sq_eps, S, R6, T, R6g, Tg)]
+        g = _geom_struct(static, *args)
+        n = static['n_blocks'] * static['verts_per_block'] + static['n_ground_verts']
+        out = torch.empty(n, 3, device=sq_eps.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dbw_scene_geometry_forward(ctypes.byref(g), _c(out), _stream()), 'dbw_scene_geometry_forward')
+        ctx.save_for_backward(*args)
+        ctx.static = static
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        args = ctx.saved_tensors
+        g = _geom_struct(ctx.static, *args)
+        grads = [torch.zeros_like(t) for t in args]
+        _lib.check(_lib.lib().dbw_scene_geometry_backward(ctypes.byref(g), _c(g_out.contiguous().float()), *[_c(t) for t in grads],
+                                                          _stream()), 'dbw_scene_geometry_backward')
+        return (*grads, None)
+
+
+def scene_geometry(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static):
+    """World-space vertices (N*Vb + Vg, 3): the N superquadric blocks, then the ground plane.  `static` holds the
+    buffers / constants of the scene template (see DifferentiableBlocksWorld._geometry_static)."""
+    return _SceneGeometryFn.apply(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static)
+
+
+class _TextureAtlasFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, textures, p_left, p_right, decimate):
+        tex = textures.detach().contiguous().float()
+        M, TS = tex.shape[0], tex.shape[1]
+        atlas = torch.empty(M, TS, TS + p_left + p_right, 4, device=tex.device, dtype=torch.float32)
+        _lib.check(_lib.lib().dbw_texture_prep_forward(_c(tex), M, TS, p_left, p_right, decimate, _c(atlas), _stream()),
+                   'dbw_texture_prep_forward')
+        ctx.save_for_backward(tex)
+        ctx.cfg = (M, TS, p_left, p_right, decimate)
+        return atlas
+
+    @staticmethod
+    def backward(ctx, g_atlas):
+        (tex,) = ctx.saved_tensors
+        M, TS, p_left, p_right, decimate = ctx.cfg
+        g_tex = torch.empty_like(tex)
+        _lib.check(_lib.lib().dbw_texture_prep_backward(_c(tex), M, TS, p_left, p_right, decimate, _c(g_atlas.contiguous().float()),
+                                                        _c(g_tex), _stream()), 'dbw_texture_prep_backward')
+        return g_tex, None, None, None
+
+
+def texture_atlas(textures, p_left=0, p_right=0, decimate=1):
+    """(M,TS,TS,3) logits -> (M, TS, p_left+TS+p_right, 4) float4 texels: sigmoid, optional 8x8 box decimation, circular
+    padding along u -- the layout the rasterizer samples directly (render_scene(..., maps_are_texels4=True))."""
+    return _TextureAtlasFn.apply(textures, int(p_left), int(p_right), int(decimate))

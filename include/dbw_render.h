@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 2
+#define DBW_ABI_VERSION 3
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -54,6 +54,8 @@ typedef struct DbwRenderSettings {
   int32_t detach_bary;        /* LayeredShader detach_bary (renderer.py:43,222-223): no gradient through barycentrics */
   int32_t verts_are_ndc;      /* 1: `verts` is (B,V,3) = (x_ndc, y_ndc, z_view) and R/T/K are ignored                 */
   int32_t n_map_floats;       /* total floats in `maps` (= 3 * sum_m H_m*W_m): sizes the library's float4 texel scratch    */
+  int32_t maps_are_texels4;   /* 1: `maps` (and `g_maps`) are already RGB+pad float4 texel atlases (dbw_texture_prep_*);
+                                 DbwMapDesc.offset keeps its meaning (3 * first texel index)                              */
 } DbwRenderSettings;
 
 /* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */
@@ -112,6 +114,38 @@ int dbw_render_backward(const DbwRenderSettings* settings, const float* verts, c
 int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
                       const float* imgs, float inv_count, float* rec, float* loss_sum, float* g_fg, float* g_env,
                       void* stream);
+
+/*
+ * Fused scene construction (src/model/dbw.py:267-352), so that a training step needs no eager tensor ops between the
+ * leaf parameters and the rasterizer.  All pointers are device pointers.
+ */
+typedef struct DbwSceneGeometry {
+  int32_t n_blocks, verts_per_block, n_ground_verts, reserved;
+  const float* sq_eta;        /* (N,Vb) buffers sq_eta / sq_omega (dbw.py:86-87)                                           */
+  const float* sq_omega;
+  const float* sq_eps;        /* (N,2)  dbw.py:84, eps = sigmoid(.)*1.8 + 0.1 (dbw.py:349)                                 */
+  const float* S;             /* (N,3)  scale = exp(S) + scale_min (dbw.py:299)                                            */
+  const float* R_6d;          /* (N,6)  rotation_6d_to_matrix (dbw.py:299)                                                 */
+  const float* T;             /* (N,3)                                                                                     */
+  const float* ground_verts;  /* (Vg,3) static plane vertices (dbw.py:76-78); may be NULL when n_ground_verts == 0         */
+  const float* R_6d_ground;   /* (6)    dbw.py:99,285                                                                      */
+  const float* T_ground;      /* (3)    dbw.py:100                                                                         */
+  float ratio_block_scene, scale_min, S_world;
+  float R_world[9], T_world[3];   /* world transform (v * S_world) @ R_world + T_world (dbw.py:264,344)                    */
+} DbwSceneGeometry;
+
+/* verts_out (N*Vb + Vg, 3): world-space vertices of the N superquadric blocks, then of the ground plane. */
+int dbw_scene_geometry_forward(const DbwSceneGeometry* g, float* verts_out, void* stream);
+/* g_verts (N*Vb + Vg, 3) -> gradients of the leaf parameters (written, not accumulated). */
+int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const float* g_verts, float* g_sq_eps, float* g_S, float* g_R_6d,
+                                float* g_T, float* g_R_6d_ground, float* g_T_ground, void* stream);
+
+/* textures (M,TS,TS,3) logits -> atlas (M, TS, p_left+TS+p_right) float4 texels: sigmoid, optional `decimate`xdecimate box
+ * filter (1 = off, 8 = dbw.py:331-334), circular padding along u (dbw.py:339-341).  Backward: g_atlas -> g_textures. */
+int dbw_texture_prep_forward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
+                             int32_t decimate, float* atlas_out, void* stream);
+int dbw_texture_prep_backward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
+                              int32_t decimate, const float* g_atlas, float* g_textures, void* stream);
 
 /*
  * Host-buffer variants (the end-to-end call a reference-side binding makes with numpy / CPU tensors): every

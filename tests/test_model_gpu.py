@@ -136,3 +136,69 @@ def test_cuda_graph_step_equals_eager_step():
     inp2 = {k: (v.flip(0).contiguous() if k in ('imgs',) else v) for k, v in inp.items()}
     l2 = graphed.run(inp2)['rgb'].item()
     assert abs(l2 - l_graph) > 1e-9
+
+
+def test_fused_scene_geometry_matches_torch_path():
+    """dbw_scene_geometry_* (one kernel each way) vs the eager restatement of dbw.py:299-311,344,348-352."""
+    from dbw_b200 import geometry as G
+    from dbw_b200.scene_ops import scene_geometry
+    model, tpl, p, dev = _model_and_oracle()
+    with torch.no_grad():
+        model.sq_eps.copy_(torch.randn_like(model.sq_eps))
+        model.R_6d_ground.add_(0.1 * torch.randn_like(model.R_6d_ground))
+    st = model._fused_arrays()
+    leaves = [model.sq_eps, model.S, model.R_6d, model.T, model.R_6d_ground, model.T_ground]
+    out = scene_geometry(*leaves, st['geom'])
+    # eager
+    S, R, T = model.S.exp() + model.scale_min, G.rotation_6d_to_matrix(model.R_6d), model.T
+    vb = model._to_world((model.get_blocks_verts() * S[:, None]) @ R + T[:, None]).reshape(-1, 3)
+    gv = model.ground.get_mesh_verts_faces(0)[0][None]
+    vg = model._to_world(gv @ G.rotation_6d_to_matrix(model.R_6d_ground) + model.T_ground[:, None])[0]
+    ref = torch.cat([vb, vg])
+    assert (out - ref).abs().max().item() < 2e-6
+    w = torch.randn_like(ref)
+    g_f = torch.autograd.grad((out * w).sum(), leaves)
+    g_r = torch.autograd.grad((ref * w).sum(), leaves)
+    for a, b, n in zip(g_f, g_r, ['sq_eps', 'S', 'R_6d', 'T', 'R_6d_ground', 'T_ground']):
+        assert (a - b).norm() <= 2e-5 * b.norm() + 1e-7, (n, (a - b).norm().item(), b.norm().item())
+
+
+@pytest.mark.parametrize('decim', [1, 8])
+@pytest.mark.parametrize('pad', [(0, 0), (0, 5), (3, 2)])
+def test_fused_texture_atlas_matches_torch_path(decim, pad):
+    import torch.nn.functional as F
+    from dbw_b200.scene_ops import texture_atlas
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(3)
+    tex = torch.randn(3, 32, 32, 3, generator=g).to(dev).requires_grad_(True)
+    atlas = texture_atlas(tex, pad[0], pad[1], decim)
+    maps = torch.sigmoid(tex)
+    if decim > 1:
+        sub = F.avg_pool2d(maps.permute(0, 3, 1, 2), kernel_size=decim, stride=decim)
+        maps = F.interpolate(sub, scale_factor=decim).permute(0, 2, 3, 1)
+    ref = F.pad(maps.permute(0, 3, 1, 2), pad=(pad[0], pad[1], 0, 0), mode='circular').permute(0, 2, 3, 1)
+    assert atlas.shape == (3, 32, 32 + sum(pad), 4)
+    assert (atlas[..., :3] - ref).abs().max().item() < 1e-6 and (atlas[..., 3] == 0).all()
+    w = torch.randn(3, 32, 32 + sum(pad), 4, generator=g).to(dev)
+    (ga,) = torch.autograd.grad((atlas * w).sum(), tex)
+    (gr,) = torch.autograd.grad((ref * w[..., :3]).sum(), tex)
+    assert (ga - gr).norm() <= 1e-5 * gr.norm()
+
+
+@pytest.mark.parametrize('fine', [False, True])
+def test_fused_scene_path_equals_eager_path(fine):
+    model, tpl, p, dev = _model_and_oracle(fine=fine)
+    inp, *_ = _inputs(dev)
+    outs = []
+    for fused in (True, False):
+        model.fused_scene = fused
+        model.zero_grad(set_to_none=True)
+        losses = model(inp, None)
+        losses['total'].backward()
+        outs.append(({k: v.item() for k, v in losses.items()},
+                     {n: (prm.grad.clone() if prm.grad is not None else torch.zeros_like(prm)) for n, prm in model.named_parameters()}))
+    for k in outs[1][0]:
+        assert abs(outs[0][0][k] - outs[1][0][k]) <= 1e-6 * max(1.0, abs(outs[1][0][k])), k
+    for n in outs[1][1]:
+        a, b = outs[0][1][n], outs[1][1][n]
+        assert (a - b).norm() <= 2e-4 * b.norm() + 1e-10, (n, (a - b).norm().item(), b.norm().item())
