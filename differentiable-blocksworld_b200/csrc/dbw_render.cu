@@ -81,7 +81,7 @@ extern "C" void dbw_timing_reset(void) {
 }
 
 struct Workspace {
-  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; float4* maps4; size_t total;
+  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
   Workspace w; char* p = (char*)base; size_t off = 0;
@@ -92,6 +92,7 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.rec2 = (float4*)(p + off);     off += align_up(B * S * 2 * sizeof(float4));
   w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
+  w.view_bbox = (int*)(p + off);   off += align_up(B * 4 * sizeof(int));
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   w.total = off; return w;
 }
@@ -182,6 +183,10 @@ __global__ void project_verts_backward_kernel(const float* __restrict__ vw, cons
   }
   g_vw[v * 3] += ax; g_vw[v * 3 + 1] += ay; g_vw[v * 3 + 2] += az;
 }
+
+// order-preserving float <-> int map, so that atomicMin/atomicMax on ints order floats of either sign
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
 // ------------------------------------------------------------------------------------------------ face setup + z-clip (A3)
 struct ClipResult {
@@ -276,13 +281,19 @@ __device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float4* re
   }
 }
 
+__global__ void init_view_bbox_kernel(int* vb, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * 4) vb[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+}
+
 __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
                                   float z_clip, int persp, float sqrt_blur, const float* __restrict__ faces_uvs,
                                   const int* __restrict__ face_map, const DbwMapDesc* __restrict__ map_table,
                                   float4* __restrict__ bbox, float4* __restrict__ rec, float4* __restrict__ rec2,
-                                  float* __restrict__ conv, int* __restrict__ view_flags) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * F) return;
+                                  float* __restrict__ conv, int* __restrict__ view_flags, int* __restrict__ view_bbox) {
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool tail = i0 >= B * F;                    // tail lanes redo the last face (idempotent writes) so that the warp
+  const int i = tail ? B * F - 1 : i0;              // stays converged for the shuffles below
   const int b = i / F, f = i - b * F;
   float a[3][3];
 #pragma unroll
@@ -303,6 +314,35 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   write_slot(bbox, rec, rec2, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur, uv01, uv2m);
   write_slot(bbox, rec, rec2, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur, uv01, uv2m);
   if (r.ntri == 2) atomicOr(&view_flags[b], 1);
+  // union of the (blur-expanded) face boxes of the view: tiles outside it skip the binning scan altogether
+  float ux0 = INFINITY, ux1 = -INFINITY, uy0 = INFINITY, uy1 = -INFINITY;
+  for (int q = 0; q < r.ntri; ++q) {
+    const float4 bb = bbox[q == 0 ? s0 : s1];
+    ux0 = fminf(ux0, bb.x); ux1 = fmaxf(ux1, bb.y); uy0 = fminf(uy0, bb.z); uy1 = fmaxf(uy1, bb.w);
+  }
+  // one atomic set per warp
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ux0 = fminf(ux0, __shfl_xor_sync(0xffffffffu, ux0, o)); ux1 = fmaxf(ux1, __shfl_xor_sync(0xffffffffu, ux1, o));
+    uy0 = fminf(uy0, __shfl_xor_sync(0xffffffffu, uy0, o)); uy1 = fmaxf(uy1, __shfl_xor_sync(0xffffffffu, uy1, o));
+  }
+  const int b_lead = __shfl_sync(0xffffffffu, b, 0);
+  if (__all_sync(0xffffffffu, b == b_lead)) {
+    if ((threadIdx.x & 31) == 0 && ux0 <= ux1) {
+      atomicMin(&view_bbox[b * 4], f2ord(ux0)); atomicMax(&view_bbox[b * 4 + 1], f2ord(ux1));
+      atomicMin(&view_bbox[b * 4 + 2], f2ord(uy0)); atomicMax(&view_bbox[b * 4 + 3], f2ord(uy1));
+    }
+  } else if (r.ntri > 0) {          // warp straddles two views: recompute this lane's own box
+    float lx0 = INFINITY, lx1 = -INFINITY, ly0 = INFINITY, ly1 = -INFINITY;
+    for (int q = 0; q < r.ntri; ++q) {
+      const float4 bb = bbox[q == 0 ? s0 : s1];
+      lx0 = fminf(lx0, bb.x); lx1 = fmaxf(lx1, bb.y); ly0 = fminf(ly0, bb.z); ly1 = fmaxf(ly1, bb.w);
+    }
+    if (lx0 <= lx1) {
+      atomicMin(&view_bbox[b * 4], f2ord(lx0)); atomicMax(&view_bbox[b * 4 + 1], f2ord(lx1));
+      atomicMin(&view_bbox[b * 4 + 2], f2ord(ly0)); atomicMax(&view_bbox[b * 4 + 3], f2ord(ly1));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ raster + shade + blend, forward
@@ -311,7 +351,7 @@ struct RasterParams {
   int alpha_stride;
   float sigma, blur, bg0, bg1, bg2;
   int clip_inside, persp, clipb, detach_bary;
-  const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags;
+  const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags; const int* view_bbox;
   const float4* maps4;
   const float* faces_alpha;
   float* out_rgba; int* topk;
@@ -385,23 +425,29 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
   const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
   const bool live = xi < P.W && yi < P.H;
   const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
-  // NDC extent of the tile's pixel centres (+X is left, +Y is up)
-  const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
-  const float t_xmin = pix_to_ndc(P.W - 1 - tx1, P.W, P.H), t_xmax = pix_to_ndc(P.W - 1 - tx0, P.W, P.H);
-  const float t_ymin = pix_to_ndc(P.H - 1 - ty1, P.H, P.W), t_ymax = pix_to_ndc(P.H - 1 - ty0, P.H, P.W);
+  // NDC extent of the tile's pixel centres (+X is left, +Y is up): computed by four threads, shared by the CTA
+  __shared__ float s_ext[4];
+  if (tid < 4) {
+    const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
+    s_ext[tid] = tid == 0 ? pix_to_ndc(P.W - 1 - tx1, P.W, P.H) : tid == 1 ? pix_to_ndc(P.W - 1 - tx0, P.W, P.H)
+               : tid == 2 ? pix_to_ndc(P.H - 1 - ty1, P.H, P.W) : pix_to_ndc(P.H - 1 - ty0, P.H, P.W);
+  }
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  const float t_xmin = s_ext[0], t_xmax = s_ext[1], t_ymin = s_ext[2], t_ymax = s_ext[3];
+  // tiles outside the union of the view's face boxes have nothing to rasterize: no scan
+  const int* vb = P.view_bbox + view * 4;
+  const bool tile_empty = ord2f(vb[0]) > t_xmax || ord2f(vb[1]) < t_xmin || ord2f(vb[2]) > t_ymax || ord2f(vb[3]) < t_ymin;
 
   unsigned long long key[K];
   float dk[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) { key[k] = ~0ull; dk[k] = 0.f; }
 
-  const int nslots = (P.view_flags[view] & 1) ? 2 * P.F : P.F;
+  const int nslots = tile_empty ? 0 : ((P.view_flags[view] & 1) ? 2 * P.F : P.F);
   const float4* bbox = P.bbox + (size_t)view * 2 * P.F;
   const float4* rec = P.rec + (size_t)view * 2 * P.F * 4;
   const bool dist_inside = (!P.clip_inside && P.sigma > 0.f);
-
-  if (tid == 0) s_count = 0;
-  __syncthreads();
 
   for (int base = 0; base < nslots; base += NTHREADS) {
     // ---- bin: which face slots of this batch touch the tile?
@@ -489,14 +535,16 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = (size_t)yi * P.W + xi;
   int* ids = P.topk + (size_t)view * P.K * plane + pix;
+  int n_frag = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) n_frag += (key[k] != ~0ull) ? 1 : 0;
+  if (n_frag > P.K) n_frag = P.K;
 #pragma unroll 1
-  for (int k = 0; k < P.K; ++k) {
+  for (int k = 0; k < n_frag; ++k) {
     const unsigned long long k0 = key[0];
     const float d0 = dk[0];
 #pragma unroll
     for (int q = 0; q < K - 1; ++q) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
-    key[K - 1] = ~0ull;
-    if (k0 == ~0ull) { ids[(size_t)k * plane] = -1; continue; }
     const int slot = (int)(unsigned)k0;
     ids[(size_t)k * plane] = slot;
     Shade s;
@@ -507,6 +555,7 @@ __global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterPa
     r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
     occ *= (1.f - a);
   }
+  for (int k = n_frag; k < P.K; ++k) ids[(size_t)k * plane] = -1;
   float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
   o[0] = r + occ * P.bg0; o[plane] = g + occ * P.bg1; o[2 * plane] = bl + occ * P.bg2; o[3 * plane] = 1.f - occ;
 }
@@ -616,7 +665,16 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
 
   // number of fragments of this pixel; warp-uniform trip count
   int n = 0;
-  if (any_grad) { while (n < P.K && ids[(size_t)n * plane] >= 0) ++n; }
+  if (any_grad) {
+    bool open = true;
+    for (int k0 = 0; k0 < P.K; k0 += 8) {          // 8 independent loads in flight instead of a serial chain
+      int v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < P.K) ? ids[(size_t)(k0 + j) * plane] : -1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { open = open && v[j] >= 0; n += open ? 1 : 0; }
+    }
+  }
   const int n_warp = __reduce_max_sync(0xffffffffu, n);
   if (P.debug_skip & 8) { if (gr + gg + gb + ga + (float)n == 12345.f) P.g_tri[0] = 1.f; return; }
 
@@ -876,7 +934,7 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   P.alpha_stride = s.alpha_view_stride;
   P.sigma = s.sigma; P.blur = s.blur_radius; P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
-  P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags;
+  P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
   P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
   return P;
 }
@@ -905,9 +963,11 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
     verts_ndc = w.verts_ndc;
   }
   CK(cudaMemsetAsync(w.view_flags, 0, B * sizeof(int), st));
+  init_view_bbox_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(w.view_bbox, B);
+  LAUNCH_CK("init_view_bbox_kernel");
   face_setup_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
                                                          sqrtf(s->blur_radius), faces_uvs, face_map, map_table, w.bbox, w.rec,
-                                                         w.rec2, w.conv, w.view_flags);
+                                                         w.rec2, w.conv, w.view_flags, w.view_bbox);
   LAUNCH_CK("face_setup_kernel");
   if (!s->maps_are_texels4) {
     const int n_texels = s->n_map_floats / 3;
