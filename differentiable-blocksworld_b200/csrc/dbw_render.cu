@@ -357,8 +357,6 @@ struct RasterParams {
   float* out_rgba; int* topk;
   // backward only
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
-  int debug_skip;   // experiments only (env DBW_DEBUG_SKIP): 1 = no texture scatter, 2 = no vertex-gradient accumulation, 4 = no pass 2,
-                    // 8 = return after the per-pixel loads, 16 = no gradient work in pass 1, 32 = no barycentric-path math
 };
 
 #define TILE_W 16
@@ -602,6 +600,34 @@ __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride
   }
 }
 
+// same for the distance path, which only touches (x, y) of the three vertices: offsets 0,1, 3,4, 6,7 of the slot's 9 floats
+__device__ __forceinline__ void warp_agg_add_xy(float* __restrict__ dst, int key, const float (&v)[6], int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = (key == lk);
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    float* d = dst + (size_t)lk * 9;
+    if (__popc(grp) <= 2) {
+      if (mine) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (v[i] != 0.f) atomicAdd(d + i + (i >> 1), v[i]);
+      }
+    } else {
+      float x[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) x[i] = mine ? v[i] : 0.f;
+      warp_sum<6>(x);
+      if (lane == leader) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) if (x[i] != 0.f) atomicAdd(d + i + (i >> 1), x[i]);
+      }
+    }
+    todo &= ~grp;
+  }
+}
+
 // Texture-gradient scatter of one fragment: 4 bilinear taps x RGB.  Under magnification (the environment maps seen
 // through a narrow field of view: hundreds of pixels per texel) whole warps hit the same 2x2 texel footprint, so
 // lanes that share the footprint with >= 8 others are reduced with shuffles first; the rest issue plain atomics.
@@ -663,29 +689,23 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
   const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
   const size_t slot_base = (size_t)view * 2 * P.F;
 
-  // number of fragments of this pixel; warp-uniform trip count
+  // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count, so that the
+  // aggregation helpers run converged); the id of layer k+1 is prefetched while layer k is processed
   int n = 0;
-  if (any_grad) {
-    bool open = true;
-    for (int k0 = 0; k0 < P.K; k0 += 8) {          // 8 independent loads in flight instead of a serial chain
-      int v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (k0 + j < P.K) ? ids[(size_t)(k0 + j) * plane] : -1;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { open = open && v[j] >= 0; n += open ? 1 : 0; }
-    }
-  }
-  const int n_warp = __reduce_max_sync(0xffffffffu, n);
-  if (P.debug_skip & 8) { if (gr + gg + gb + ga + (float)n == 12345.f) P.g_tri[0] = 1.f; return; }
-
+  int slot_next = any_grad ? ids[0] : -1;
+  int n_warp = 0;
   float occ = 1.f;
-  for (int k = 0; k < n_warp; ++k) {
+  for (int k = 0; k < P.K; ++k) {
+    const int slot = slot_next;
+    if (!__any_sync(0xffffffffu, slot >= 0)) break;
+    n_warp = k + 1;
+    slot_next = (slot >= 0 && k + 1 < P.K) ? ids[(size_t)(k + 1) * plane] : -1;
     int key = -1, ckey = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
     float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float gc9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tv[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (k < n) {
-      const int slot = ids[(size_t)k * plane];
+    if (slot >= 0) {
+      n = k + 1;
       Shade s;
       shade_fragment(P, view, slot, p, s);
       float d;
@@ -698,7 +718,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
       s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
       s_occ[k * NTHREADS + tid] = occ;
       const float w = occ * a;                 // d RGB / d colour_k
-      if (w != 0.f && !(P.debug_skip & 16)) {
+      if (w != 0.f) {
         const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
         if (P.g_maps4) {
           tkey = s.tap.i00; t01 = s.tap.i01; t10 = s.tap.i10; t11 = s.tap.i11;
@@ -707,7 +727,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
           tv[6] = gcx * s.tap.w10; tv[7] = gcy * s.tap.w10; tv[8] = gcz * s.tap.w10;
           tv[9] = gcx * s.tap.w11; tv[10] = gcy * s.tap.w11; tv[11] = gcz * s.tap.w11;
         }
-        if (!DETACH && !(P.debug_skip & 32)) {
+        if (!DETACH) {
           // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
           const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
           const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
@@ -733,18 +753,18 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
           }
           float gz0 = 0.f, gz1 = 0.f, gz2 = 0.f;
           f3 gb_ = gbc;
-          if (P.clipb && !(P.debug_skip & 128)) gb_ = clip_backward(s.b.bp, gb_);
-          if (P.persp && !(P.debug_skip & 256)) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
+          if (P.clipb) gb_ = clip_backward(s.b.bp, gb_);
+          if (P.persp) gb_ = persp_backward(s.b.b0, s.t.z0, s.t.z1, s.t.z2, gb_, gz0, gz1, gz2);
           f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
-          if (!(P.debug_skip & 512)) bary_backward(p, s.t, gb_, g0, g1, g2);
+          bary_backward(p, s.t, gb_, g0, g1, g2);
           key = slot;
           gv9[0] = g0.x; gv9[1] = g0.y; gv9[2] = gz0; gv9[3] = g1.x; gv9[4] = g1.y; gv9[5] = gz1; gv9[6] = g2.x; gv9[7] = g2.y; gv9[8] = gz2;
         }
       }
       occ *= (1.f - a);
     }
-    if (P.g_maps4 && !(P.debug_skip & 1)) warp_tex_scatter(P.g_maps4, tkey, t01, t10, t11, tv, lane);
-    if (!DETACH && !(P.debug_skip & 2)) {
+    if (P.g_maps4) warp_tex_scatter(P.g_maps4, tkey, t01, t10, t11, tv, lane);
+    if (!DETACH) {
       warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
       if (__ballot_sync(0xffffffffu, ckey >= 0)) warp_agg_add<9>(P.g_conv + slot_base * 9, 9, ckey, gc9, lane);
     }
@@ -752,7 +772,6 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
-  if (P.debug_skip & 4) return;
   for (int k = n_warp - 1; k >= 0; --k) {
     int akey = -1, vkey = -1;
     float ga1[1] = {0.f};
@@ -789,11 +808,7 @@ __global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const Rast
     if (ALPHA && P.g_faces_alpha) warp_agg_add<1>(P.g_faces_alpha + (size_t)view * P.alpha_stride, 1, akey, ga1, lane);
     if (P.sigma > 0.f) {
       // (x, y) of the three vertices live at offsets 0,1, 3,4, 6,7 of the slot's 9 floats
-      const unsigned any_v = __ballot_sync(0xffffffffu, vkey >= 0);
-      if (any_v) {
-        float gv9[9] = {gv6[0], gv6[1], 0.f, gv6[2], gv6[3], 0.f, gv6[4], gv6[5], 0.f};
-        warp_agg_add<9>(P.g_tri + slot_base * 9, 9, vkey, gv9, lane);
-      }
+      if (__ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_xy(P.g_tri + slot_base * 9, vkey, gv6, lane);
     }
   }
 }
@@ -1011,7 +1026,6 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
-  { const char* e = getenv("DBW_DEBUG_SKIP"); P.debug_skip = e ? atoi(e) : 0; }
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
   {

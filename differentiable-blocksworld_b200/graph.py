@@ -45,3 +45,45 @@ class GraphedStep:
         self.graph.replay()
         self.vp.bucket.all_reduce(self.vp.group)
         return self.losses
+
+
+class PipelinedGraphedStep:
+    """Two GraphedSteps on alternating static input buffers: while step i replays, the inputs of step i+1 are copied
+    host->device on a side stream (what a prefetching DataLoader does for src/trainer.py:141).  `run(host_inp)` returns
+    the losses of the step that consumed `host_inp`."""
+
+    def __init__(self, view_parallel, example_inp, n_total_views):
+        self.steps = [GraphedStep(view_parallel, example_inp, n_total_views) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream()
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # inputs of buffer b have landed
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]       # buffer b has been consumed by its replay
+        self.i = 0
+        self.primed = False
+
+    def _stage(self, b, host_inp):
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[b])
+            for k, v in host_inp.items():
+                if k in self.steps[b].static_inp:
+                    self.steps[b].static_inp[k].copy_(v, non_blocking=True)
+            self.ready[b].record(self.copy_stream)
+
+    def run(self, host_inp, next_host_inp=None):
+        """consume `host_inp` (staged now unless it was prefetched as the previous call's `next_host_inp`) and
+        prefetch `next_host_inp` for the following call."""
+        b = self.i % 2
+        cur = torch.cuda.current_stream()
+        if not self.primed:
+            self.free[0].record(cur)
+            self.free[1].record(cur)
+            self._stage(b, host_inp)
+            self.primed = True
+        if next_host_inp is not None:
+            self._stage(1 - b, next_host_inp)
+        else:
+            self.primed = False
+        cur.wait_event(self.ready[b])
+        losses = self.steps[b].run()
+        self.free[b].record(cur)
+        self.i += 1
+        return losses

@@ -6,6 +6,6 @@ TAG=${1:-r1}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${TAG}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:raster_ -s 12 -c 4 -o gpurun_out/prof_${TAG} -f \
+ncu --set full --clock-control none --import-source on -k regex:raster_ -s 16 -c 4 -o gpurun_out/prof_${TAG} -f \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
