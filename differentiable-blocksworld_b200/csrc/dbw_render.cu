@@ -155,15 +155,15 @@ __global__ void project_verts_kernel(const float* __restrict__ vw, const float* 
   out[i * 3 + 2] = zv;
 }
 
-// one thread per vertex, deterministic sum over the views
+// one warp per vertex: lanes stride over the views, shuffle-reduce, lane 0 accumulates (deterministic, no atomics)
 __global__ void project_verts_backward_kernel(const float* __restrict__ vw, const float* __restrict__ R, const float* __restrict__ T,
                                               float fx, float fy, float px, float py, float eps, int B, int V,
                                               const float* __restrict__ g_ndc, float* __restrict__ g_vw) {
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (v >= V) return;
   const float X = vw[v * 3], Y = vw[v * 3 + 1], Z = vw[v * 3 + 2];
   float ax = 0.f, ay = 0.f, az = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = lane; b < B; b += 32) {
     const float* r = R + b * 9; const float* t = T + b * 3;
     const float xv = X * r[0] + Y * r[3] + Z * r[6] + t[0];
     const float yv = X * r[1] + Y * r[4] + Z * r[7] + t[1];
@@ -181,7 +181,11 @@ __global__ void project_verts_backward_kernel(const float* __restrict__ vw, cons
     ay += r[3] * gxv + r[4] * gyv + r[5] * gzv;
     az += r[6] * gxv + r[7] * gyv + r[8] * gzv;
   }
-  g_vw[v * 3] += ax; g_vw[v * 3 + 1] += ay; g_vw[v * 3 + 2] += az;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ax += __shfl_xor_sync(0xffffffffu, ax, o); ay += __shfl_xor_sync(0xffffffffu, ay, o); az += __shfl_xor_sync(0xffffffffu, az, o);
+  }
+  if (lane == 0) { g_vw[v * 3] += ax; g_vw[v * 3 + 1] += ay; g_vw[v * 3 + 2] += az; }
 }
 
 // order-preserving float <-> int map, so that atomicMin/atomicMax on ints order floats of either sign
@@ -941,6 +945,33 @@ __global__ void composite_mse_kernel(int n_px_total, int plane, const float* __r
   }
 }
 
+// gradient of (g_loss * loss + <g_rec, rec>) w.r.t. fg and env, straight from the inputs: no saved gradient buffers and
+// no elementwise rescaling kernels
+__global__ void composite_backward_kernel(int n_px_total, int plane, const float* __restrict__ fg, const float* __restrict__ env,
+                                          const float* __restrict__ imgs, float inv_count, const float* __restrict__ g_loss,
+                                          const float* __restrict__ g_rec, float* __restrict__ g_fg, float* __restrict__ g_env) {
+  const float gl = g_loss ? __ldg(g_loss) : 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_px_total; i += gridDim.x * blockDim.x) {
+    const int b = i / plane, px = i - b * plane;
+    const float* f = fg + (size_t)b * 4 * plane + px;
+    const float* e = env + (size_t)b * 4 * plane + px;
+    const float m = f[3 * (size_t)plane];
+    float gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float fc = f[(size_t)c * plane], ec = e[(size_t)c * plane];
+      const float r = fc * m + (1.f - m) * ec;
+      float gr = 2.f * (r - imgs[(size_t)b * 3 * plane + (size_t)c * plane + px]) * inv_count * gl;
+      if (g_rec) gr += g_rec[(size_t)b * 3 * plane + (size_t)c * plane + px];
+      g_fg[(size_t)b * 4 * plane + (size_t)c * plane + px] = gr * m;
+      g_env[(size_t)b * 4 * plane + (size_t)c * plane + px] = gr * (1.f - m);
+      gm += gr * (fc - ec);
+    }
+    g_fg[(size_t)b * 4 * plane + 3 * (size_t)plane + px] = gm;
+    g_env[(size_t)b * 4 * plane + 3 * (size_t)plane + px] = 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, const float* faces_alpha) {
   RasterParams P;
@@ -1055,7 +1086,7 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
     LAUNCH_CK("face_setup_backward_kernel");
     if (!s->verts_are_ndc) {
       if (!R || !T) return fail("dbw_render_backward: R and T are required unless verts_are_ndc");
-      project_verts_backward_kernel<<<(V + 127) / 128, 128, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V,
+      project_verts_backward_kernel<<<(V * 32 + 127) / 128, 128, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V,
                                                                      g.g_verts_ndc, g_verts);
       LAUNCH_CK("project_verts_backward_kernel");
     }
@@ -1075,6 +1106,21 @@ extern "C" int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width,
   if (blocks > 148 * 16) blocks = 148 * 16;
   composite_mse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((int)total, plane, fg, env, imgs, inv_count, rec, loss_sum, g_fg, g_env);
   LAUNCH_CK("composite_mse_kernel");
+  return 0;
+}
+
+extern "C" int dbw_composite_mse_backward(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
+                                          const float* imgs, float inv_count, const float* g_loss, const float* g_rec,
+                                          float* g_fg, float* g_env, void* stream) {
+  if (!fg || !env || !imgs || !g_fg || !g_env) return fail("dbw_composite_mse_backward: null pointer argument");
+  if (n_views <= 0 || height <= 0 || width <= 0) return fail("dbw_composite_mse_backward: bad sizes");
+  const int plane = height * width;
+  const long long total = (long long)n_views * plane;
+  if (total > 0x7fffffffLL) return fail("dbw_composite_mse_backward: too many pixels for one call");
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  composite_backward_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((int)total, plane, fg, env, imgs, inv_count, g_loss, g_rec, g_fg, g_env);
+  LAUNCH_CK("composite_backward_kernel");
   return 0;
 }
 

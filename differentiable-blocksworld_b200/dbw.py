@@ -29,8 +29,8 @@ tv_norm_funcs = {'l2': lambda x: torch.norm(x, dim=-1), 'l1': lambda x: x.abs().
 
 
 class _CompositeMSE(torch.autograd.Function):
-    """rec = fg_rgb * fg_a + (1 - fg_a) * env_rgb ; loss = mean((imgs - rec)^2)   (dbw.py:223 + :366-367), one kernel
-    that also emits d loss / d fg and d loss / d env so that backward is a scale."""
+    """rec = fg_rgb * fg_a + (1 - fg_a) * env_rgb ; loss = mean((imgs - rec)^2)   (dbw.py:223 + :366-367): one kernel
+    forward, one kernel backward (which also folds in a gradient arriving at `rec` from other loss terms)."""
 
     @staticmethod
     def forward(ctx, fg, env, imgs, n_total_views):
@@ -39,26 +39,23 @@ class _CompositeMSE(torch.autograd.Function):
         fg, env, imgs = fg.contiguous(), env.contiguous(), imgs.contiguous().float()
         rec = torch.empty(B, 3, H, W, device=fg.device, dtype=torch.float32)
         loss = torch.zeros((), device=fg.device, dtype=torch.float32)
-        g_fg, g_env = torch.empty_like(fg), torch.empty_like(env)
         inv = 1.0 / (float(n_total_views) * 3 * H * W)
         _lib.check(_lib.lib().dbw_composite_mse(B, H, W, _c(fg), _c(env), _c(imgs), ctypes.c_float(inv), _c(rec), _c(loss),
-                                                _c(g_fg), _c(g_env), _stream()), 'dbw_composite_mse')
-        ctx.save_for_backward(g_fg, g_env, fg, env)
+                                                None, None, _stream()), 'dbw_composite_mse')
+        ctx.save_for_backward(fg, env, imgs)
+        ctx.inv = inv
         return rec, loss
 
     @staticmethod
     def backward(ctx, g_rec, g_loss):
-        g_fg, g_env, fg, env = ctx.saved_tensors
-        if g_loss is None:
-            out_fg, out_env = torch.zeros_like(g_fg), torch.zeros_like(g_env)
-        else:
-            out_fg, out_env = g_fg * g_loss, g_env * g_loss
-        if g_rec is not None:
-            m = fg[:, 3:]
-            extra_fg = torch.cat([g_rec * m, (g_rec * (fg[:, :3] - env[:, :3])).sum(1, keepdim=True)], 1)
-            extra_env = torch.cat([g_rec * (1 - m), torch.zeros_like(m)], 1)
-            out_fg, out_env = out_fg + extra_fg, out_env + extra_env
-        return out_fg, out_env, None, None
+        fg, env, imgs = ctx.saved_tensors
+        B, _, H, W = fg.shape
+        g_fg, g_env = torch.empty_like(fg), torch.empty_like(env)
+        gl = g_loss.contiguous().float() if g_loss is not None else None
+        gr = g_rec.contiguous().float() if g_rec is not None else None
+        _lib.check(_lib.lib().dbw_composite_mse_backward(B, H, W, _c(fg), _c(env), _c(imgs), ctypes.c_float(ctx.inv), _c(gl),
+                                                         _c(gr), _c(g_fg), _c(g_env), _stream()), 'dbw_composite_mse_backward')
+        return g_fg, g_env, None, None
 
 
 class DifferentiableBlocksWorld(nn.Module):

@@ -115,6 +115,12 @@ int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width, const floa
                       const float* imgs, float inv_count, float* rec, float* loss_sum, float* g_fg, float* g_env,
                       void* stream);
 
+/* Backward of dbw_composite_mse: d(g_loss * loss + <g_rec, rec>) / d fg, d env, written to g_fg / g_env ((B,4,H,W)).
+ * g_loss: device scalar (may be NULL = 0); g_rec: (B,3,H,W) gradient arriving at `rec` from other losses (may be NULL). */
+int dbw_composite_mse_backward(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
+                               const float* imgs, float inv_count, const float* g_loss, const float* g_rec, float* g_fg,
+                               float* g_env, void* stream);
+
 /*
  * Fused scene construction (src/model/dbw.py:267-352), so that a training step needs no eager tensor ops between the
  * leaf parameters and the rasterizer.  All pointers are device pointers.

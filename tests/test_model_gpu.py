@@ -202,3 +202,22 @@ def test_fused_scene_path_equals_eager_path(fine):
     for n in outs[1][1]:
         a, b = outs[0][1][n], outs[1][1][n]
         assert (a - b).norm() <= 2e-4 * b.norm() + 1e-10, (n, (a - b).norm().item(), b.norm().item())
+
+
+def test_composite_mse_fused_matches_torch():
+    """dbw_composite_mse / _backward vs the eager expressions of dbw.py:223,366-367, incl. a gradient arriving at rec."""
+    from dbw_b200.dbw import _CompositeMSE
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(0)
+    fg = torch.rand(3, 4, 20, 28, generator=g).to(dev).requires_grad_(True)
+    env = torch.rand(3, 4, 20, 28, generator=g).to(dev).requires_grad_(True)
+    imgs = torch.rand(3, 3, 20, 28, generator=g).to(dev)
+    w = torch.rand(3, 3, 20, 28, generator=g).to(dev)
+    rec, loss = _CompositeMSE.apply(fg, env, imgs, 5)
+    (0.7 * loss + (rec * w).sum()).backward()
+    a = (fg.grad.clone(), env.grad.clone()); fg.grad = None; env.grad = None
+    rec_t = fg[:, :3] * fg[:, 3:] + (1 - fg[:, 3:]) * env[:, :3]
+    loss_t = ((imgs - rec_t) ** 2).sum() / (5 * 3 * 20 * 28)
+    (0.7 * loss_t + (rec_t * w).sum()).backward()
+    assert torch.allclose(rec, rec_t, atol=1e-6) and abs(loss.item() - loss_t.item()) < 1e-6
+    assert torch.allclose(a[0], fg.grad, atol=1e-6, rtol=1e-5) and torch.allclose(a[1], env.grad, atol=1e-6, rtol=1e-5)
