@@ -184,3 +184,32 @@ def test_verts_are_ndc_entry():
     sc['verts'] = ndc.to(dev).contiguous()
     out = render_product(sc, None, None, K, (64, 64), 1e-4, 10, z_clip=0.001, verts_are_ndc=True)
     _check_image(out.cpu(), ref)
+
+
+def test_stress_shape_many_faces_k25():
+    """BASELINE configs[4] shape at reduced resolution: 50 blocks (4000 faces), K = 25 -- exercises the chunked tile
+    lists (more listed faces than the shared-memory list holds at once) and the K = 25 register top-K."""
+    dev = _dev()
+    tpl = D.SceneTemplate(n_blocks=50, txt_size=16)
+    p = D.init_params(50, 16, seed=7, boxy=True)
+    p['T'] = p['T'] * 0.35                       # crowd the blocks so that many faces overlap the same tiles
+    R, T, K = D.ring_cameras(2, jitter=0.3, seed=7, dist=2.0)
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF)
+    ref, fr = D.render(blocks, R, T, K, (96, 128), sigma=1e-4, faces_per_pixel=25, z_clip=0.001, detach_bary=True,
+                       faces_alpha=fa, return_fragments=True)
+    sc = scene_to_device(blocks, dev)
+    out, ids = render_product(sc, R.to(dev), T.to(dev), K, (96, 128), 1e-4, 25, z_clip=0.001, detach_bary=True,
+                              faces_alpha=fa.to(dev), return_ids=True)
+    assert (fr.pix_to_face[..., -1] >= 0).float().mean() > 0.01       # K really is exceeded somewhere
+    _check_image(out.cpu(), ref, max_bad_frac=3e-4)
+    mism = 1 - decision_mask(ids, fr, blocks['faces'].shape[0]).mean().item()
+    assert mism < 2e-3, mism
+
+
+def test_bmvs_shape_non_square_backward():
+    """BASELINE configs[3] aspect (576x768 -> 72x96 here), fine phase."""
+    tpl, p, R, T, K = _setup(n_blocks=5, dtype=torch.float64, n_views=2, boxy=True)
+    p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    blocks, alpha = tpl.build_blocks(p)
+    _grad_parity(blocks, R, T, K, (72, 96), 5e-6, 10, 0.001, True, None, True, seed=6)
