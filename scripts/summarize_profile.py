@@ -1,7 +1,7 @@
 """Turn gpurun_out/{launches_TAG.csv, prof_TAG.ncu-rep} into the committed summaries under profiles/."""
 import collections, csv, os, subprocess, sys
 tag = sys.argv[1]
-steps_in_run = int(sys.argv[2]) if len(sys.argv) > 2 else 7      # warmup 3 + timed 1 + e2e (2 + 1)
+steps_in_run = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: infer from the once-per-step composite kernel
 os.makedirs('profiles', exist_ok=True)
 lines = [l for l in open(f'gpurun_out/launches_{tag}.csv') if not l.startswith('==')]
 agg = collections.OrderedDict()
@@ -10,6 +10,8 @@ for row in csv.DictReader(lines):
     v *= {'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3}[u]
     a = agg.setdefault(row['Kernel Name'][:90], [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
+if not steps_in_run:
+    steps_in_run = max(1, sum(a[0] for k, a in agg.items() if k.startswith('composite_mse_kernel')))
 with open(f'profiles/launches_{tag}_summary.txt', 'w') as f:
     f.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n')
     f.write(f'# {sum(a[0] for a in agg.values())} launches over {steps_in_run} steps; per-step averages; cold-cache serialised times: compare SHARES\n')
