@@ -413,7 +413,7 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
 }
 
 template <int K>
-__global__ void __launch_bounds__(NTHREADS) raster_forward_kernel(const RasterParams P) {
+__global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 16 ? 2 : 1)))) raster_forward_kernel(const RasterParams P) {
   __shared__ float4 s_bbox[LIST_CAP];
   __shared__ float4 s_rec[LIST_CAP * 4];
   __shared__ int s_slot[LIST_CAP];
@@ -672,7 +672,7 @@ __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int ke
 // division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
 // Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
 template <bool DETACH, bool ALPHA>
-__global__ void __launch_bounds__(NTHREADS, 3) raster_backward_kernel(const RasterParams P) {
+__global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;

@@ -82,6 +82,8 @@ class DifferentiableBlocksWorld(nn.Module):
         # fused scene construction (scene_ops.py): mesh build + texture prep as one kernel each way
         self.fused_scene = True
         self._fused_static = None
+        self.overlap_passes = False               # environment pass on a side stream, concurrent with the blocks pass
+        self._env_stream = None
 
     @property
     def init_kwargs(self):
@@ -383,10 +385,20 @@ class DifferentiableBlocksWorld(nn.Module):
         Hb = self.texture_bkg.shape[1]
         table_e = [(0, Hb, Hb), (Hb * Hb * 3, Hb, Hb)]
         re = self.renderer_env
-        out_env = render_scene(env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, table_e, R_tgt, T_tgt,
-                               re.cameras.intrinsics(), re.img_size, re.sigma, re.faces_per_pixel, re.z_clip, re.detach_bary,
-                               re.clip_inside, re.background_color, None, re.perspective_correct, blur_radius=re.blur_radius,
-                               maps_are_texels4=True)
+        # the two passes are independent until compositing: the environment pass runs on a side stream so that its
+        # kernels (and, through autograd, their backward) overlap the blocks pass -- each raster kernel alone leaves
+        # 35-50 % of the issue slots idle (profiles/), two different ones interleave on the SMs
+        cur = torch.cuda.current_stream()
+        if self._env_stream is None:
+            self._env_stream = torch.cuda.Stream()
+        side = self._env_stream if self.overlap_passes else cur
+        if side is not cur:
+            side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            out_env = render_scene(env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, table_e, R_tgt, T_tgt,
+                                   re.cameras.intrinsics(), re.img_size, re.sigma, re.faces_per_pixel, re.z_clip, re.detach_bary,
+                                   re.clip_inside, re.background_color, None, re.perspective_correct, blur_radius=re.blur_radius,
+                                   maps_are_texels4=True)
         # ---- blocks pass
         alpha_logit = self.alpha_logit
         if self.opacity_noise and coarse_learning:
@@ -408,6 +420,9 @@ class DifferentiableBlocksWorld(nn.Module):
                               r.cameras.intrinsics(), r.img_size, r.sigma, r.faces_per_pixel, r.z_clip, r.detach_bary,
                               r.clip_inside, r.background_color, alpha, r.perspective_correct, blur_radius=r.blur_radius,
                               maps_are_texels4=True)
+        if side is not cur:
+            cur.wait_stream(side)
+            out_env.record_stream(cur)
         # the regularisers of compute_losses() read these (plain torch on parameters, only built when they are used)
         self._blocks_SRT = None
         self._needs_reg_state = True
