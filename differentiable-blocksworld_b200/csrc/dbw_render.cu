@@ -451,8 +451,69 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
   const float4* rec = P.rec + (size_t)view * 2 * P.F * 4;
   const bool dist_inside = (!P.clip_inside && P.sigma > 0.f);
 
+  // stage the records of the `cnt` listed faces in shared memory, then test every pixel against every listed face
+  auto raster_list = [&](int cnt) {
+    // ---- stage the records of the listed faces in shared memory
+    for (int j = tid; j < cnt; j += NTHREADS) {
+      const int sl = s_slot[j];
+      s_rec[j * 4 + 0] = __ldg(&rec[sl * 4 + 0]);
+      s_rec[j * 4 + 1] = __ldg(&rec[sl * 4 + 1]);
+      s_rec[j * 4 + 2] = __ldg(&rec[sl * 4 + 2]);
+      s_rec[j * 4 + 3] = __ldg(&rec[sl * 4 + 3]);
+    }
+    __syncthreads();
+    // ---- per pixel: test every listed face, keep the K nearest
+    if (live) {
+      for (int j = 0; j < cnt; ++j) {
+        const float4 b4 = s_bbox[j];
+        if (p.x > b4.y || p.x < b4.x || p.y > b4.w || p.y < b4.z) continue;
+        const TriGeom t = unpack_tri(s_rec[j * 4], s_rec[j * 4 + 1], s_rec[j * 4 + 2], s_rec[j * 4 + 3]);
+        // cheap, exact part first: edge functions -> inside; pixels outside the face and beyond the halo leave here
+        const Edges ed = eval_edges(p, t);
+        float dist = 1.f;
+        const bool need_dist = !ed.inside || dist_inside || t.neighbor >= 0;
+        if (need_dist) dist = tri_dist2(p, t);
+        if (!ed.inside && dist >= P.blur) continue;
+        const Bary b = bary_from_edges(ed, t, P.persp, P.clipb);
+        if (b.pz < 0.f) continue;
+        const float sd = b.inside ? -dist : dist;
+        const int slot = s_slot[j];
+        if (t.neighbor >= 0) {
+          // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3)
+          bool drop_new = false;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) {
+              if (dist < fabsf(dk[k])) {
+#pragma unroll
+                for (int q = 0; q < K - 1; ++q) if (q >= k) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
+                key[K - 1] = ~0ull; dk[K - 1] = 0.f;
+              } else drop_new = true;
+              break;
+            }
+          }
+          if (drop_new) continue;
+        }
+        const unsigned long long nk = make_key(b.pz, slot);
+        if (nk >= key[K - 1]) continue;
+        // sorted insertion with static indexing
+#pragma unroll
+        for (int k = K - 1; k >= 1; --k) {
+          const bool up = nk < key[k - 1];
+          const bool here = !up && nk < key[k];
+          key[k] = up ? key[k - 1] : (here ? nk : key[k]);
+          dk[k] = up ? dk[k - 1] : (here ? sd : dk[k]);
+        }
+        if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
+      }
+    }
+    __syncthreads();
+  };
+
+  // ---- bin: which face slots of the view touch the tile?  Fast path: every batch of 256 slots is tested and compacted
+  // with NO block barrier in between (ballot + one shared atomic per warp); hits beyond the list capacity are counted
+  // but not stored, and only then the chunked path below (barrier per batch) is taken.
   for (int base = 0; base < nslots; base += NTHREADS) {
-    // ---- bin: which face slots of this batch touch the tile?
     const int s = base + tid;
     bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
     if (s < nslots) {
@@ -463,71 +524,41 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
     int wbase = 0;
     if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (hit) {
-      const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-      s_slot[pos] = s; s_bbox[pos] = bb;
-    }
+    const int pos = wbase + __popc(m & ((1u << lane) - 1u));
+    if (hit && pos < LIST_CAP) { s_slot[pos] = s; s_bbox[pos] = bb; }
+  }
+  __syncthreads();
+  const int total = s_count;
+  if (total <= LIST_CAP) {
+    if (total > 0) raster_list(total);
+  } else {
+    // chunked path (more than LIST_CAP faces touch this tile): re-scan, flushing the list whenever it may overflow
     __syncthreads();
-    const int cnt = s_count;
-    const bool last = base + NTHREADS >= nslots;
-    if (cnt > LIST_CAP - NTHREADS || last) {
-      // ---- stage the records of the listed faces in shared memory
-      for (int j = tid; j < cnt; j += NTHREADS) {
-        const int sl = s_slot[j];
-        s_rec[j * 4 + 0] = __ldg(&rec[sl * 4 + 0]);
-        s_rec[j * 4 + 1] = __ldg(&rec[sl * 4 + 1]);
-        s_rec[j * 4 + 2] = __ldg(&rec[sl * 4 + 2]);
-        s_rec[j * 4 + 3] = __ldg(&rec[sl * 4 + 3]);
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int base = 0; base < nslots; base += NTHREADS) {
+      const int s = base + tid;
+      bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
+      if (s < nslots) {
+        bb = __ldg(&bbox[s]);
+        hit = !(bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      int wbase = 0;
+      if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (hit) {
+        const int pos = wbase + __popc(m & ((1u << lane) - 1u));
+        s_slot[pos] = s; s_bbox[pos] = bb;
       }
       __syncthreads();
-      // ---- per pixel: test every listed face, keep the K nearest
-      if (live) {
-        for (int j = 0; j < cnt; ++j) {
-          const float4 b4 = s_bbox[j];
-          if (p.x > b4.y || p.x < b4.x || p.y > b4.w || p.y < b4.z) continue;
-          const TriGeom t = unpack_tri(s_rec[j * 4], s_rec[j * 4 + 1], s_rec[j * 4 + 2], s_rec[j * 4 + 3]);
-          // cheap, exact part first: edge functions -> inside; pixels outside the face and beyond the halo leave here
-          const Edges ed = eval_edges(p, t);
-          float dist = 1.f;
-          const bool need_dist = !ed.inside || dist_inside || t.neighbor >= 0;
-          if (need_dist) dist = tri_dist2(p, t);
-          if (!ed.inside && dist >= P.blur) continue;
-          const Bary b = bary_from_edges(ed, t, P.persp, P.clipb);
-          if (b.pz < 0.f) continue;
-          const float sd = b.inside ? -dist : dist;
-          const int slot = s_slot[j];
-          if (t.neighbor >= 0) {
-            // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3)
-            bool drop_new = false;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) {
-                if (dist < fabsf(dk[k])) {
-#pragma unroll
-                  for (int q = 0; q < K - 1; ++q) if (q >= k) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
-                  key[K - 1] = ~0ull; dk[K - 1] = 0.f;
-                } else drop_new = true;
-                break;
-              }
-            }
-            if (drop_new) continue;
-          }
-          const unsigned long long nk = make_key(b.pz, slot);
-          if (nk >= key[K - 1]) continue;
-          // sorted insertion with static indexing
-#pragma unroll
-          for (int k = K - 1; k >= 1; --k) {
-            const bool up = nk < key[k - 1];
-            const bool here = !up && nk < key[k];
-            key[k] = up ? key[k - 1] : (here ? nk : key[k]);
-            dk[k] = up ? dk[k - 1] : (here ? sd : dk[k]);
-          }
-          if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
-        }
+      const int cnt = s_count;
+      const bool last = base + NTHREADS >= nslots;
+      if (cnt > LIST_CAP - NTHREADS || last) {
+        raster_list(cnt);
+        if (tid == 0) s_count = 0;
+        __syncthreads();
       }
-      __syncthreads();
-      if (tid == 0) s_count = 0;
-      __syncthreads();
     }
   }
 
