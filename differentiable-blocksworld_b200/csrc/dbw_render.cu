@@ -418,6 +418,8 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
   __shared__ float4 s_rec[LIST_CAP * 4];
   __shared__ int s_slot[LIST_CAP];
   __shared__ int s_count;
+  __shared__ __align__(8) uint64_t s_bar;      // mbarrier of the TMA record gather
+  uint32_t bar_phase = 0;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
     s_ext[tid] = tid == 0 ? pix_to_ndc(P.W - 1 - tx1, P.W, P.H) : tid == 1 ? pix_to_ndc(P.W - 1 - tx0, P.W, P.H)
                : tid == 2 ? pix_to_ndc(P.H - 1 - ty1, P.H, P.W) : pix_to_ndc(P.H - 1 - ty0, P.H, P.W);
   }
-  if (tid == 0) s_count = 0;
+  if (tid == 0) { s_count = 0; mbar_init(&s_bar, 1); }
   __syncthreads();
   const float t_xmin = s_ext[0], t_xmax = s_ext[1], t_ymin = s_ext[2], t_ymax = s_ext[3];
   // tiles outside the union of the view's face boxes have nothing to rasterize: no scan
@@ -453,15 +455,12 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
 
   // stage the records of the `cnt` listed faces in shared memory, then test every pixel against every listed face
   auto raster_list = [&](int cnt) {
-    // ---- stage the records of the listed faces in shared memory
-    for (int j = tid; j < cnt; j += NTHREADS) {
-      const int sl = s_slot[j];
-      s_rec[j * 4 + 0] = __ldg(&rec[sl * 4 + 0]);
-      s_rec[j * 4 + 1] = __ldg(&rec[sl * 4 + 1]);
-      s_rec[j * 4 + 2] = __ldg(&rec[sl * 4 + 2]);
-      s_rec[j * 4 + 3] = __ldg(&rec[sl * 4 + 3]);
-    }
-    __syncthreads();
+    // ---- stage the records of the listed faces in shared memory: one 64 B TMA bulk copy per face, all landing on s_bar
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of s_rec precede the async writes
+    if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)cnt * 64u);
+    for (int j = tid; j < cnt; j += NTHREADS) bulk_copy_g2s(&s_rec[j * 4], &rec[(size_t)s_slot[j] * 4], 64u, &s_bar);
+    mbar_wait(&s_bar, bar_phase);
+    bar_phase ^= 1u;
     // ---- per pixel: test every listed face, keep the K nearest
     if (live) {
       for (int j = 0; j < cnt; ++j) {
