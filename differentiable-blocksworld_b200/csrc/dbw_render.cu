@@ -469,6 +469,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
         const TriGeom t = unpack_tri(s_rec[j * 4], s_rec[j * 4 + 1], s_rec[j * 4 + 2], s_rec[j * 4 + 3]);
         // cheap, exact part first: edge functions -> inside; pixels outside the face and beyond the halo leave here
         const Edges ed = eval_edges(p, t);
+        if (!ed.inside && P.blur == 0.f) continue;      // hard pass: nothing outside a face can be within a zero halo
         float dist = 1.f;
         const bool need_dist = !ed.inside || dist_inside || t.neighbor >= 0;
         if (need_dist) dist = tri_dist2(p, t);
