@@ -6,7 +6,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdbw_render.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class DbwRenderSettings(ctypes.Structure):
@@ -19,7 +19,7 @@ class DbwRenderSettings(ctypes.Structure):
         ('proj_eps', ctypes.c_float), ('background', ctypes.c_float * 3),
         ('clip_inside', ctypes.c_int32), ('perspective_correct', ctypes.c_int32),
         ('clip_barycentric', ctypes.c_int32), ('detach_bary', ctypes.c_int32), ('verts_are_ndc', ctypes.c_int32),
-        ('n_map_floats', ctypes.c_int32), ('maps_are_texels4', ctypes.c_int32),
+        ('n_map_floats', ctypes.c_int32), ('maps_are_texels4', ctypes.c_int32), ('save_fragment_state', ctypes.c_int32),
     ]
 
 

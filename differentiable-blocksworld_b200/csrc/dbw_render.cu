@@ -16,6 +16,8 @@
 //   maps4      (sum H*W) float4   the caller's (H,W,3) maps re-packed as RGB+pad texels: one 128-bit load per bilinear tap
 //   conv       (B,2F,9)           barycentric conversion (clipped -> original face), only for clipped slots
 //   slots [0,F) hold each face's (first) triangle, slots [F,2F) the second triangle of a z-clipped quad.
+//   frag       (B,K,H,W,2) float4 optional saved fragment state (u, v, signed dist, r | g, b, -, -): two 128-bit stores per kept
+//                                 fragment (only where one exists); lets the detach_bary backward stream instead of re-deriving geometry
 //   out_rgba   (B,4,H,W), topk_ids (B,K,H,W) planar so that every warp store is a run of full 32 B sectors.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -81,7 +83,7 @@ extern "C" void dbw_timing_reset(void) {
 }
 
 struct Workspace {
-  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4; size_t total;
+  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4; float* frag; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
   Workspace w; char* p = (char*)base; size_t off = 0;
@@ -94,6 +96,7 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
   w.view_bbox = (int*)(p + off);   off += align_up(B * 4 * sizeof(int));
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
+  w.frag = (float*)(p + off);      off += s.save_fragment_state ? align_up(B * (size_t)s.faces_per_pixel * 8 * s.height * s.width * sizeof(float)) : 0;
   w.total = off; return w;
 }
 struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; float4* g_maps4; size_t total; };
@@ -360,6 +363,7 @@ struct RasterParams {
   const float* faces_alpha;
   float* out_rgba; int* topk;
   // backward only
+  float* frag;     // (B,K,H,W,8) saved fragment state or NULL
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
 };
 
@@ -584,6 +588,10 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
     shade_fragment(P, view, slot, p, s);
     float a = frag_alpha(d0, P.sigma, P.clip_inside);
     if (P.faces_alpha) a *= __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]);
+    if (P.frag) {
+      float4* fs = reinterpret_cast<float4*>(P.frag) + (((size_t)view * P.K + k) * plane + pix) * 2;
+      fs[0] = make_float4(s.u, s.v, d0, s.color.x); fs[1] = make_float4(s.color.y, s.color.z, 0.f, 0.f);
+    }
     const float w = occ * a;
     r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
     occ *= (1.f - a);
@@ -702,7 +710,7 @@ __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int ke
 // texture gradient and (unless detach_bary) the barycentric-path vertex gradient; pass 2 walks back to front with the
 // division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
 // Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
-template <bool DETACH, bool ALPHA>
+template <bool DETACH, bool ALPHA, bool SAVED>
 __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -742,20 +750,34 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
     if (slot >= 0) {
       n = k + 1;
       Shade s;
-      shade_fragment(P, view, slot, p, s);
-      float d;
-      if (s.b.inside && P.clip_inside) d = -1.f;
-      else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
-      const float e = frag_alpha(d, P.sigma, P.clip_inside);
-      const float fa = ALPHA ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
-      const float a = e * fa;
-      const float cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
+      float d, e, fa, a, cdot;
+      if (SAVED) {
+        // stream the fragment's saved state (7 coalesced planar loads) instead of re-deriving geometry and texels
+        const float4* fs = reinterpret_cast<const float4*>(P.frag) + (((size_t)view * P.K + k) * plane + pix) * 2;
+        const float4 f0 = fs[0], f1 = fs[1];
+        s.u = f0.x; s.v = f0.y; d = f0.z;
+        s.color = {f0.w, f1.x, f1.y};
+        s.t.face = slot >= P.F ? slot - P.F : slot;
+      } else {
+        shade_fragment(P, view, slot, p, s);
+        if (s.b.inside && P.clip_inside) d = -1.f;
+        else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
+      }
+      e = frag_alpha(d, P.sigma, P.clip_inside);
+      fa = ALPHA ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
+      a = e * fa;
+      cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
       s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
       s_occ[k * NTHREADS + tid] = occ;
       const float w = occ * a;                 // d RGB / d colour_k
       if (w != 0.f) {
         const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
         if (P.g_maps4) {
+          if (SAVED) {
+            const float4 q1 = __ldg(&P.rec2[(slot_base + slot) * 2 + 1]);      // map offset / size of the face
+            const int hw = __float_as_int(q1.w);
+            s.tap = tex_tap(s.u, s.v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
+          }
           tkey = s.tap.i00; t01 = s.tap.i01; t10 = s.tap.i10; t11 = s.tap.i11;
           tv[0] = gcx * s.tap.w00; tv[1] = gcy * s.tap.w00; tv[2] = gcz * s.tap.w00;
           tv[3] = gcx * s.tap.w01; tv[4] = gcy * s.tap.w01; tv[5] = gcz * s.tap.w01;
@@ -826,7 +848,9 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
           if (P.g_faces_alpha) { akey = t.face; ga1[0] = g_alpha * e; }
         }
         if (P.sigma > 0.f && P.g_tri) {
-          const Bary b = eval_bary(p, t, P.persp, P.clipb);
+          Bary b;
+          if (SAVED) b.inside = P.frag[(((size_t)view * P.K + k) * plane + pix) * 8 + 2] < 0.f;   // sign of the saved distance
+          else b = eval_bary(p, t, P.persp, P.clipb);
           float g_sd = 0.f;           // gradient w.r.t. the SIGNED squared distance
           if (P.clip_inside) { if (!b.inside) g_sd = g_alpha * fa * (-e / P.sigma); }   // clamp(d, 0): flat inside the face
           else g_sd = g_alpha * fa * (-e * (1.f - e) / P.sigma);
@@ -1012,7 +1036,7 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   P.sigma = s.sigma; P.blur = s.blur_radius; P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
-  P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
+  P.maps4 = w.maps4; P.faces_alpha = faces_alpha; P.frag = s.save_fragment_state ? w.frag : nullptr;
   return P;
 }
 
@@ -1097,9 +1121,10 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
       kern<<<grid, NTHREADS, smem, st>>>(P);
       return cudaSuccess;
     };
-    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr;
-    cudaError_t e = det ? (al ? launch(raster_backward_kernel<true, true>) : launch(raster_backward_kernel<true, false>))
-                        : (al ? launch(raster_backward_kernel<false, true>) : launch(raster_backward_kernel<false, false>));
+    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr, sv = det && s->save_fragment_state;
+    cudaError_t e = sv  ? (al ? launch(raster_backward_kernel<true, true, true>) : launch(raster_backward_kernel<true, false, true>))
+                  : det ? (al ? launch(raster_backward_kernel<true, true, false>) : launch(raster_backward_kernel<true, false, false>))
+                        : (al ? launch(raster_backward_kernel<false, true, false>) : launch(raster_backward_kernel<false, false, false>));
     if (e != cudaSuccess) return fail("raster_backward_kernel attribute", e);
   }
   LAUNCH_CK("raster_backward_kernel");

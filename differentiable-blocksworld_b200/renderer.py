@@ -112,7 +112,7 @@ def _device_map_table(table_host, dev):
 
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
                   perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
-                  n_map_floats=0, maps_are_texels4=False):
+                  n_map_floats=0, maps_are_texels4=False, save_fragment_state=False):
     s = DbwRenderSettings()
     s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
     s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
@@ -125,6 +125,7 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     s.clip_barycentric, s.detach_bary, s.verts_are_ndc = int(clip_barycentric), int(detach_bary), int(verts_are_ndc)
     s.n_map_floats = int(n_map_floats)
     s.maps_are_texels4 = int(maps_are_texels4)
+    s.save_fragment_state = int(save_fragment_state)
     return s
 
 
@@ -152,7 +153,9 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     cfg = make_settings(B, H, W, faces_per_pixel, V, Fn, len(map_table_host), alpha_stride, intr, sigma, blur_radius,
                         z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc,
                         n_map_floats=(maps.numel() // 4 * 3) if maps_are_texels4 else maps.numel(),
-                        maps_are_texels4=maps_are_texels4)
+                        maps_are_texels4=maps_are_texels4,
+                        # a detach_bary backward can stream saved fragment colours / UVs instead of re-deriving them
+                        save_fragment_state=bool(detach_bary) and torch.is_grad_enabled())
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 3
+#define DBW_ABI_VERSION 4
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -56,6 +56,9 @@ typedef struct DbwRenderSettings {
   int32_t n_map_floats;       /* total floats in `maps` (= 3 * sum_m H_m*W_m): sizes the library's float4 texel scratch    */
   int32_t maps_are_texels4;   /* 1: `maps` (and `g_maps`) are already RGB+pad float4 texel atlases (dbw_texture_prep_*);
                                  DbwMapDesc.offset keeps its meaning (3 * first texel index)                              */
+  int32_t save_fragment_state;/* 1: the forward also keeps (u, v, signed dist, r, g, b) of every kept fragment in its workspace
+                                 (32 B per fragment actually present) so that a detach_bary backward re-derives no
+                                 geometry for colours / opacities; costs B*K*H*W*32 bytes of workspace ADDRESS space        */
 } DbwRenderSettings;
 
 /* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */
