@@ -417,7 +417,7 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
 }
 
 template <int K>
-__global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 16 ? 2 : 1)))) raster_forward_kernel(const RasterParams P) {
+__global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 25 ? 2 : 1)))) raster_forward_kernel(const RasterParams P) {
   __shared__ float4 s_bbox[LIST_CAP];
   __shared__ float4 s_rec[LIST_CAP * 4];
   __shared__ int s_slot[LIST_CAP];
@@ -483,20 +483,19 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 1
         const float sd = b.inside ? -dist : dist;
         const int slot = s_slot[j];
         if (t.neighbor >= 0) {
-          // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3)
-          bool drop_new = false;
+          // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3).  Every index below is a
+          // compile-time constant of a fully unrolled loop, so that key[] / dk[] stay in registers.
+          int found = -1; float d_found = 0.f;
 #pragma unroll
-          for (int k = 0; k < K; ++k) {
-            if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) {
-              if (dist < fabsf(dk[k])) {
+          for (int k = 0; k < K; ++k)
+            if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) { found = k; d_found = dk[k]; }
+          if (found >= 0) {
+            if (dist < fabsf(d_found)) {
 #pragma unroll
-                for (int q = 0; q < K - 1; ++q) if (q >= k) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
-                key[K - 1] = ~0ull; dk[K - 1] = 0.f;
-              } else drop_new = true;
-              break;
-            }
+              for (int q = 0; q < K - 1; ++q) if (q >= found) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
+              key[K - 1] = ~0ull; dk[K - 1] = 0.f;
+            } else continue;
           }
-          if (drop_new) continue;
         }
         const unsigned long long nk = make_key(b.pz, slot);
         if (nk >= key[K - 1]) continue;
