@@ -583,6 +583,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     for (int q = 0; q < K - 1; ++q) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
     const int slot = (int)(unsigned)k0;
     ids[(size_t)k * plane] = slot;
+    if (occ == 0.f) continue;     // behind a fully opaque fragment (fine phase: alpha = 1 inside a face): contributes exactly 0
     Shade s;
     shade_fragment(P, view, slot, p, s);
     float a = frag_alpha(d0, P.sigma, P.clip_inside);
@@ -746,7 +747,8 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
     float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float gc9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tv[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (slot >= 0) {
+    if (slot >= 0 && occ == 0.f) slot_next = -1;   // everything behind a fully opaque fragment has zero weight and zero gradient
+    if (slot >= 0 && occ != 0.f) {
       n = k + 1;
       Shade s;
       float d, e, fa, a, cdot;

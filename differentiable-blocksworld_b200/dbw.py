@@ -255,6 +255,7 @@ class DifferentiableBlocksWorld(nn.Module):
         if 'K' in inp and self.renderer.cameras.K is None:
             for r in (self.renderer, self.renderer_fine, self.renderer_env, self.renderer_light):
                 r.update_cameras(device=inp['imgs'].device, K=inp['K'][0:1])
+                r.cameras.intrinsics()          # the one host read of K happens here, never inside a step
 
     def _render_layers(self, inp, filter_transparent=False):
         """(env RGBA, blocks RGBA or None) in decoupled mode, (scene RGBA, None) in joint mode."""

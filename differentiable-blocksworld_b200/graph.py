@@ -18,7 +18,16 @@ class GraphedStep:
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(self.vp.seed)
         self.model._install_cameras(self.static_inp)          # the one-off host read of the intrinsics happens here
-        side = torch.cuda.Stream()
+        self._capture(warmup=warmup)
+
+    def _phase(self):
+        """what the captured control flow depends on: the training-schedule switches of dbw.py:210-212,276,331-334"""
+        m = self.model
+        return (m.training, m.is_live('coarse_learning'), m.is_live('decimate_txt'), m.is_live('kill_blocks'))
+
+    def _capture(self, warmup=1):
+        self.phase = self._phase()
+        side = torch.cuda.Stream()                 # eager run(s) of the new control flow first (lazy state, allocator warm-up)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
@@ -41,6 +50,8 @@ class GraphedStep:
             for k, v in inp.items():
                 if k in self.static_inp:
                     self.static_inp[k].copy_(v, non_blocking=non_blocking)
+        if self._phase() != self.phase:          # a schedule milestone was crossed (coarse -> fine, decimation off): re-capture
+            self._capture()
         self.model.opacity_noise_buffer.normal_(generator=self.gen)     # identical on every rank (same seed, same count)
         self.graph.replay()
         self.vp.bucket.all_reduce(self.vp.group)

@@ -13,6 +13,7 @@ from dbw_b200.synthetic import ring_cameras
 dev = torch.device('cuda:0')
 CASES = {
     'cfg2 dtu 400x400 N=10 K=10 B=49': dict(H=400, W=400, N=10, K=10, txt=256, up=1, B=49),
+    'cfg2 FINE phase (sigma=5e-6, hard opacities) B=49': dict(H=400, W=400, N=10, K=10, txt=256, up=1, B=49, fine=True),
     'cfg4 bmvs 576x768 N=10 K=10 B=8': dict(H=576, W=768, N=10, K=10, txt=256, up=1, B=8),
     'cfg5 stress 800x800 N=50 K=25 B=4': dict(H=800, W=800, N=50, K=25, txt=128, up=2, B=4),
 }
@@ -22,6 +23,10 @@ for name, c in CASES.items():
     cfg['renderer']['faces_per_pixel'] = c['K']
     torch.manual_seed(0)
     model = DifferentiableBlocksWorld((c['H'], c['W']), **cfg).to(dev); model.train()
+    if c.get('fine'):
+        model.set_cur_epoch(1600)
+        with torch.no_grad():
+            model.alpha_logit.copy_(torch.linspace(-1, 3, c['N']))
     R, T, K = ring_cameras(c['B'])
     inp = {'imgs': torch.rand(c['B'], 3, c['H'], c['W'], device=dev), 'R': R.to(dev), 'T': T.to(dev), 'K': K[None].expand(c['B'], -1, -1).to(dev)}
     for _ in range(3):

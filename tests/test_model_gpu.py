@@ -221,3 +221,20 @@ def test_composite_mse_fused_matches_torch():
     (0.7 * loss_t + (rec_t * w).sum()).backward()
     assert torch.allclose(rec, rec_t, atol=1e-6) and abs(loss.item() - loss_t.item()) < 1e-6
     assert torch.allclose(a[0], fg.grad, atol=1e-6, rtol=1e-5) and torch.allclose(a[1], env.grad, atol=1e-6, rtol=1e-5)
+
+
+def test_graphed_step_recaptures_when_the_schedule_switches_phase():
+    from dbw_b200.parallel import ViewParallel
+    from dbw_b200.graph import GraphedStep
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    vp = ViewParallel(model, seed=5)
+    graphed = GraphedStep(vp, inp, len(inp['imgs']))
+    l_coarse = graphed.run()['rgb'].item()
+    model.set_cur_epoch(2000)                      # past coarse_learning (1500) and decimate_txt (750)
+    l_fine = graphed.run()['rgb'].item()
+    vp.bucket.zero_()
+    model.opacity_noise_buffer = None
+    ref = model(inp, None)['rgb'].item()
+    assert abs(l_fine - ref) < 1e-7 and abs(l_fine - l_coarse) > 1e-9
