@@ -364,6 +364,8 @@ struct RasterParams {
   float* out_rgba; int* topk;
   // backward only
   float* frag;     // (B,K,H,W,8) saved fragment state or NULL
+  const float* face_shade;   // (B,F,3) per-view per-face colour multiplier (flat shading) or NULL
+  float* out_dists;          // (B,K,H,W) signed squared distances of the kept fragments (-1 = empty) or NULL
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
 };
 
@@ -455,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
   const int nslots = tile_empty ? 0 : ((P.view_flags[view] & 1) ? 2 * P.F : P.F);
   const float4* bbox = P.bbox + (size_t)view * 2 * P.F;
   const float4* rec = P.rec + (size_t)view * 2 * P.F * 4;
-  const bool dist_inside = (!P.clip_inside && P.sigma > 0.f);
+  const bool dist_inside = (!P.clip_inside && P.sigma > 0.f) || P.out_dists != nullptr;
 
   // stage the records of the `cnt` listed faces in shared memory, then test every pixel against every listed face
   auto raster_list = [&](int cnt) {
@@ -583,11 +585,16 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     for (int q = 0; q < K - 1; ++q) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
     const int slot = (int)(unsigned)k0;
     ids[(size_t)k * plane] = slot;
+    if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = d0;
     if (occ == 0.f) continue;     // behind a fully opaque fragment (fine phase: alpha = 1 inside a face): contributes exactly 0
     Shade s;
     shade_fragment(P, view, slot, p, s);
     float a = frag_alpha(d0, P.sigma, P.clip_inside);
     if (P.faces_alpha) a *= __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]);
+    if (P.face_shade) {          // flat shading: colour = texel * (ambient + diffuse * relu(n . l)) per (view, face)
+      const float* m = P.face_shade + ((size_t)view * P.F + s.t.face) * 3;
+      s.color.x *= __ldg(m); s.color.y *= __ldg(m + 1); s.color.z *= __ldg(m + 2);
+    }
     if (P.frag) {
       float4* fs = reinterpret_cast<float4*>(P.frag) + (((size_t)view * P.K + k) * plane + pix) * 2;
       fs[0] = make_float4(s.u, s.v, d0, s.color.x); fs[1] = make_float4(s.color.y, s.color.z, 0.f, 0.f);
@@ -596,7 +603,10 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
     occ *= (1.f - a);
   }
-  for (int k = n_frag; k < P.K; ++k) ids[(size_t)k * plane] = -1;
+  for (int k = n_frag; k < P.K; ++k) {
+    ids[(size_t)k * plane] = -1;
+    if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = -1.f;
+  }
   float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
   o[0] = r + occ * P.bg0; o[plane] = g + occ * P.bg1; o[2 * plane] = bl + occ * P.bg2; o[3 * plane] = 1.f - occ;
 }
@@ -1050,6 +1060,14 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
                                   const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
                                   const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
                                   size_t workspace_bytes, void* stream) {
+  return dbw_render_forward_ex(s, verts, faces, faces_uvs, face_map, maps, map_table, R, T, faces_alpha, out_rgba, topk_ids,
+                               workspace, workspace_bytes, nullptr, nullptr, stream);
+}
+
+extern "C" int dbw_render_forward_ex(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                     const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                                     const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
+                                     size_t workspace_bytes, const float* face_shade, float* out_dists, void* stream) {
   if (validate(s)) return -1;
   if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba || !topk_ids || !workspace)
     return fail("dbw_render_forward: null pointer argument");
@@ -1079,7 +1097,7 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
   }
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
-  P.out_rgba = out_rgba; P.topk = topk_ids;
+  P.out_rgba = out_rgba; P.topk = topk_ids; P.face_shade = face_shade; P.out_dists = out_dists;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const int K = s->faces_per_pixel;
   ScopedTimer timer(0, K, st);

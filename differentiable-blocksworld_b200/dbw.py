@@ -4,7 +4,8 @@
 `forward(inp, labels) -> dict of losses` / `predict(inp, labels)` signatures, so src/trainer.py:137-147 can drive it.
 Rendering goes through the B200 kernels (renderer.py); compositing + RGB loss are one fused kernel when possible.
 
-Out of this file's scope ("next"): qualitative_eval / video export, lit synthetic renders, edge overlays."""
+Visualisation helpers of SURVEY.md section 8f are covered as far as the trainer's periodic logging needs them (predict(w_edges=True),
+predict_synthetic, get_arranged_block_txt); qualitative_eval / video / OBJ export remain out of scope."""
 import ctypes
 from collections import OrderedDict
 from copy import deepcopy
@@ -303,9 +304,40 @@ class DifferentiableBlocksWorld(nn.Module):
         return rec_fg * mask + (1 - mask) * first[:, :3]
 
     def predict(self, inp, labels=None, w_edges=False, filter_transparent=False):
-        if w_edges:
-            raise NotImplementedError('edge overlays (renderer.py:134-175) are a visualisation path: not ported yet')
-        return self._composite(self._render_layers(inp, filter_transparent))
+        rec = self._composite(self._render_layers(inp, filter_transparent))
+        if w_edges:                                   # dbw.py:234-238: coloured face edges drawn over the reconstruction
+            B, R_tgt, T_tgt = len(inp['imgs']), inp['R'], inp['T']
+            fine_learning = not self.is_live('coarse_learning')
+            filter_tsp = filter_transparent or fine_learning
+            renderer = self.renderer_fine if fine_learning else self.renderer
+            env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
+            blocks = self.build_blocks(filter_transparent=filter_tsp, as_scene=True)
+            scene = join_meshes_as_scene([env, blocks]) if len(blocks) > 0 else env
+            colors = self.get_scene_face_colors(filter_transparent=filter_tsp).repeat(B, 1)
+            rec = renderer.draw_edges(rec, scene.extend(B), R_tgt, T_tgt, colors=colors)
+        return rec
+
+    def predict_synthetic(self, inp, labels=None):
+        """flat-shaded render of the opaque blocks with one synthetic colour per block (dbw.py:241-248)."""
+        B, R_tgt, T_tgt = len(inp['imgs']), inp['R'], inp['T']
+        self._install_cameras(inp)
+        blocks = self.build_blocks(filter_transparent=True, synthetic_colors=True, as_scene=True)
+        if len(blocks) > 0:
+            return self.renderer_light(blocks.extend(B), R=R_tgt, T=T_tgt, viz_purpose=True)[:, :3]
+        return torch.ones_like(inp['imgs'])
+
+    @torch.no_grad()
+    def get_scene_face_colors(self, filter_transparent=False, w_env=True):
+        """one colour per face of the scene mesh: environment faces get the first colour of the map, block k the colour at
+        (k+1)/N (dbw.py:420-431)."""
+        val_blocks = torch.linspace(0, 1, self.n_blocks + 1)[1:]
+        if filter_transparent:
+            val_blocks = val_blocks[self.get_opacities().cpu() > 0.5]
+        elif self.kill_blocks:
+            val_blocks = val_blocks[self.get_opacities().cpu() > 0.01]
+        NFE = self.env_n_faces if w_env else 0
+        values = torch.cat([torch.zeros(NFE), val_blocks.repeat_interleave(self.BNF)])
+        return torch.from_numpy(G.fancy_cmap()(values.numpy())).float().to(self.bkg.device)
 
     # ------------------------------------------------------------------ scene construction (dbw.py:250-352)
     def _decimate(self, maps):
@@ -479,7 +511,7 @@ class DifferentiableBlocksWorld(nn.Module):
         table = [(i * Ht * Wt * 3, Ht, Wt) for i in range(N)]
         return verts, faces, fvu, fmap, maps.reshape(-1), table
 
-    def build_blocks(self, filter_transparent=False, world_coord=False, as_scene=False):
+    def build_blocks(self, filter_transparent=False, world_coord=False, as_scene=False, synthetic_colors=False):
         coarse_learning = self.training and self.is_live('coarse_learning')
         S, R, T = self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
         if self.opacity_noise and coarse_learning:
@@ -489,6 +521,10 @@ class DifferentiableBlocksWorld(nn.Module):
         self._alpha = torch.sigmoid(alpha_logit)
         self._alpha_full = self._alpha.clone()
         maps = torch.sigmoid(self.textures)
+        if synthetic_colors:
+            values = torch.linspace(0, 1, self.n_blocks + 1)[1:]
+            colors = torch.from_numpy(G.fancy_cmap()(values.numpy())).float().to(maps.device)
+            maps = colors[:, None, None].expand(-1, self.txt_size, self.txt_size, -1)
         verts = (self.get_blocks_verts() * S[:, None]) @ R + T[:, None]
         faces = self.blocks.faces_padded()
         self._blocks_maps, self._blocks_SRT = maps, (S, R, T)

@@ -155,3 +155,24 @@ def superquadric_implicit(points, eps1, eps2):
     x, y, z = safe_pow(x2, 1 / eps2), safe_pow(y2, 1 / eps1), safe_pow(z2, 1 / eps2)
     res = safe_pow(x + z, eps2 / eps1) + y
     return safe_pow(res, eps1 / 2) - 1
+
+
+def fancy_cmap():
+    """The reference's block colour map (src/utils/plot.py:77-87): gold followed by seaborn's 21-colour 'hls' palette
+    rotated by three entries, as a 256-level linearly interpolated lookup table.  Restated without seaborn/matplotlib:
+    hls_palette(21) = hls_to_rgb(h, l=0.6, s=0.65) for h = (i/21 + 0.01) mod 1; 'gold' = (1, 0.843137, 0)."""
+    import colorsys
+    hues = [(i / 21.0 + 0.01) % 1.0 for i in range(21)]
+    hls = [colorsys.hls_to_rgb(h, 0.6, 0.65) for h in hues]
+    anchors = np.array([(1.0, 215.0 / 255.0, 0.0)] + hls[3:] + hls[:2])
+    xs = np.linspace(0.0, 1.0, len(anchors))
+    lut = np.stack([np.interp(np.linspace(0.0, 1.0, 256), xs, anchors[:, c]) for c in range(3)], axis=1)
+
+    def cmap(values):
+        if isinstance(values, torch.Tensor):
+            values = values.detach().cpu().numpy()
+        v = np.asarray(values, dtype=np.float64)
+        idx = np.clip((v * 256).astype(np.int64), 0, 255)
+        idx[v == 1.0] = 255
+        return lut[idx]
+    return cmap

@@ -58,7 +58,7 @@ class _RenderFn(torch.autograd.Function):
     """autograd seam over dbw_render_forward / dbw_render_backward (include/dbw_render.h)."""
 
     @staticmethod
-    def forward(ctx, verts, maps, faces_alpha, R, T, faces, faces_uvs, face_map, map_table, cfg):
+    def forward(ctx, verts, maps, faces_alpha, R, T, faces, faces_uvs, face_map, map_table, cfg, face_shade=None, want_dists=False):
         if not verts.is_cuda:
             raise DbwError('the B200 renderer needs CUDA tensors (there is no CPU fallback)')
         s = cfg
@@ -72,16 +72,23 @@ class _RenderFn(torch.autograd.Function):
         ws = torch.empty(fwd.value, dtype=torch.uint8, device=verts.device)
         out = torch.empty(B, 4, H, W, dtype=torch.float32, device=verts.device)
         ids = torch.empty(B, K, H, W, dtype=torch.int32, device=verts.device)
-        _lib.check(L.dbw_render_forward(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
-                                        _c(map_table), _c(R), _c(T), _c(fa), _c(out), _c(ids), _c(ws), fwd.value,
-                                        _stream()), 'dbw_render_forward')
+        dists = torch.empty(B, K, H, W, dtype=torch.float32, device=verts.device) if want_dists else None
+        shade = face_shade.detach().contiguous().float() if face_shade is not None else None
+        _lib.check(L.dbw_render_forward_ex(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
+                                           _c(map_table), _c(R), _c(T), _c(fa), _c(out), _c(ids), _c(ws), fwd.value,
+                                           _c(shade), _c(dists), _stream()), 'dbw_render_forward_ex')
         ctx.save_for_backward(verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws)
-        ctx.cfg, ctx.bwd_bytes = s, bwd.value
+        ctx.cfg, ctx.bwd_bytes, ctx.lit = s, bwd.value, shade is not None
         ctx.mark_non_differentiable(ids)
+        if want_dists:
+            ctx.mark_non_differentiable(dists)
+            return out, ids, dists
         return out, ids
 
     @staticmethod
-    def backward(ctx, g_out, _g_ids):
+    def backward(ctx, g_out, _g_ids, _g_dists=None):
+        if ctx.lit:
+            raise NotImplementedError('flat-shaded (lit) renders are a visualisation path: no backward')
         verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws = ctx.saved_tensors
         s = ctx.cfg
         L = _lib.lib()
@@ -95,7 +102,7 @@ class _RenderFn(torch.autograd.Function):
                                          _c(map_table), _c(R), _c(T), _c(fa), _c(ids), _c(ws), ws.numel(), _c(g_out),
                                          _c(g_verts), _c(g_fa), _c(g_maps), _c(scratch), scratch.numel(), _stream()),
                    'dbw_render_backward')
-        return g_verts, g_maps, g_fa, None, None, None, None, None, None, None
+        return g_verts, g_maps, g_fa, None, None, None, None, None, None, None, None, None
 
 
 _TABLE_CACHE = {}
@@ -131,7 +138,8 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
 
 def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
                  z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
-                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False):
+                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False,
+                 face_shade=None, return_dists=False):
     """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
     verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
     map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
@@ -159,9 +167,12 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)
-    out, ids = _RenderFn.apply(verts, maps, faces_alpha, R, T, faces.to(torch.int32).contiguous(),
-                               faces_uvs.contiguous().float(), face_map.to(torch.int32).contiguous(), map_table, cfg)
-    return (out, ids) if return_ids else out
+    res = _RenderFn.apply(verts, maps, faces_alpha, R, T, faces.to(torch.int32).contiguous(),
+                          faces_uvs.contiguous().float(), face_map.to(torch.int32).contiguous(), map_table, cfg,
+                          face_shade, return_dists)
+    if return_dists:
+        return res                       # (rgba, slot ids, signed squared distances)
+    return (res[0], res[1]) if return_ids else res[0]
 
 
 class Renderer(nn.Module):
@@ -208,23 +219,87 @@ class Renderer(nn.Module):
         self.cameras = self.cameras.to(device)
         return self
 
-    def forward(self, meshes, R, T, viz_purpose=False, **kwargs):
-        if self.shading_type != 'raw' or self.light_kwargs.get('name', 'ambient') != 'ambient':
-            raise NotImplementedError('lit shading (renderer_light) is a visualisation-only path: not in the B200 hot path yet')
-        faces_alpha = kwargs.get('faces_alpha')
+    def _flat_shade(self, verts, faces, R):
+        """PyTorch3D flat shading with ambient + directional diffuse light, as the reference configures renderer_light
+        (dbw.py:139-143): per (view, face) colour multiplier ambient + diffuse * relu(n_f . l_b), the light direction
+        being re-expressed per view so that it is fixed relative to the camera (renderer.py:87-89)."""
+        lk = self.light_kwargs
+        col = lambda k, d: torch.tensor(lk.get(k, d), dtype=torch.float32, device=verts.device).reshape(-1, 3)[0]
+        ambient, diffuse = col('ambient_color', [[0.5] * 3]), col('diffuse_color', [[0.3] * 3])
+        direction = col('direction', [[0, 1, 0]])
+        fv = verts[faces.long()]
+        n = torch.cross(fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0], dim=-1)
+        n = F.normalize(n, dim=-1, eps=1e-6)
+        l = F.normalize(direction[None] @ R.transpose(1, 2), dim=-1, eps=1e-6)          # (B,1,3)
+        cos = torch.relu((n[None] * l).sum(-1))                                          # (B,F)
+        return ambient[None, None] + diffuse[None, None] * cos[..., None]
+
+    def _scene(self, meshes):
         verts, faces = meshes.get_mesh_verts_faces(0)
-        txt = meshes.textures
-        fvu, fmap = txt.scene_arrays()
-        maps, table = txt.packed_maps()
+        fvu, fmap = meshes.textures.scene_arrays()
+        maps, table = meshes.textures.packed_maps()
+        return verts, faces, fvu, fmap, maps, table
+
+    def forward(self, meshes, R, T, viz_purpose=False, **kwargs):
+        lit = self.light_kwargs.get('name', 'ambient') == 'directional'
+        if self.shading_type not in ('raw', 'flat') or (lit != (self.shading_type == 'flat')):
+            raise NotImplementedError(f'shading_type={self.shading_type} with lights={self.light_kwargs.get("name", "ambient")}: '
+                                      'only raw+ambient (training) and flat+directional (renderer_light) are implemented')
+        faces_alpha = kwargs.get('faces_alpha')
+        verts, faces, fvu, fmap, maps, table = self._scene(meshes)
         H, W = self.img_size
         intr = self.cameras.intrinsics()
+        shade = self._flat_shade(verts, faces, R) if lit else None
         if viz_purpose:
             # VizMeshRenderer (renderer.py:56-60,178-183): hard 4x supersampled render, box-filtered, no gradient
             with torch.no_grad():
                 out = render_scene(verts, faces, fvu, fmap, maps, table, R, T, intr, (H * 4, W * 4), 0.0, 1, self.z_clip,
                                    self.detach_bary, self.clip_inside, self.background_color, faces_alpha,
-                                   self.perspective_correct)
+                                   self.perspective_correct, face_shade=shade)
                 return F.avg_pool2d(out, kernel_size=4, stride=4)
         return render_scene(verts, faces, fvu, fmap, maps, table, R, T, intr, (H, W), self.sigma, self.faces_per_pixel,
                             self.z_clip, self.detach_bary, self.clip_inside, self.background_color, faces_alpha,
-                            self.perspective_correct, blur_radius=self.blur_radius)
+                            self.perspective_correct, blur_radius=self.blur_radius, face_shade=shade)
+
+    # ------------------------------------------------------------------ edge overlays (renderer.py:134-175)
+    @torch.no_grad()
+    def render_edges(self, meshes, R, T, image_size=None, linewidth=1, return_pix2face=False, faces_per_pixel=1):
+        """mask of the pixels closer than `linewidth` pixels to an edge of the face(s) they see: a hard rasterization whose
+        signed squared NDC distances are thresholded at (linewidth * 2 / min(image_size))^2."""
+        image_size = tuple(image_size or self.img_size)
+        verts, faces, fvu, fmap, maps, table = self._scene(meshes)
+        _, ids, dists = render_scene(verts, faces, fvu, fmap, maps, table, R, T, self.cameras.intrinsics(), image_size, 0.0,
+                                     faces_per_pixel, self.z_clip, perspective_correct=self.perspective_correct,
+                                     return_dists=True)
+        mask = (-dists < (linewidth * 2 / min(image_size)) ** 2).float().max(1, keepdim=True)[0]       # (B,1,H,W)
+        if return_pix2face:
+            Fn = faces.shape[0]
+            slot = ids[:, 0].long()
+            face = torch.where(slot >= Fn, slot - Fn, slot)                 # second halves of z-clipped quads -> their face
+            pix2face = torch.where(slot >= 0, face + torch.arange(len(R), device=slot.device)[:, None, None] * Fn, slot)
+            return mask, pix2face                                           # batch-packed ids like fragments.pix_to_face
+        return mask
+
+    def draw_edges(self, img, meshes, R=None, T=None, colors=None, linewidth=1, antialias=True):
+        dev = meshes.device
+        B = img.shape[0] if isinstance(img, torch.Tensor) and img.dim() == 4 else 1
+        if R is None:
+            R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
+        if T is None:
+            T = torch.zeros(1, 3, device=dev).expand(B, -1)
+        if colors is None:
+            colors = (1, 0, 0)
+        assert isinstance(img, torch.Tensor), 'PIL inputs are an export path of the reference: pass a (B,3,H,W) tensor'
+        img_size = tuple(img.shape[-2:])
+        if antialias:
+            img_size, linewidth = (img_size[0] * 4, img_size[1] * 4), linewidth * 4
+        if isinstance(colors, (list, tuple)):
+            colors = torch.Tensor(colors)
+        mask, pix2face = self.render_edges(meshes, R, T, image_size=img_size, linewidth=linewidth, return_pix2face=True)
+        if colors.dim() == 2:
+            face_img = colors.to(mask.device)[pix2face].permute(0, 3, 1, 2)               # one colour per (packed) face
+        else:
+            face_img = colors.to(mask.device)[:, None, None].expand(-1, *mask.shape[2:])[None].expand(len(mask), -1, -1, -1)
+        if antialias:
+            mask, face_img = [F.avg_pool2d(t, kernel_size=4, stride=4) for t in [mask, face_img]]
+        return img * (1 - mask) + mask * face_img

@@ -94,6 +94,19 @@ int dbw_render_forward(const DbwRenderSettings* settings, const float* verts, co
                        float* out_rgba, int32_t* topk_ids, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Same, with the two optional extras the reference's visualisation paths need:
+ *   face_shade  (B,F,3) or NULL: per-view per-face colour multiplier = PyTorch3D flat shading with ambient + directional
+ *               diffuse light, as configured for renderer_light (src/model/dbw.py:139-143, renderer.py:87-97,195-205)
+ *   out_dists   (B,K,H,W) or NULL: signed squared NDC distance of each kept fragment to its face's nearest edge
+ *               (< 0 inside, -1 for empty slots) = fragments.dists, what render_edges thresholds (renderer.py:134-146)
+ */
+int dbw_render_forward_ex(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                          const float* faces_uvs, const int32_t* face_map, const float* maps,
+                          const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                          float* out_rgba, int32_t* topk_ids, void* workspace, size_t workspace_bytes,
+                          const float* face_shade, float* out_dists, void* stream);
+
+/*
  * Backward of the same (replaces autograd through layered_rgb_blend, grid_sample, interpolate_face_attributes
  * and _C.rasterize_meshes_backward).  grad_rgba (B,4,H,W).  Outputs accumulate:
  *   g_verts        (V,3)  [or (B,V,3) when verts_are_ndc]

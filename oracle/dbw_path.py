@@ -154,9 +154,30 @@ def layered_rgb_blend(colors, pix_to_face, dists, sigma, background=(0., 0., 0.)
     return torch.cat([rgb, a[..., None]], dim=-1).permute(0, 3, 1, 2)
 
 
+def flat_shade_multiplier(verts, faces, R, direction=(1, 0.25, -1), ambient=(0.7, 0.7, 0.7), diffuse=(0.4, 0.4, 0.4)):
+    """PyTorch3D flat_shading + DirectionalLights.diffuse for the reference's renderer_light (src/model/dbw.py:139-143):
+    colour = (ambient + diffuse * relu(n_face . l)) * texel (+ specular 0); the reference re-expresses the light direction
+    per view as direction @ R^T (src/model/renderer.py:87-89).  Returns (B,F,3)."""
+    fv = verts[faces]
+    n = F.normalize(torch.cross(fv[:, 1] - fv[:, 0], fv[:, 2] - fv[:, 0], dim=-1), p=2, dim=-1, eps=1e-6)
+    d = torch.as_tensor(direction, dtype=verts.dtype)[None]
+    l = F.normalize(d[None] @ R.to(verts.dtype).transpose(1, 2), p=2, dim=-1, eps=1e-6)      # (B,1,3)
+    cos = torch.relu((n[None] * l).sum(-1))
+    return torch.as_tensor(ambient, dtype=verts.dtype)[None, None] + torch.as_tensor(diffuse, dtype=verts.dtype)[None, None] * cos[..., None]
+
+
+def render_edges(scene, R, T, K, image_size, linewidth=1, z_clip=None, faces_per_pixel=1):
+    """Renderer.render_edges (src/model/renderer.py:134-146): K=1 hard rasterization, mask = -dists < (lw*2/min(size))^2."""
+    verts_ndc = pt3d.world_to_ndc(scene['verts'], R, T, K)
+    fr = pt3d.rasterize_meshes(verts_ndc, scene['faces'], image_size, blur_radius=0.0, faces_per_pixel=faces_per_pixel,
+                               perspective_correct=True, clip_barycentric_coords=True, z_clip_value=z_clip)
+    mask = (-fr.dists < (linewidth * 2 / min(image_size)) ** 2).to(verts_ndc)[:, None].max(-1)[0]
+    return mask, fr.pix_to_face[..., 0]
+
+
 def render(scene, R, T, K, image_size, sigma=1e-4, faces_per_pixel=25, z_clip=None, detach_bary=False,
            clip_inside=True, background=(0., 0., 0.), faces_alpha=None, perspective_correct=True, eps=1e-8,
-           return_fragments=False):
+           return_fragments=False, face_shade=None):
     """Renderer.forward (renderer.py:84-98) for the 'raw' LayeredShader: scene is a dict with
     verts (V,3), faces (F,3), faces_verts_uvs (F,3,2), face_map (F,), maps [ (Ht,Wt,3) ];
     R (B,3,3), T (B,3), K (4,4); faces_alpha None | (F,) | (B*F,) (batch-packed, dbw.py:219).  -> (B,4,H,W)."""
@@ -168,6 +189,9 @@ def render(scene, R, T, K, image_size, sigma=1e-4, faces_per_pixel=25, z_clip=No
     if detach_bary:
         frags.bary_coords = frags.bary_coords.detach()
     texels = pt3d.sample_textures(frags, scene['faces_verts_uvs'], scene['face_map'], scene['maps'])
+    if face_shade is not None:                      # (B,F,3) flat-shading multiplier, batch-packed like pix_to_face
+        Fn = scene['faces'].shape[0]
+        texels = texels * face_shade.reshape(-1, 3)[frags.pix_to_face.clamp(min=0)] * (frags.pix_to_face >= 0)[..., None]
     if faces_alpha is not None and faces_alpha.numel() == scene['faces'].shape[0]:
         faces_alpha = faces_alpha.repeat(B)
     out = layered_rgb_blend(texels, frags.pix_to_face, frags.dists, sigma, background, clip_inside, faces_alpha)

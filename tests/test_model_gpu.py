@@ -238,3 +238,25 @@ def test_graphed_step_recaptures_when_the_schedule_switches_phase():
     model.opacity_noise_buffer = None
     ref = model(inp, None)['rgb'].item()
     assert abs(l_fine - ref) < 1e-7 and abs(l_fine - l_coarse) > 1e-9
+
+
+def test_visualisation_paths_of_the_trainer_run():
+    """what src/trainer.py:177-199 calls every val_stat_interval: predict(w_edges=True), predict_synthetic,
+    get_arranged_block_txt -- shapes, ranges, and that the overlay only touches pixels near face edges."""
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.eval()
+    with torch.no_grad():
+        rec = model.predict(inp, None)
+        rec_e = model.predict(inp, None, w_edges=True)
+        syn = model.predict_synthetic(inp, None)
+        txt = model.get_arranged_block_txt()
+    assert rec.shape == rec_e.shape == syn.shape == inp['imgs'].shape and txt.shape[:2] == (1, 3)
+    for t in (rec, rec_e, syn):
+        assert torch.isfinite(t).all() and t.min() >= -1e-5 and t.max() <= 1 + 1e-5
+    changed = ((rec - rec_e).abs().max(1)[0] > 1e-6).float().mean().item()
+    assert 0.005 < changed < 0.6                                  # lines, not areas
+    white = (syn.min(1)[0] > 0.999).float().mean().item()         # white background where no opaque block is
+    assert 0.1 < white < 0.99
+    cols = model.get_scene_face_colors()
+    assert cols.shape == (model.env_n_faces + model.blocks_n_faces, 3) and cols.min() >= 0 and cols.max() <= 1

@@ -213,3 +213,52 @@ def test_bmvs_shape_non_square_backward():
     p = {k: v.clone().requires_grad_(True) for k, v in p.items()}
     blocks, alpha = tpl.build_blocks(p)
     _grad_parity(blocks, R, T, K, (72, 96), 5e-6, 10, 0.001, True, None, True, seed=6)
+
+
+def test_flat_shaded_viz_render_matches_oracle():
+    """renderer_light path: flat shading with a camera-fixed directional light, white background,
+    4x supersampled hard render + 4x4 box filter (viz_purpose=True)."""
+    import torch.nn.functional as F
+    from dbw_b200 import Renderer, Meshes, TexturesUV, join_meshes_as_scene
+    dev = _dev()
+    tpl, p, R, T, K = _setup(n_blocks=3)
+    blocks, alpha = tpl.build_blocks(p)
+    shade = D.flat_shade_multiplier(blocks['verts'], blocks['faces'], R)
+    ref = D.render(blocks, R, T, K, (128, 160), sigma=0, faces_per_pixel=1, z_clip=0.001, background=(1., 1., 1.), face_shade=shade)
+    ref = F.avg_pool2d(ref, 4, 4)
+    rend = Renderer((32, 40), faces_per_pixel=1, sigma=0, z_clip=0.001, cameras={'name': 'perspective'}, shading_type='flat',
+                    background_color=(1, 1, 1), lights={'name': 'directional', 'direction': [[1, 0.25, -1]],
+                                                        'ambient_color': [[0.7] * 3], 'diffuse_color': [[0.4] * 3],
+                                                        'specular_color': [[0.] * 3]}).to(dev)
+    rend.update_cameras(device=dev, K=K[None].to(dev))
+    # the same scene as Meshes / TexturesUV objects (3 blocks joined)
+    nb, Fn = 3, tpl.BNF
+    verts = blocks['verts'].reshape(nb, -1, 3).to(dev)
+    faces = tpl.block_faces[None].expand(nb, -1, -1).to(dev)
+    maps = torch.stack(blocks['maps']).to(dev)
+    txt = TexturesUV(maps, tpl.block_faces_uvs[None].expand(nb, -1, -1).to(dev), tpl.block_verts_uvs[None].expand(nb, -1, -1).to(dev))
+    scene = join_meshes_as_scene(Meshes(verts, faces, txt))
+    out = rend(scene.extend(2), R.to(dev), T.to(dev), viz_purpose=True)
+    err = (out.cpu() - ref).abs()
+    assert (err > 1e-4).float().mean().item() < 2e-3 and err.max().item() < 0.1, err.max().item()   # 16 hard samples per pixel
+
+
+def test_render_edges_matches_oracle():
+    """edge overlay: K=1 hard rasterization, signed distances thresholded at the line width."""
+    from dbw_b200 import Renderer, Meshes, TexturesUV, join_meshes_as_scene
+    dev = _dev()
+    tpl, p, R, T, K = _setup(n_blocks=3)
+    blocks, alpha = tpl.build_blocks(p)
+    mask_ref, p2f_ref = D.render_edges(blocks, R, T, K, (96, 128), linewidth=2, z_clip=0.001)
+    rend = Renderer((96, 128), faces_per_pixel=10, z_clip=0.001, cameras={'name': 'perspective'}).to(dev)
+    rend.update_cameras(device=dev, K=K[None].to(dev))
+    nb = 3
+    txt = TexturesUV(torch.stack(blocks['maps']).to(dev), tpl.block_faces_uvs[None].expand(nb, -1, -1).to(dev),
+                     tpl.block_verts_uvs[None].expand(nb, -1, -1).to(dev))
+    scene = join_meshes_as_scene(Meshes(blocks['verts'].reshape(nb, -1, 3).to(dev), tpl.block_faces[None].expand(nb, -1, -1).to(dev), txt))
+    mask, p2f = rend.render_edges(scene.extend(2), R.to(dev), T.to(dev), linewidth=2, return_pix2face=True)
+    assert (p2f.cpu() != p2f_ref).float().mean().item() < 1e-4
+    assert (mask.cpu() != mask_ref).float().mean().item() < 2e-4
+    img = torch.rand(2, 3, 24, 32, device=dev)
+    drawn = rend.draw_edges(img, scene.extend(2), R.to(dev), T.to(dev), colors=(1, 0, 0), linewidth=1)
+    assert drawn.shape == img.shape and torch.isfinite(drawn).all() and (drawn - img).abs().max() > 0.1
