@@ -434,17 +434,16 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
   const int xi = tx0 + (warp & 1) * 8 + (lane & 7);
   const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
   const bool live = xi < P.W && yi < P.H;
-  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
-  // NDC extent of the tile's pixel centres (+X is left, +Y is up): computed by four threads, shared by the CTA
-  __shared__ float s_ext[4];
-  if (tid < 4) {
-    const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
-    s_ext[tid] = tid == 0 ? pix_to_ndc(P.W - 1 - tx1, P.W, P.H) : tid == 1 ? pix_to_ndc(P.W - 1 - tx0, P.W, P.H)
-               : tid == 2 ? pix_to_ndc(P.H - 1 - ty1, P.H, P.W) : pix_to_ndc(P.H - 1 - ty0, P.H, P.W);
-  }
+  // NDC coordinates of the tile's 16 pixel columns and 16 rows (+X is left, +Y is up): 32 exact evaluations per CTA,
+  // shared through shared memory, instead of two per thread
+  __shared__ float s_ndc[TILE_W + TILE_H];
+  if (tid < TILE_W) s_ndc[tid] = pix_to_ndc(P.W - 1 - min(tx0 + tid, P.W - 1), P.W, P.H);
+  else if (tid < TILE_W + TILE_H) s_ndc[tid] = pix_to_ndc(P.H - 1 - min(ty0 + tid - TILE_W, P.H - 1), P.H, P.W);
   if (tid == 0) { s_count = 0; mbar_init(&s_bar, 1); }
   __syncthreads();
-  const float t_xmin = s_ext[0], t_xmax = s_ext[1], t_ymin = s_ext[2], t_ymax = s_ext[3];
+  const f2 p = {s_ndc[xi - tx0], s_ndc[TILE_W + yi - ty0]};
+  const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
+  const float t_xmin = s_ndc[tx1 - tx0], t_xmax = s_ndc[0], t_ymin = s_ndc[TILE_W + ty1 - ty0], t_ymax = s_ndc[TILE_W];
   // tiles outside the union of the view's face boxes have nothing to rasterize: no scan
   const int* vb = P.view_bbox + view * 4;
   const bool tile_empty = ord2f(vb[0]) > t_xmax || ord2f(vb[1]) < t_xmin || ord2f(vb[2]) > t_ymax || ord2f(vb[3]) < t_ymin;
