@@ -138,8 +138,9 @@ def run_ours(args):
     def step_eager():
         return vp.forward_backward(dev_local, None, already_sharded=True, n_total_views=B)
 
-    graphed = None if args.no_graph else GraphedStep(vp, dev_local, B)
-    piped = None if args.no_graph else PipelinedGraphedStep(vp, dev_local, B)
+    car = args.allreduce_in_graph
+    graphed = None if args.no_graph else GraphedStep(vp, dev_local, B, capture_all_reduce=car)
+    piped = None if args.no_graph else PipelinedGraphedStep(vp, dev_local, B, capture_all_reduce=car)
 
     def step_resident():
         return graphed.run() if graphed is not None else step_eager()
@@ -326,6 +327,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='submit the step eagerly instead of replaying a CUDA graph')
+    ap.add_argument('--allreduce-in-graph', action='store_true', help='capture the NCCL all-reduce into the CUDA graph (experimental)')
     args = ap.parse_args()
     if args.impl == 'reference':
         if args.steps > 5:

@@ -8,8 +8,11 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3):
+    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3, capture_all_reduce=False):
         self.vp, self.model = view_parallel, view_parallel.model
+        # optionally capture the gradient all-reduce INTO the graph.  Off by default: with this image's NCCL the captured
+        # collective hung on 2 GPUs (measured, round 1), so the all-reduce is issued right after the replay instead.
+        self.capture_all_reduce = capture_all_reduce and view_parallel.world_size > 1
         self.n_total = n_total_views
         dev = example_inp['imgs'].device
         self.static_inp = {k: v.clone() for k, v in example_inp.items()}
@@ -42,6 +45,8 @@ class GraphedStep:
         losses = self.model(self.static_inp, None)
         total = self.vp.weighted_total(losses, len(self.static_inp['imgs']), self.n_total)
         total.backward()
+        if self.capture_all_reduce:
+            self.vp.bucket.all_reduce(self.vp.group)
         return losses
 
     def run(self, inp=None, non_blocking=True):
@@ -54,7 +59,8 @@ class GraphedStep:
             self._capture()
         self.model.opacity_noise_buffer.normal_(generator=self.gen)     # identical on every rank (same seed, same count)
         self.graph.replay()
-        self.vp.bucket.all_reduce(self.vp.group)
+        if not self.capture_all_reduce:
+            self.vp.bucket.all_reduce(self.vp.group)
         return self.losses
 
 
@@ -63,8 +69,8 @@ class PipelinedGraphedStep:
     host->device on a side stream (what a prefetching DataLoader does for src/trainer.py:141).  `run(host_inp)` returns
     the losses of the step that consumed `host_inp`."""
 
-    def __init__(self, view_parallel, example_inp, n_total_views):
-        self.steps = [GraphedStep(view_parallel, example_inp, n_total_views) for _ in range(2)]
+    def __init__(self, view_parallel, example_inp, n_total_views, capture_all_reduce=False):
+        self.steps = [GraphedStep(view_parallel, example_inp, n_total_views, capture_all_reduce=capture_all_reduce) for _ in range(2)]
         self.copy_stream = torch.cuda.Stream()
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # inputs of buffer b have landed
         self.free = [torch.cuda.Event(), torch.cuda.Event()]       # buffer b has been consumed by its replay
