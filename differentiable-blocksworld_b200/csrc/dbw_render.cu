@@ -381,8 +381,9 @@ __device__ __forceinline__ unsigned long long make_key(float pz, int slot) {
 // opacity of one fragment from its signed squared distance (layered_rgb_blend, src/model/renderer.py:252-257)
 __device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_inside) {
   if (sigma == 0.f) return d <= 0.f ? 1.f : 0.f;
-  if (clip_inside) return expf(-fmaxf(d, 0.f) / sigma);
-  return 1.f / (1.f + expf(d / sigma));
+  // __expf: ex2.approx-based, relative error ~1e-6 over the halo range |d/sigma| <= 9.3 -- far inside the 1e-4 image tolerance
+  if (clip_inside) return __expf(-fmaxf(d, 0.f) / sigma);
+  return 1.f / (1.f + __expf(d / sigma));
 }
 
 // shared by forward shading and backward: colour of fragment (slot) at pixel p
