@@ -1,11 +1,16 @@
-"""Drop-in for the reference's scene model on the render hot path: `DifferentiableBlocksWorld`
-(src/model/dbw.py:38-462).  Same constructor kwargs (configs/*.yml parse unmodified), same parameter / buffer names
-(checkpoints and the texture-prefixed Adam group of src/optimizer.py:9-14 keep working), same
-`forward(inp, labels) -> dict of losses` / `predict(inp, labels)` signatures, so src/trainer.py:137-147 can drive it.
-Rendering goes through the B200 kernels (renderer.py); compositing + RGB loss are one fused kernel when possible.
+"""Scene model of the render hot path: a drop-in for the reference's `DifferentiableBlocksWorld`
+(/root/reference src/model/dbw.py:38-462) as far as src/trainer.py, src/optimizer.py and configs/*.yml see it --
+same constructor kwargs, same parameter / buffer names (checkpoints, the `texture*` Adam group), same
+`forward(inp, labels) -> {loss name: tensor}` / `predict(...)` / `build_*` / `get_opacities` surface.
 
-Visualisation helpers of SURVEY.md section 8f are covered as far as the trainer's periodic logging needs them (predict(w_edges=True),
-predict_synthetic, get_arranged_block_txt); qualitative_eval / video / OBJ export remain out of scope."""
+What is different underneath is everything that costs time:
+  * leaf parameters -> world-space vertices and float4 texel atlases by two fused kernels (scene_ops.py) instead of
+    ~200 eager ops; the background sphere's world vertices are a constant;
+  * blocks dropped by the opacity filters stay in the mesh and are DISABLED (face_map = -1): fixed shapes, no host
+    synchronisation, so a whole optimisation step replays as one CUDA graph (graph.py);
+  * both render passes, compositing and the RGB loss go through the C-ABI kernels (renderer.py).
+The reference-shaped `build_bkg / build_ground / build_blocks / build_scene` (returning Meshes) remain for the
+visualisation / export call sites (trainer.py:181-198,261-263)."""
 import ctypes
 from collections import OrderedDict
 from copy import deepcopy
@@ -15,18 +20,28 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, geometry as G
+from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
 from .scene_ops import scene_geometry, texture_atlas
-from .structures import Meshes, TexturesUV, join_meshes_as_scene, join_meshes_as_batch
+from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
-DECIMATE_FACTOR = 8
-OVERLAP_N_POINTS = 1000
-OVERLAP_N_BLOCKS = 1.95
-OVERLAP_TEMPERATURE = 0.005
-DIRECTION_LIGHT = [1, 0.25, -1]
+# accepted keys and defaults of the config sub-dicts (configs/*/*.yml -> model.{mesh,rend_optim,loss}); unknown keys are
+# an error, as in the reference (dbw.py:71,129,157)
+MESH_KEYS = dict(n_blocks=1, S_world=1, R_world=(0, 0, 0), T_world=(0., 0., 0.), z_far=10, ratio_block_scene=0.25,
+                 txt_size=256, txt_bkg_upscale=1, scale_min=0.2, opacity_init=0.5, T_range=(1, 1, 1), T_init_mode='gauss')
+REND_OPTIM_KEYS = dict(opacity_noise=False, decouple_rendering=False, coarse_learning=True, decimate_txt=False,
+                       decimate_factor=8, kill_blocks=False)
+LOSS_KEYS = dict(rgb_weight=1.0, perceptual_weight=0, parsimony_weight=0, scale_weight=0, tv_weight=0, overlap_weight=0,
+                 name='mse', perceptual_name='lpips', tv_type='l2sq')
+LIGHT_FOR_SYNTHETIC_VIEWS = {'name': 'directional', 'direction': [[1, 0.25, -1]], 'ambient_color': [[0.7, 0.7, 0.7]],
+                             'diffuse_color': [[0.4, 0.4, 0.4]], 'specular_color': [[0., 0., 0.]]}
 
-tv_norm_funcs = {'l2': lambda x: torch.norm(x, dim=-1), 'l1': lambda x: x.abs().sum(-1), 'l2sq': lambda x: (x ** 2).sum(-1)}
+
+def _parse(cfg, spec, what):
+    cfg = dict(cfg or {})
+    out = {k: cfg.pop(k, d) for k, d in spec.items()}
+    assert not cfg, f'unknown {what} options: {cfg}'
+    return out
 
 
 class _CompositeMSE(torch.autograd.Function):
@@ -64,144 +79,114 @@ class DifferentiableBlocksWorld(nn.Module):
 
     def __init__(self, img_size, **kwargs):
         super().__init__()
-        self._init_kwargs = deepcopy(kwargs)
-        self._init_kwargs['img_size'] = img_size
-        self._init_blocks(**kwargs.get('mesh', {}))
-        self._init_renderer(img_size, **kwargs.get('renderer', {}))
-        self._init_rend_optim(**kwargs.get('rend_optim', {}))
-        self._init_loss(**kwargs.get('loss', {}))
+        self._init_kwargs = dict(deepcopy(kwargs), img_size=img_size)
+        mesh = _parse(kwargs.get('mesh'), MESH_KEYS, 'mesh')
+        sched = _parse(kwargs.get('rend_optim'), REND_OPTIM_KEYS, 'rend_optim')
+        loss = _parse(kwargs.get('loss'), LOSS_KEYS, 'loss')
+
+        for k in ('n_blocks', 'S_world', 'z_far', 'ratio_block_scene', 'txt_size', 'txt_bkg_upscale', 'scale_min'):
+            setattr(self, k, mesh[k])
+        self._build_template(mesh['R_world'], mesh['T_world'])
+        self._build_parameters(mesh['opacity_init'], mesh['T_range'], mesh['T_init_mode'])
+        self._build_renderers(img_size, kwargs.get('renderer', {}))
+
+        # training schedule switches: bool, or the epoch from which the feature is OFF (is_live)
+        self.opacity_noise, self.decouple_rendering = sched['opacity_noise'], sched['decouple_rendering']
+        self.coarse_learning, self.decimate_txt = sched['coarse_learning'], sched['decimate_txt']
+        self.decim_factor, self.kill_blocks = sched['decimate_factor'], sched['kill_blocks']
+
+        weights = {k[:-len('_weight')]: loss[k] for k in ('rgb_weight', 'perceptual_weight', 'parsimony_weight',
+                                                          'scale_weight', 'tv_weight', 'overlap_weight')}
+        self.loss_weights = {k: w for k, w in weights.items() if w > 0}
+        self.loss_names = [f'loss_{k}' for k in self.loss_weights] + ['loss_total']
+        self.tv_norm = L.TV_NORMS[loss['tv_type']]
+        self.criterion = {'mse': nn.MSELoss, 'l2': nn.MSELoss, 'l1': nn.L1Loss}[loss['name']]()
+        if 'perceptual' in self.loss_weights:
+            # LPIPS is a VGG16 conv network (cuDNN / tensor cores): outside the render hot path;
+            # any callable (imgs, rec) -> scalar can be installed with set_perceptual_loss()
+            self.perceptual_loss = _make_perceptual(loss['perceptual_name'])
         self.cur_epoch = 0
-        # data-parallel context (parallel.py): this rank renders `len(inp['imgs'])` of `n_total_views` views
-        self.n_total_views = None
-        self.noise_generator = None
-        # static topology (default): blocks dropped by the opacity filters (dbw.py:316-328) keep their slot in the mesh
-        # and are DISABLED through face_map = -1 instead of being sliced out -> identical images and gradients, but no
-        # host sync and fixed shapes, so the whole step can be captured in a CUDA graph (graph.py)
-        self.static_topology = True
-        self.opacity_noise_buffer = None          # optional pre-drawn randn (N,) used instead of drawing inside forward
-        self._static_arrays = None
-        # fused scene construction (scene_ops.py): mesh build + texture prep as one kernel each way
-        self.fused_scene = True
-        self._fused_static = None
-        self.overlap_passes = False               # environment pass on a side stream, concurrent with the blocks pass
+
+        # execution options of this implementation
+        self.static_topology = True       # disable filtered blocks via face_map = -1 instead of slicing (no host sync)
+        self.fused_scene = True           # scene_ops kernels for mesh build + texture prep
+        self.overlap_passes = False       # environment pass on a side stream (measured: +1 %)
+        self.n_total_views = None         # data-parallel context (parallel.py): views of the whole step
+        self.noise_generator = None       # RNG shared by all ranks for opacity noise / overlap samples
+        self.opacity_noise_buffer = None  # pre-drawn randn (N,) used instead of drawing inside forward (graph.py)
+        self._static = None
         self._env_stream = None
+        self._reg_state_stale = False
+
+    # ------------------------------------------------------------------ construction
+    def _build_template(self, R_world, T_world):
+        """static topology: inward-facing background icosphere (level 2, radius z_far), ground plane subdivided 3x,
+        N block icospheres (level 1) with seam/pole-fixed spherical UVs padded circularly along u (dbw.py:73-96)"""
+        N, TS = self.n_blocks, self.txt_size
+        self.register_buffer('R_world', G.euler_world_rotation(*R_world))
+        self.register_buffer('T_world', torch.tensor([float(t) for t in T_world])[None])
+        sphere_v, sphere_f = G.ico_sphere(2)
+        self.bkg = Meshes((sphere_v * self.z_far)[None], sphere_f.flip(1)[None])
+        self.register_buffer('bkg_verts_uvs', G.spherical_uv(self.bkg.verts_packed()))
+        plane_v, plane_f = G.unit_plane()
+        plane_v = plane_v * torch.tensor([self.z_far, 1., self.z_far])
+        for _ in range(3):
+            plane_v, plane_f = G.subdivide_mesh(plane_v, plane_f)
+        self.ground = Meshes(plane_v[None], plane_f[None])
+        self.register_buffer('ground_verts_uvs', (plane_v[:, [0, 2]] / self.z_far + 1) / 2)
+        unit_v, unit_f = G.ico_sphere(1)
+        self.blocks = Meshes((unit_v * self.ratio_block_scene).expand(N, -1, -1).clone(), unit_f.expand(N, -1, -1).clone())
+        local = self.blocks.verts_padded() / self.ratio_block_scene
+        self.register_buffer('sq_eta', torch.asin(local[..., 1]))
+        self.register_buffer('sq_omega', torch.atan2(local[..., 0], local[..., 2]))
+        faces_uvs, uvs = G.icosphere_uvs(1)
+        u_lo, u_hi = uvs[:, 0].min().item(), uvs[:, 0].max().item()
+        pad_left, pad_right = abs(int(np.floor(u_lo * TS))), int(np.ceil((u_hi - 1) * TS))
+        self.txt_padding = (pad_left, pad_right)
+        self.BNF = len(faces_uvs)
+        self.register_buffer('block_faces_uvs', faces_uvs)
+        self.register_buffer('block_verts_uvs', torch.stack([(uvs[:, 0] * TS + pad_left) / (TS + pad_left + pad_right), uvs[:, 1]], -1))
+
+    def _build_parameters(self, opacity_init, T_range, T_init_mode):
+        """leaf parameters, initialised as dbw.py:84,98-119 (random draws in the same order: S, rotations, T, textures)"""
+        N, TS, up = self.n_blocks, self.txt_size, self.txt_bkg_upscale
+        T_range = torch.tensor([float(t) for t in T_range])
+        self.sq_eps = nn.Parameter(torch.zeros(N, 2))
+        self.R_6d_ground = nn.Parameter(torch.tensor([[1., 0., 0., 0., 1., 0.]]))
+        self.T_ground = nn.Parameter(torch.tensor([[0., -0.9 * T_range[1].item(), 0.]]))
+        self.S = nn.Parameter((torch.rand(N, 3) + 0.5 - self.scale_min).log())
+        self.R_6d = nn.Parameter(G.matrix_to_rotation_6d(G.random_rotations(N)))
+        if T_init_mode == 'gauss':
+            T0 = torch.randn(N, 3) / 2 * T_range
+        elif T_init_mode == 'uni':
+            T0 = (2 * torch.rand(N, 3) - 1) * T_range
+        else:
+            raise NotImplementedError(T_init_mode)
+        self.T = nn.Parameter(T0)
+        self.alpha_logit = nn.Parameter(torch.logit(torch.full((N,), float(opacity_init))) + 1e-3)
+        self.texture_bkg = nn.Parameter(torch.randn(1, TS * up, TS * up, 3) / 10)
+        self.texture_ground = nn.Parameter(torch.randn(1, TS * up, TS * up, 3) / 10)
+        self.textures = nn.Parameter(torch.randn(N, TS, TS, 3) / 10)
+
+    def _build_renderers(self, img_size, cfg):
+        """the four renderers of dbw.py:131-143: coarse (config sigma), fine (5e-6), environment (hard, K=1, gradients
+        through barycentrics), and the lit flat-shaded one for synthetic-colour views"""
+        variants = OrderedDict([
+            ('renderer', {}),
+            ('renderer_fine', {'sigma': 5e-6}),
+            ('renderer_env', {'sigma': 0, 'faces_per_pixel': 1, 'detach_bary': False}),
+            ('renderer_light', {'sigma': 0, 'faces_per_pixel': 1, 'detach_bary': False, 'lights': LIGHT_FOR_SYNTHETIC_VIEWS,
+                                'shading_type': 'flat', 'background_color': (1, 1, 1)}),
+        ])
+        for attr, override in variants.items():
+            setattr(self, attr, Renderer(img_size, **dict(deepcopy(cfg), **deepcopy(override))))
+
+    def _renderers(self):
+        return self.renderer, self.renderer_fine, self.renderer_env, self.renderer_light
 
     @property
     def init_kwargs(self):
         return deepcopy(self._init_kwargs)
-
-    # ------------------------------------------------------------------ construction (dbw.py:55-163)
-    def _init_blocks(self, **kwargs):
-        self.n_blocks = kwargs.pop('n_blocks', 1)
-        self.S_world = kwargs.pop('S_world', 1)
-        elev, azim, roll = kwargs.pop('R_world', [0, 0, 0])
-        self.register_buffer('R_world', G.euler_world_rotation(elev, azim, roll))
-        self.register_buffer('T_world', torch.Tensor(kwargs.pop('T_world', [0., 0., 0.]))[None])
-        self.z_far = kwargs.pop('z_far', 10)
-        self.ratio_block_scene = kwargs.pop('ratio_block_scene', 1 / 4)
-        self.txt_size = kwargs.pop('txt_size', 256)
-        self.txt_bkg_upscale = kwargs.pop('txt_bkg_upscale', 1)
-        self.scale_min = kwargs.pop('scale_min', 0.2)
-        opacity_init = kwargs.pop('opacity_init', 0.5)
-        T_range = kwargs.pop('T_range', [1, 1, 1])
-        T_init_mode = kwargs.pop('T_init_mode', 'gauss')
-        assert len(kwargs) == 0, kwargs
-
-        # spherical background (faces flipped to look inward) and planar ground
-        bv, bf = G.ico_sphere(2)
-        self.bkg = Meshes((bv * self.z_far)[None], bf.flip(1)[None])
-        self.register_buffer('bkg_verts_uvs', G.spherical_uv(self.bkg.verts_packed()))
-        gv, gf = G.unit_plane()
-        gv = gv * torch.Tensor([self.z_far, 1, self.z_far])[None]
-        for _ in range(3):
-            gv, gf = G.subdivide_mesh(gv, gf)
-        self.ground = Meshes(gv[None], gf[None])
-        self.register_buffer('ground_verts_uvs', (gv[:, [0, 2]] / self.z_far + 1) / 2)
-
-        # primitive blocks
-        sv, sf = G.ico_sphere(1)
-        N = self.n_blocks
-        self.blocks = Meshes((sv * self.ratio_block_scene)[None].repeat(N, 1, 1), sf[None].repeat(N, 1, 1))
-        self.sq_eps = nn.Parameter(torch.zeros(N, 2))
-        verts = self.blocks.verts_padded() / self.ratio_block_scene
-        self.register_buffer('sq_eta', torch.asin(verts[..., 1]))
-        self.register_buffer('sq_omega', torch.atan2(verts[..., 0], verts[..., 2]))
-        faces_uvs, verts_uvs = G.icosphere_uvs(1)
-        p_left = abs(int(np.floor(verts_uvs.min(0)[0][0].item() * self.txt_size)))
-        p_right = int(np.ceil((verts_uvs.max(0)[0][0].item() - 1) * self.txt_size))
-        verts_u = (verts_uvs[..., 0] * self.txt_size + p_left) / (self.txt_size + p_left + p_right)
-        self.txt_padding = p_left, p_right
-        self.BNF = len(faces_uvs)
-        self.register_buffer('block_faces_uvs', faces_uvs)
-        self.register_buffer('block_verts_uvs', torch.stack([verts_u, verts_uvs[..., 1]], dim=-1))
-
-        # learnable poses
-        self.R_6d_ground = nn.Parameter(torch.Tensor([[1., 0., 0., 0., 1., 0.]]))
-        self.T_ground = nn.Parameter(torch.Tensor([[0., -0.9 * T_range[1], 0.]]))
-        S_init = (torch.rand(N, 3) + 0.5 - self.scale_min).log()
-        R_6d_init = G.matrix_to_rotation_6d(G.random_rotations(N))
-        if T_init_mode == 'gauss':
-            T_init = torch.randn(N, 3) / 2 * torch.Tensor(T_range)
-        elif T_init_mode == 'uni':
-            T_init = (2 * torch.rand(N, 3) - 1) * torch.Tensor(T_range)
-        else:
-            raise NotImplementedError
-        self.S = nn.Parameter(S_init.clone())
-        self.R_6d = nn.Parameter(R_6d_init.clone())
-        self.T = nn.Parameter(T_init.clone())
-
-        # learnable opacities and textures
-        self.alpha_logit = nn.Parameter(torch.logit(torch.ones(N) * opacity_init) + 1e-3)
-        TS, s = self.txt_size, self.txt_bkg_upscale
-        self.texture_bkg = nn.Parameter(torch.randn(1, TS * s, TS * s, 3) / 10)
-        self.texture_ground = nn.Parameter(torch.randn(1, TS * s, TS * s, 3) / 10)
-        self.textures = nn.Parameter(torch.randn(N, TS, TS, 3) / 10)
-
-    def _init_rend_optim(self, **kwargs):
-        self.opacity_noise = kwargs.pop('opacity_noise', False)
-        self.decouple_rendering = kwargs.pop('decouple_rendering', False)
-        self.coarse_learning = kwargs.pop('coarse_learning', True)
-        self.decimate_txt = kwargs.pop('decimate_txt', False)
-        self.decim_factor = kwargs.pop('decimate_factor', DECIMATE_FACTOR)
-        self.kill_blocks = kwargs.pop('kill_blocks', False)
-        assert len(kwargs) == 0, kwargs
-
-    def _init_renderer(self, img_size, **kwargs):
-        kwargs = deepcopy(kwargs)
-        self.renderer = Renderer(img_size, **deepcopy(kwargs))
-        kwargs['sigma'] = 5e-6
-        self.renderer_fine = Renderer(img_size, **deepcopy(kwargs))
-        kwargs['faces_per_pixel'] = 1
-        kwargs['sigma'] = 0
-        kwargs['detach_bary'] = False
-        self.renderer_env = Renderer(img_size, **deepcopy(kwargs))
-        kwargs['lights'] = {'name': 'directional', 'direction': [DIRECTION_LIGHT], 'ambient_color': [[0.7, 0.7, 0.7]],
-                            'diffuse_color': [[0.4, 0.4, 0.4]], 'specular_color': [[0., 0., 0.]]}
-        kwargs['shading_type'] = 'flat'
-        kwargs['background_color'] = (1, 1, 1)
-        self.renderer_light = Renderer(img_size, **deepcopy(kwargs))
-
-    def _init_loss(self, **kwargs):
-        loss_weights = {
-            'rgb': kwargs.pop('rgb_weight', 1.0),
-            'perceptual': kwargs.pop('perceptual_weight', 0),
-            'parsimony': kwargs.pop('parsimony_weight', 0),
-            'scale': kwargs.pop('scale_weight', 0),
-            'tv': kwargs.pop('tv_weight', 0),
-            'overlap': kwargs.pop('overlap_weight', 0),
-        }
-        name = kwargs.pop('name', 'mse')
-        perceptual_name = kwargs.pop('perceptual_name', 'lpips')
-        self.tv_norm = tv_norm_funcs[kwargs.pop('tv_type', 'l2sq')]
-        assert len(kwargs) == 0, kwargs
-        self.loss_weights = {k: v for k, v in loss_weights.items() if v > 0}
-        self.loss_names = [f'loss_{n}' for n in list(self.loss_weights.keys()) + ['total']]
-        self.loss_name = name
-        self.criterion = {'mse': nn.MSELoss, 'l2': nn.MSELoss, 'l1': nn.L1Loss}[name]()
-        if 'perceptual' in self.loss_weights:
-            # LPIPS / VGG perceptual terms are dense-conv networks served by cuDNN: outside the render hot path
-            # (SURVEY 8a row a13).  Plug any callable (imgs, rec) -> scalar via set_perceptual_loss().
-            self.perceptual_loss = _make_perceptual(perceptual_name)
 
     def set_perceptual_loss(self, fn):
         self.perceptual_loss = fn
@@ -212,264 +197,123 @@ class DifferentiableBlocksWorld(nn.Module):
     def step(self):
         self.cur_epoch += 1
 
+    def is_live(self, name):
+        switch = getattr(self, name)
+        return switch if isinstance(switch, bool) else self.cur_epoch < switch
+
     def to(self, device):
         super().to(device)
         self.bkg, self.ground, self.blocks = self.bkg.to(device), self.ground.to(device), self.blocks.to(device)
-        for r in (self.renderer, self.renderer_fine, self.renderer_env, self.renderer_light):
+        for r in self._renderers():
             r.to(device)
         return self
 
-    @property
-    def bkg_n_faces(self):
-        return self.bkg.num_faces_per_mesh().sum().item()
+    bkg_n_faces = property(lambda self: int(self.bkg.num_faces_per_mesh().sum()))
+    ground_n_faces = property(lambda self: int(self.ground.num_faces_per_mesh().sum()))
+    env_n_faces = property(lambda self: self.bkg_n_faces + self.ground_n_faces)
+    blocks_n_faces = property(lambda self: int(self.blocks.num_faces_per_mesh().sum()))
 
-    @property
-    def ground_n_faces(self):
-        return self.ground.num_faces_per_mesh().sum().item()
-
-    @property
-    def env_n_faces(self):
-        return self.bkg_n_faces + self.ground_n_faces
-
-    @property
-    def blocks_n_faces(self):
-        return self.blocks.num_faces_per_mesh().sum().item()
-
-    def is_live(self, name):
-        milestone = getattr(self, name)
-        if isinstance(milestone, bool):
-            return milestone
-        return True if self.cur_epoch < milestone else False
-
-    # ------------------------------------------------------------------ forward (dbw.py:198-239)
+    # ------------------------------------------------------------------ one step
     def forward(self, inp, labels=None):
-        layers = self._render_layers(inp)
+        env_rgba, fg_rgba = self._render_layers(inp)
         imgs = inp['imgs']
         n_total = self.n_total_views or len(imgs)
-        if layers[1] is not None and isinstance(self.criterion, nn.MSELoss) and imgs.is_cuda:
-            rec, mse = _CompositeMSE.apply(layers[1], layers[0], imgs, n_total)
+        if fg_rgba is not None and isinstance(self.criterion, nn.MSELoss) and imgs.is_cuda:
+            rec, mse = _CompositeMSE.apply(fg_rgba, env_rgba, imgs, n_total)
             return self.compute_losses(imgs, rec, rgb_loss=mse)
-        rec = self._composite(layers)
+        rec = self._composite(env_rgba, fg_rgba)
         return self.compute_losses(imgs, rec, rgb_loss=self.criterion(imgs, rec) * (len(imgs) / float(n_total)))
 
     def _install_cameras(self, inp):
+        """dbw.py:204-208: the first batch's intrinsics become the cameras of all four renderers"""
         if 'K' in inp and self.renderer.cameras.K is None:
-            for r in (self.renderer, self.renderer_fine, self.renderer_env, self.renderer_light):
+            for r in self._renderers():
                 r.update_cameras(device=inp['imgs'].device, K=inp['K'][0:1])
                 r.cameras.intrinsics()          # the one host read of K happens here, never inside a step
 
+    def _phase(self, filter_transparent=False):
+        fine = not self.is_live('coarse_learning')
+        return fine, (filter_transparent or fine), (self.renderer_fine if fine else self.renderer)
+
     def _render_layers(self, inp, filter_transparent=False):
-        """(env RGBA, blocks RGBA or None) in decoupled mode, (scene RGBA, None) in joint mode."""
-        B, R_tgt, T_tgt = len(inp['imgs']), inp['R'], inp['T']
+        """(environment RGBA, blocks RGBA) in decoupled mode (every shipped config), (whole-scene RGBA, None) otherwise"""
+        B, R, T = len(inp['imgs']), inp['R'], inp['T']
         self._install_cameras(inp)
-        fine_learning = not self.is_live('coarse_learning')
-        filter_tsp = filter_transparent or fine_learning
-        renderer = self.renderer_fine if fine_learning else self.renderer
-        if self.decouple_rendering and self.static_topology and self.fused_scene and R_tgt.is_cuda:
-            return self._render_layers_fused(B, R_tgt, T_tgt, filter_tsp, renderer)
-        if self.decouple_rendering and self.static_topology:
-            env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
-            out_env = self.renderer_env(env.extend(B), R=R_tgt, T=T_tgt)
-            verts, faces, fvu, fmap, maps, table = self._blocks_scene_static(filter_tsp)
-            alpha = None if filter_tsp else self._alpha.repeat_interleave(self.BNF)
-            r = renderer
-            out_fg = render_scene(verts, faces, fvu, fmap, maps, table, R_tgt, T_tgt, r.cameras.intrinsics(), r.img_size,
-                                  r.sigma, r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color,
-                                  alpha, r.perspective_correct, blur_radius=r.blur_radius)
-            return out_env, out_fg
-        if self.decouple_rendering:
-            env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
-            out_env = self.renderer_env(env.extend(B), R=R_tgt, T=T_tgt)
-            blocks = self.build_blocks(filter_transparent=filter_tsp, as_scene=True)
-            if len(blocks) > 0:
-                alpha = None if filter_tsp else self._alpha.repeat_interleave(self.BNF)
-                out_fg = renderer(blocks.extend(B), R=R_tgt, T=T_tgt, faces_alpha=alpha)
-            else:
-                out_fg = torch.zeros_like(out_env)
-            return out_env, out_fg
-        scene = self.build_scene(filter_transparent=filter_tsp)
-        if not filter_tsp:
-            alpha_env = torch.ones(self.env_n_faces, device=R_tgt.device)
-            alpha = torch.cat([alpha_env, self._alpha.repeat_interleave(self.BNF)], dim=0)
-        else:
+        fine, hard_filter, renderer = self._phase(filter_transparent)
+        if not self.decouple_rendering:
+            scene = self.build_scene(filter_transparent=hard_filter)
             alpha = None
-        return renderer(scene.extend(B), R=R_tgt, T=T_tgt, faces_alpha=alpha), None
+            if not hard_filter:
+                alpha = torch.cat([torch.ones(self.env_n_faces, device=R.device), self._alpha.repeat_interleave(self.BNF)])
+            return renderer(scene.extend(B), R=R, T=T, faces_alpha=alpha), None
+        if self.static_topology and self.fused_scene and R.is_cuda:
+            return self._render_decoupled_fused(R, T, hard_filter, renderer)
+        env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
+        env_rgba = self.renderer_env(env.extend(B), R=R, T=T)
+        if self.static_topology:
+            verts, faces, fvu, fmap, maps, table = self._blocks_static(hard_filter)
+            alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
+            return env_rgba, self._raster(renderer, verts, faces, fvu, fmap, maps, table, R, T, alpha, texels4=False)
+        blocks = self.build_blocks(filter_transparent=hard_filter, as_scene=True)
+        if len(blocks) == 0:
+            return env_rgba, torch.zeros_like(env_rgba)
+        alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
+        return env_rgba, renderer(blocks.extend(B), R=R, T=T, faces_alpha=alpha)
 
     @staticmethod
-    def _composite(layers):
-        first, fg = layers
-        if fg is None:
-            return first[:, :3]
-        rec_fg, mask = fg.split([3, 1], dim=1)
-        return rec_fg * mask + (1 - mask) * first[:, :3]
+    def _raster(r, verts, faces, fvu, fmap, maps, table, R, T, alpha, texels4):
+        return render_scene(verts, faces, fvu, fmap, maps, table, R, T, r.cameras.intrinsics(), r.img_size, r.sigma,
+                            r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color, alpha,
+                            r.perspective_correct, blur_radius=r.blur_radius, maps_are_texels4=texels4)
 
-    def predict(self, inp, labels=None, w_edges=False, filter_transparent=False):
-        rec = self._composite(self._render_layers(inp, filter_transparent))
-        if w_edges:                                   # dbw.py:234-238: coloured face edges drawn over the reconstruction
-            B, R_tgt, T_tgt = len(inp['imgs']), inp['R'], inp['T']
-            fine_learning = not self.is_live('coarse_learning')
-            filter_tsp = filter_transparent or fine_learning
-            renderer = self.renderer_fine if fine_learning else self.renderer
-            env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
-            blocks = self.build_blocks(filter_transparent=filter_tsp, as_scene=True)
-            scene = join_meshes_as_scene([env, blocks]) if len(blocks) > 0 else env
-            colors = self.get_scene_face_colors(filter_transparent=filter_tsp).repeat(B, 1)
-            rec = renderer.draw_edges(rec, scene.extend(B), R_tgt, T_tgt, colors=colors)
-        return rec
+    @staticmethod
+    def _composite(env_rgba, fg_rgba):
+        if fg_rgba is None:
+            return env_rgba[:, :3]
+        cover = fg_rgba[:, 3:]
+        return fg_rgba[:, :3] * cover + (1 - cover) * env_rgba[:, :3]          # dbw.py:223
 
-    def predict_synthetic(self, inp, labels=None):
-        """flat-shaded render of the opaque blocks with one synthetic colour per block (dbw.py:241-248)."""
-        B, R_tgt, T_tgt = len(inp['imgs']), inp['R'], inp['T']
-        self._install_cameras(inp)
-        blocks = self.build_blocks(filter_transparent=True, synthetic_colors=True, as_scene=True)
-        if len(blocks) > 0:
-            return self.renderer_light(blocks.extend(B), R=R_tgt, T=T_tgt, viz_purpose=True)[:, :3]
-        return torch.ones_like(inp['imgs'])
-
-    @torch.no_grad()
-    def get_scene_face_colors(self, filter_transparent=False, w_env=True):
-        """one colour per face of the scene mesh: environment faces get the first colour of the map, block k the colour at
-        (k+1)/N (dbw.py:420-431)."""
-        val_blocks = torch.linspace(0, 1, self.n_blocks + 1)[1:]
-        if filter_transparent:
-            val_blocks = val_blocks[self.get_opacities().cpu() > 0.5]
-        elif self.kill_blocks:
-            val_blocks = val_blocks[self.get_opacities().cpu() > 0.01]
-        NFE = self.env_n_faces if w_env else 0
-        values = torch.cat([torch.zeros(NFE), val_blocks.repeat_interleave(self.BNF)])
-        return torch.from_numpy(G.fancy_cmap()(values.numpy())).float().to(self.bkg.device)
-
-    # ------------------------------------------------------------------ scene construction (dbw.py:250-352)
-    def _decimate(self, maps):
-        sub = F.avg_pool2d(maps.permute(0, 3, 1, 2), kernel_size=self.decim_factor, stride=self.decim_factor)
-        return F.interpolate(sub, scale_factor=self.decim_factor).permute(0, 2, 3, 1)
-
-    def _to_world(self, verts):
-        return (verts * self.S_world) @ self.R_world + self.T_world[:, None]
-
-    def build_scene(self, filter_transparent=False, w_bkg=True, reduce_ground=False):
-        meshes = []
-        if w_bkg:
-            meshes.append(self.build_bkg())
-        meshes.append(self.build_ground(reduced=reduce_ground))
-        blocks = self.build_blocks(filter_transparent)
-        if len(blocks) > 0:
-            meshes.append(blocks)
-        scene = join_meshes_as_scene(meshes) if (len(meshes) - 1 + len(blocks)) > 1 else meshes[0]
-        verts, faces = scene.get_mesh_verts_faces(0)
-        return Meshes(self._to_world(verts[None]), faces[None], scene.textures)
-
-    def build_bkg(self, reduced=False, world_coord=False):
-        verts, faces = [t[None] for t in self.bkg.get_mesh_verts_faces(0)]
-        if reduced:
-            verts = verts * 3 / self.z_far
-        if world_coord:
-            verts = self._to_world(verts)
-        maps = torch.sigmoid(self.texture_bkg)
-        self._bkg_maps = maps
-        if self.training and self.is_live('decimate_txt'):
-            maps = self._decimate(maps)
-        return Meshes(verts, faces, textures=TexturesUV(maps, faces, self.bkg_verts_uvs[None], align_corners=True))
-
-    def build_ground(self, reduced=False, world_coord=False):
-        S_ground = 1. if not reduced else torch.Tensor([3 / self.z_far, 1, 3 / self.z_far]).to(self.bkg.device)
-        verts, faces = [t[None] for t in self.ground.get_mesh_verts_faces(0)]
-        verts = (verts * S_ground) @ G.rotation_6d_to_matrix(self.R_6d_ground) + self.T_ground[:, None]
-        if world_coord:
-            verts = self._to_world(verts)
-        maps = torch.sigmoid(self.texture_ground)
-        self._ground_maps = maps
-        if self.training and self.is_live('decimate_txt'):
-            maps = self._decimate(maps)
-        return Meshes(verts, faces, textures=TexturesUV(maps, faces, self.ground_verts_uvs[None], align_corners=True))
-
-    def _fused_arrays(self):
+    # ------------------------------------------------------------------ fused / static scene construction
+    def _static_arrays(self):
+        """device-side constants of the scene: face / UV / map-index arrays of both passes, the background sphere's
+        world vertices, and the constants of the geometry kernel"""
         dev = self.alpha_logit.device
-        if self._fused_static is None or self._fused_static['dev'] != dev:
+        if self._static is None or self._static['dev'] != dev:
             N, Vb = self.n_blocks, self.sq_eta.shape[1]
             gv, gf = self.ground.get_mesh_verts_faces(0)
             bv, bf = self.bkg.get_mesh_verts_faces(0)
-            geom = {'n_blocks': N, 'verts_per_block': Vb, 'n_ground_verts': gv.shape[0], 'sq_eta': self.sq_eta.contiguous(),
-                    'sq_omega': self.sq_omega.contiguous(), 'ground_verts': gv.contiguous().float(),
-                    'ratio': float(self.ratio_block_scene), 'scale_min': float(self.scale_min), 'S_world': float(self.S_world),
-                    'R_world': [float(x) for x in self.R_world.reshape(-1).cpu()], 'T_world': [float(x) for x in self.T_world.reshape(-1).cpu()]}
-            bkg_world = self._to_world(bv[None])[0].contiguous()             # static: no learnable pose
-            faces_b = (self.blocks.faces_padded() + (torch.arange(N, device=dev) * Vb)[:, None, None]).reshape(-1, 3)
-            fvu_b = self.block_verts_uvs[self.block_faces_uvs][None].expand(N, -1, -1, -1).reshape(-1, 3, 2).contiguous()
-            fmap_b = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF)
-            faces_e = torch.cat([bf, gf + bv.shape[0]]).to(torch.int32).contiguous()
-            fvu_e = torch.cat([self.bkg_verts_uvs[bf], self.ground_verts_uvs[gf]]).contiguous()
-            fmap_e = torch.cat([torch.zeros(len(bf)), torch.ones(len(gf))]).to(dev).to(torch.int32)
-            self._fused_static = {'dev': dev, 'geom': geom, 'bkg_world': bkg_world, 'faces_b': faces_b.to(torch.int32).contiguous(),
-                                  'fvu_b': fvu_b, 'fmap_b': fmap_b, 'faces_e': faces_e, 'fvu_e': fvu_e, 'fmap_e': fmap_e}
-        return self._fused_static
+            geom = dict(n_blocks=N, verts_per_block=Vb, n_ground_verts=gv.shape[0], sq_eta=self.sq_eta.contiguous(),
+                        sq_omega=self.sq_omega.contiguous(), ground_verts=gv.contiguous().float(),
+                        ratio=float(self.ratio_block_scene), scale_min=float(self.scale_min), S_world=float(self.S_world),
+                        R_world=[float(x) for x in self.R_world.flatten().cpu()], T_world=[float(x) for x in self.T_world.flatten().cpu()])
+            offsets = (torch.arange(N, device=dev) * Vb)[:, None, None]
+            self._static = dict(
+                dev=dev, geom=geom, bkg_world=self._to_world(bv[None])[0].contiguous(),
+                faces_b=(self.blocks.faces_padded() + offsets).reshape(-1, 3).to(torch.int32).contiguous(),
+                fvu_b=self.block_verts_uvs[self.block_faces_uvs].expand(N, -1, -1, -1).reshape(-1, 3, 2).contiguous(),
+                fmap_b=torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF),
+                faces_e=torch.cat([bf, gf + bv.shape[0]]).to(torch.int32).contiguous(),
+                fvu_e=torch.cat([self.bkg_verts_uvs[bf], self.ground_verts_uvs[gf]]).contiguous(),
+                fmap_e=torch.cat([torch.zeros(len(bf)), torch.ones(len(gf))]).to(dev).to(torch.int32))
+        return self._static
 
-    def _render_layers_fused(self, B, R_tgt, T_tgt, filter_tsp, renderer):
-        """decoupled rendering with the fused scene kernels: leaf parameters -> 2 scene kernels -> 2 render passes."""
-        st = self._fused_arrays()
-        N, Vb = self.n_blocks, st['geom']['verts_per_block']
-        coarse_learning = self.training and self.is_live('coarse_learning')
-        decim = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
-        verts = scene_geometry(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground, st['geom'])
-        # ---- environment pass (bkg sphere is static, the ground follows R_6d_ground / T_ground)
-        env_verts = torch.cat([st['bkg_world'], verts[N * Vb:]])
-        tb, tg = texture_atlas(self.texture_bkg, 0, 0, decim), texture_atlas(self.texture_ground, 0, 0, decim)
-        env_atlas = torch.cat([tb.reshape(-1, 4), tg.reshape(-1, 4)])
-        Hb = self.texture_bkg.shape[1]
-        table_e = [(0, Hb, Hb), (Hb * Hb * 3, Hb, Hb)]
-        re = self.renderer_env
-        # the two passes are independent until compositing: the environment pass runs on a side stream so that its
-        # kernels (and, through autograd, their backward) overlap the blocks pass -- each raster kernel alone leaves
-        # 35-50 % of the issue slots idle (profiles/), two different ones interleave on the SMs
-        cur = torch.cuda.current_stream()
-        if self._env_stream is None:
-            self._env_stream = torch.cuda.Stream()
-        side = self._env_stream if self.overlap_passes else cur
-        if side is not cur:
-            side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            out_env = render_scene(env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, table_e, R_tgt, T_tgt,
-                                   re.cameras.intrinsics(), re.img_size, re.sigma, re.faces_per_pixel, re.z_clip, re.detach_bary,
-                                   re.clip_inside, re.background_color, None, re.perspective_correct, blur_radius=re.blur_radius,
-                                   maps_are_texels4=True)
-        # ---- blocks pass
-        alpha_logit = self.alpha_logit
-        if self.opacity_noise and coarse_learning:
-            alpha_logit = alpha_logit + self.opacity_noise * self._draw_opacity_noise()
-        self._alpha = torch.sigmoid(alpha_logit)
+    def _fused_arrays(self):          # name used by tests / scene_ops callers
+        return self._static_arrays()
+
+    def _opacities(self, hard_filter, coarse_training):
+        """per-block opacities (+ exploration noise while coarse) and the face_map that disables filtered blocks"""
+        st = self._static_arrays()
+        logit = self.alpha_logit
+        if self.opacity_noise and coarse_training:
+            logit = logit + self.opacity_noise * self._draw_opacity_noise()
+        self._alpha = torch.sigmoid(logit)
         self._alpha_full = self._alpha.clone()
         fmap = st['fmap_b']
-        if filter_tsp or self.kill_blocks:
-            mask = torch.sigmoid(self.alpha_logit) > (0.5 if filter_tsp else 0.01)
-            self._alpha_full = self._alpha_full * mask
-            fmap = torch.where(mask.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
-        p_left, p_right = self.txt_padding
-        atlas = texture_atlas(self.textures, p_left, p_right, self.decim_factor if (coarse_learning and self.is_live('decimate_txt')) else 1)
-        Ht, Wt = atlas.shape[1], atlas.shape[2]
-        table_b = [(i * Ht * Wt * 3, Ht, Wt) for i in range(N)]
-        alpha = None if filter_tsp else self._alpha.repeat_interleave(self.BNF)
-        r = renderer
-        out_fg = render_scene(verts[:N * Vb], st['faces_b'], st['fvu_b'], fmap, atlas.reshape(-1, 4), table_b, R_tgt, T_tgt,
-                              r.cameras.intrinsics(), r.img_size, r.sigma, r.faces_per_pixel, r.z_clip, r.detach_bary,
-                              r.clip_inside, r.background_color, alpha, r.perspective_correct, blur_radius=r.blur_radius,
-                              maps_are_texels4=True)
-        if side is not cur:
-            cur.wait_stream(side)
-            out_env.record_stream(cur)
-        # the regularisers of compute_losses() read these (plain torch on parameters, only built when they are used)
-        self._blocks_SRT = None
-        self._needs_reg_state = True
-        return out_env, out_fg
-
-    def _ensure_reg_state(self):
-        """state the parameter-only regularisers read (dbw.py:313,349-351); the fused path builds it lazily."""
-        if getattr(self, '_needs_reg_state', False):
-            self._blocks_maps = torch.sigmoid(self.textures)
-            self._bkg_maps, self._ground_maps = torch.sigmoid(self.texture_bkg), torch.sigmoid(self.texture_ground)
-            self._blocks_SRT = (self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T)
-            eps1, eps2 = (self.sq_eps.sigmoid() * 1.8 + 0.1).split([1, 1], dim=-1)
-            self._blocks_eps = eps1, eps2
-            self._needs_reg_state = False
+        if hard_filter or self.kill_blocks:
+            keep = torch.sigmoid(self.alpha_logit) > (0.5 if hard_filter else 0.01)
+            self._alpha_full = self._alpha_full * keep
+            fmap = torch.where(keep.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
+        return fmap
 
     def _draw_opacity_noise(self):
         if self.opacity_noise_buffer is not None:
@@ -478,174 +322,252 @@ class DifferentiableBlocksWorld(nn.Module):
             return torch.randn(self.alpha_logit.shape, generator=self.noise_generator, device=self.alpha_logit.device)
         return torch.randn_like(self.alpha_logit)
 
-    def _blocks_scene_static(self, filter_transparent):
-        """build_blocks(as_scene=True) with fixed shapes: same vertices / maps / opacities, filtered blocks disabled via
-        face_map = -1 (see include/dbw_render.h) instead of removed.  No host synchronisation."""
-        N, dev = self.n_blocks, self.alpha_logit.device
-        coarse_learning = self.training and self.is_live('coarse_learning')
-        S, R, T = self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
-        alpha_logit = self.alpha_logit
-        if self.opacity_noise and coarse_learning:
-            alpha_logit = alpha_logit + self.opacity_noise * self._draw_opacity_noise()
-        self._alpha = torch.sigmoid(alpha_logit)
-        self._alpha_full = self._alpha.clone()
-        maps = torch.sigmoid(self.textures)
-        verts = (self.get_blocks_verts() * S[:, None]) @ R + T[:, None]
-        self._blocks_maps, self._blocks_SRT = maps, (S, R, T)
-        if self._static_arrays is None or self._static_arrays[0].device != dev:
-            faces = (self.blocks.faces_padded() + (torch.arange(N, device=dev) * verts.shape[1])[:, None, None]).reshape(-1, 3)
-            fvu = self.block_verts_uvs[self.block_faces_uvs][None].expand(N, -1, -1, -1).reshape(-1, 3, 2).contiguous()
-            fmap = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF)
-            self._static_arrays = (faces.to(torch.int32).contiguous(), fvu, fmap)
-        faces, fvu, fmap = self._static_arrays
-        if filter_transparent or self.kill_blocks:
-            mask = torch.sigmoid(self.alpha_logit) > (0.5 if filter_transparent else 0.01)
-            self._alpha_full = self._alpha_full * mask
-            fmap = torch.where(mask.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
-        if coarse_learning and self.is_live('decimate_txt'):
-            maps = self._decimate(maps)
-        p_left, p_right = self.txt_padding
-        maps = F.pad(maps.permute(0, 3, 1, 2), pad=(p_left, p_right, 0, 0), mode='circular').permute(0, 2, 3, 1).contiguous()
-        verts = self._to_world(verts).reshape(-1, 3)
-        Ht, Wt = maps.shape[1], maps.shape[2]
-        table = [(i * Ht * Wt * 3, Ht, Wt) for i in range(N)]
-        return verts, faces, fvu, fmap, maps.reshape(-1), table
+    def _render_decoupled_fused(self, R, T, hard_filter, renderer):
+        """leaf parameters -> scene kernels -> environment pass + blocks pass"""
+        st = self._static_arrays()
+        n_block_verts = self.n_blocks * st['geom']['verts_per_block']
+        coarse_training = self.training and self.is_live('coarse_learning')
+        decim_env = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
+        decim_blocks = self.decim_factor if (coarse_training and self.is_live('decimate_txt')) else 1
+        verts = scene_geometry(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground, st['geom'])
+
+        # environment: constant background sphere + posed ground, two square maps in one atlas
+        env_verts = torch.cat([st['bkg_world'], verts[n_block_verts:]])
+        env_atlas = torch.cat([texture_atlas(self.texture_bkg, 0, 0, decim_env).reshape(-1, 4),
+                               texture_atlas(self.texture_ground, 0, 0, decim_env).reshape(-1, 4)])
+        side = self.texture_bkg.shape[1]
+        env_table = [(0, side, side), (side * side * 3, side, side)]
+        main = torch.cuda.current_stream()
+        stream = main
+        if self.overlap_passes:
+            self._env_stream = self._env_stream or torch.cuda.Stream()
+            stream = self._env_stream
+            stream.wait_stream(main)
+        with torch.cuda.stream(stream):
+            env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
+                                    R, T, None, texels4=True)
+
+        # blocks
+        fmap = self._opacities(hard_filter, coarse_training)
+        atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
+        rows, cols = atlas.shape[1], atlas.shape[2]
+        table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
+        alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
+        fg_rgba = self._raster(renderer, verts[:n_block_verts], st['faces_b'], st['fvu_b'], fmap, atlas.reshape(-1, 4), table,
+                               R, T, alpha, texels4=True)
+        if stream is not main:
+            main.wait_stream(stream)
+            env_rgba.record_stream(main)
+        self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
+        return env_rgba, fg_rgba
+
+    def _blocks_static(self, hard_filter):
+        """eager (PyTorch ops) construction of the blocks scene with fixed shapes -- the reference's arithmetic
+        (dbw.py:299-344) minus the slicing: filtered blocks are disabled through face_map"""
+        st = self._static_arrays()
+        coarse_training = self.training and self.is_live('coarse_learning')
+        fmap = self._opacities(hard_filter, coarse_training)
+        S, R, T = self._pose()
+        verts = self._to_world(torch.bmm(self.get_blocks_verts() * S[:, None], R) + T[:, None]).reshape(-1, 3)
+        maps = self._maps(self.textures, decimate=coarse_training and self.is_live('decimate_txt'), pad=self.txt_padding)
+        self._blocks_maps, self._blocks_SRT = torch.sigmoid(self.textures), (S, R, T)
+        rows, cols = maps.shape[1], maps.shape[2]
+        table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
+        return verts, st['faces_b'], st['fvu_b'], fmap, maps.reshape(-1), table
+
+    # ------------------------------------------------------------------ reference-shaped builders (Meshes objects)
+    def _pose(self):
+        return self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
+
+    def _to_world(self, verts):
+        return (verts * self.S_world) @ self.R_world + self.T_world[:, None]
+
+    def _maps(self, logits, decimate=False, pad=(0, 0), synthetic=None):
+        """sigmoid -> optional box decimation (avg-pool + nearest upsample, dbw.py:331-334) -> circular u padding"""
+        maps = torch.sigmoid(logits) if synthetic is None else synthetic
+        if decimate:
+            f = self.decim_factor
+            maps = F.interpolate(F.avg_pool2d(maps.permute(0, 3, 1, 2), f, f), scale_factor=f).permute(0, 2, 3, 1)
+        if pad[0] or pad[1]:
+            maps = F.pad(maps.permute(0, 3, 1, 2), pad=(pad[0], pad[1], 0, 0), mode='circular').permute(0, 2, 3, 1)
+        return maps.contiguous()
+
+    def get_blocks_verts(self):
+        eps = self.sq_eps.sigmoid() * 1.8 + 0.1
+        self._blocks_eps = eps[:, :1], eps[:, 1:]
+        return G.superquadric_points(self.sq_eta, self.sq_omega, *self._blocks_eps) * self.ratio_block_scene
+
+    def _env_part(self, mesh, verts_uvs, logits, verts, world_coord, synthetic_colors):
+        faces = mesh.get_mesh_verts_faces(0)[1][None]
+        if world_coord:
+            verts = self._to_world(verts)
+        synthetic = torch.ones_like(logits) if synthetic_colors else None
+        maps = self._maps(logits, decimate=self.training and self.is_live('decimate_txt'), synthetic=synthetic)
+        return Meshes(verts, faces, textures=TexturesUV(maps, faces, verts_uvs[None], align_corners=True))
+
+    def build_bkg(self, reduced=False, world_coord=False, synthetic_colors=False):
+        verts = self.bkg.get_mesh_verts_faces(0)[0][None]
+        if reduced:
+            verts = verts * 3 / self.z_far
+        self._bkg_maps = torch.sigmoid(self.texture_bkg)
+        return self._env_part(self.bkg, self.bkg_verts_uvs, self.texture_bkg, verts, world_coord, synthetic_colors)
+
+    def build_ground(self, reduced=False, world_coord=False, synthetic_colors=False):
+        verts = self.ground.get_mesh_verts_faces(0)[0][None]
+        if reduced:
+            verts = verts * torch.tensor([3 / self.z_far, 1, 3 / self.z_far], device=verts.device)
+        verts = verts @ G.rotation_6d_to_matrix(self.R_6d_ground) + self.T_ground[:, None]
+        self._ground_maps = torch.sigmoid(self.texture_ground)
+        return self._env_part(self.ground, self.ground_verts_uvs, self.texture_ground, verts, world_coord, synthetic_colors)
 
     def build_blocks(self, filter_transparent=False, world_coord=False, as_scene=False, synthetic_colors=False):
-        coarse_learning = self.training and self.is_live('coarse_learning')
-        S, R, T = self.S.exp() + self.scale_min, G.rotation_6d_to_matrix(self.R_6d), self.T
-        if self.opacity_noise and coarse_learning:
-            alpha_logit = self.alpha_logit + self.opacity_noise * self._draw_opacity_noise()
-        else:
-            alpha_logit = self.alpha_logit
-        self._alpha = torch.sigmoid(alpha_logit)
-        self._alpha_full = self._alpha.clone()
-        maps = torch.sigmoid(self.textures)
-        if synthetic_colors:
-            values = torch.linspace(0, 1, self.n_blocks + 1)[1:]
-            colors = torch.from_numpy(G.fancy_cmap()(values.numpy())).float().to(maps.device)
-            maps = colors[:, None, None].expand(-1, self.txt_size, self.txt_size, -1)
-        verts = (self.get_blocks_verts() * S[:, None]) @ R + T[:, None]
+        """Meshes of the (kept) blocks, sliced like the reference (dbw.py:297-346): host-synchronising, used by the
+        visualisation / export call sites; the training step goes through _render_decoupled_fused / _blocks_static"""
+        coarse_training = self.training and self.is_live('coarse_learning')
+        self._opacities(False, coarse_training)
+        S, R, T = self._pose()
+        verts = torch.bmm(self.get_blocks_verts() * S[:, None], R) + T[:, None]
         faces = self.blocks.faces_padded()
-        self._blocks_maps, self._blocks_SRT = maps, (S, R, T)
-
+        synthetic = None
+        if synthetic_colors:
+            shades = G.fancy_cmap()(torch.linspace(0, 1, self.n_blocks + 1)[1:].numpy())
+            synthetic = torch.from_numpy(shades).float().to(verts.device)[:, None, None].expand(-1, self.txt_size, self.txt_size, -1)
+        logits = self.textures
+        self._blocks_maps, self._blocks_SRT = torch.sigmoid(self.textures), (S, R, T)
+        n_kept = self.n_blocks
         if filter_transparent or self.kill_blocks:
-            mask = torch.sigmoid(self.alpha_logit) > (0.5 if filter_transparent else 0.01)
-            self._alpha_full = self._alpha_full * mask
-            NB = int(mask.sum().item())
-            if NB == 0:
+            keep = torch.sigmoid(self.alpha_logit) > (0.5 if filter_transparent else 0.01)
+            self._alpha_full = self._alpha_full * keep
+            n_kept = int(keep.sum())
+            if n_kept == 0:
                 return Meshes([], [])
-            verts, faces, maps, self._alpha = verts[mask], faces[mask], maps[mask], self._alpha[mask]
-        else:
-            NB = self.n_blocks
-
-        if coarse_learning and self.is_live('decimate_txt'):
-            maps = self._decimate(maps)
-        p_left, p_right = self.txt_padding
-        maps = F.pad(maps.permute(0, 3, 1, 2), pad=(p_left, p_right, 0, 0), mode='circular').permute(0, 2, 3, 1)
-        txt = TexturesUV(maps, self.block_faces_uvs[None].expand(NB, -1, -1), self.block_verts_uvs[None].expand(NB, -1, -1),
-                         align_corners=True)
+            verts, faces, logits, self._alpha = verts[keep], faces[keep], logits[keep], self._alpha[keep]
+            synthetic = synthetic[keep] if synthetic is not None else None
+        maps = self._maps(logits, decimate=coarse_training and self.is_live('decimate_txt'), pad=self.txt_padding, synthetic=synthetic)
         if world_coord or as_scene:
             verts = self._to_world(verts)
+        txt = TexturesUV(maps, self.block_faces_uvs.expand(n_kept, -1, -1), self.block_verts_uvs.expand(n_kept, -1, -1), align_corners=True)
         blocks = Meshes(verts, faces, textures=txt)
         return join_meshes_as_scene(blocks) if as_scene else blocks
 
-    def get_blocks_verts(self):
-        eps1, eps2 = (self.sq_eps.sigmoid() * 1.8 + 0.1).split([1, 1], dim=-1)
-        self._blocks_eps = eps1, eps2
-        return G.superquadric_points(self.sq_eta, self.sq_omega, eps1, eps2) * self.ratio_block_scene
+    def build_scene(self, filter_transparent=False, w_bkg=True, reduce_ground=False, synthetic_colors=False):
+        parts = [self.build_bkg(synthetic_colors=synthetic_colors)] if w_bkg else []
+        parts.append(self.build_ground(reduced=reduce_ground, synthetic_colors=synthetic_colors))
+        blocks = self.build_blocks(filter_transparent, synthetic_colors=synthetic_colors)
+        if len(blocks) > 0:
+            parts.append(blocks)
+        scene = join_meshes_as_scene(parts)
+        verts, faces = scene.get_mesh_verts_faces(0)
+        return Meshes(self._to_world(verts[None]), faces[None], scene.textures)
 
-    # ------------------------------------------------------------------ losses (dbw.py:361-408)
-    def compute_losses(self, imgs, rec, rgb_loss=None):
-        losses = {k: torch.zeros((), device=imgs.device) for k in self.loss_weights}
-        coarse_learning = self.is_live('coarse_learning')
-        if any(k in self.loss_weights for k in ('tv', 'overlap')):
-            self._ensure_reg_state()
-        if 'rgb' in losses:
-            losses['rgb'] = self.loss_weights['rgb'] * (rgb_loss if rgb_loss is not None else self.criterion(imgs, rec))
-        if 'perceptual' in losses and self.perceptual_loss is not None:
-            factor = 1 if coarse_learning else 0.1
-            losses['perceptual'] = self.loss_weights['perceptual'] * factor * self.perceptual_loss(imgs, rec)
-        if 'parsimony' in losses:
-            factor = 1 if coarse_learning else 0
-            alpha = self._alpha_full if coarse_learning else (self._alpha_full > 0.5).float()
-            losses['parsimony'] = self.loss_weights['parsimony'] * factor * G.safe_pow(alpha, 0.5).mean()
-        if 'tv' in losses:
-            factor = 1 if coarse_learning else 0.1
-            tv_loss = sum([self.tv_norm(torch.diff(self._bkg_maps, dim=k)).mean() for k in [1, 2]])
-            if len(self._blocks_maps) > 0:
-                dx = self.tv_norm(torch.diff(self._blocks_maps, dim=2, append=self._blocks_maps[:, :, 0:1]))
-                dy = self.tv_norm(torch.diff(self._blocks_maps, dim=1))
-                tv_loss += (dx.sum(0).mean() + dy.sum(0).mean())
-            tv_loss += sum([self.tv_norm(torch.diff(self._ground_maps, dim=k)).mean() for k in [1, 2]]) * factor
-            losses['tv'] = self.loss_weights['tv'] * factor * tv_loss
-        if 'overlap' in losses:
-            factor = 1 if coarse_learning else 0
-            N = self.n_blocks
-            with torch.no_grad():
-                points = torch.rand(N, OVERLAP_N_POINTS, 3, device=rec.device, generator=self.noise_generator) * 2 - 1
-                S, R, T = self._blocks_SRT
-                points = (points * self.ratio_block_scene * S[:, None]) @ R + T[:, None]
-                points = points.view(-1, 3)[None].expand(N, -1, -1)
-            eps1, eps2 = self._blocks_eps
-            points_inv = ((points - T[:, None]) @ R.transpose(1, 2)) / (S[:, None] * self.ratio_block_scene)
-            sdf = G.superquadric_implicit(points_inv, eps1, eps2)
-            occupancy = torch.sigmoid(-sdf / OVERLAP_TEMPERATURE)
-            alpha = self._alpha_full if coarse_learning else (self._alpha_full > 0.5).float()
-            occupancy = occupancy * alpha[:, None]
-            losses['overlap'] = self.loss_weights['overlap'] * factor * (occupancy.sum(0) - OVERLAP_N_BLOCKS).clamp(0).mean()
-        losses['total'] = sum(losses.values())
-        return losses
+    # ------------------------------------------------------------------ prediction / visualisation
+    def predict(self, inp, labels=None, w_edges=False, filter_transparent=False):
+        rec = self._composite(*self._render_layers(inp, filter_transparent))
+        if w_edges:                                   # dbw.py:234-238: coloured face edges drawn over the reconstruction
+            B = len(inp['imgs'])
+            _, hard_filter, renderer = self._phase(filter_transparent)
+            parts = [self.build_bkg(world_coord=True), self.build_ground(world_coord=True)]
+            blocks = self.build_blocks(filter_transparent=hard_filter, as_scene=True)
+            if len(blocks) > 0:
+                parts.append(blocks)
+            colors = self.get_scene_face_colors(filter_transparent=hard_filter).repeat(B, 1)
+            rec = renderer.draw_edges(rec, join_meshes_as_scene(parts).extend(B), inp['R'], inp['T'], colors=colors)
+        return rec
 
-    def get_opacities(self):
-        alpha = torch.sigmoid(self.alpha_logit)
-        if self.kill_blocks:
-            alpha = alpha * (alpha > 0.01)
-        return alpha
+    def predict_synthetic(self, inp, labels=None):
+        """flat-shaded render of the opaque blocks with one synthetic colour per block (dbw.py:241-248)"""
+        self._install_cameras(inp)
+        blocks = self.build_blocks(filter_transparent=True, synthetic_colors=True, as_scene=True)
+        if len(blocks) == 0:
+            return torch.ones_like(inp['imgs'])
+        return self.renderer_light(blocks.extend(len(inp['imgs'])), R=inp['R'], T=inp['T'], viz_purpose=True)[:, :3]
 
     @torch.no_grad()
-    def get_nb_opaque_blocks(self):
-        return (self.get_opacities() > 0.5).sum().item()
+    def get_scene_face_colors(self, filter_transparent=False, w_env=True):
+        """one colour per scene face: environment faces the map's first colour, block k the colour at (k+1)/N (dbw.py:420-431)"""
+        values = torch.linspace(0, 1, self.n_blocks + 1)[1:]
+        if filter_transparent or self.kill_blocks:
+            values = values[self.get_opacities().cpu() > (0.5 if filter_transparent else 0.01)]
+        values = torch.cat([torch.zeros(self.env_n_faces if w_env else 0), values.repeat_interleave(self.BNF)])
+        return torch.from_numpy(G.fancy_cmap()(values.numpy())).float().to(self.bkg.device)
 
     @torch.no_grad()
     def get_arranged_block_txt(self):
+        """the block textures tiled 5 per row, (1,3,rows*TS,5*TS) (dbw.py:433-438)"""
         maps = torch.sigmoid(self.textures).permute(0, 3, 1, 2)
-        ncol, nrow = 5, len(maps) // 5
-        rows = [torch.cat([maps[k] for k in range(ncol * i, ncol * (i + 1))], dim=2) for i in range(nrow)]
+        rows = [torch.cat(list(maps[5 * i:5 * i + 5]), dim=2) for i in range(len(maps) // 5)]
         return torch.cat(rows, dim=1)[None]
 
+    def get_opacities(self):
+        alpha = torch.sigmoid(self.alpha_logit)
+        return alpha * (alpha > 0.01) if self.kill_blocks else alpha
+
+    @torch.no_grad()
+    def get_nb_opaque_blocks(self):
+        return int((self.get_opacities() > 0.5).sum())
+
+    # ------------------------------------------------------------------ objective (dbw.py:361-408)
+    def _refresh_reg_state(self):
+        if self._reg_state_stale:
+            self._blocks_maps = torch.sigmoid(self.textures)
+            self._bkg_maps, self._ground_maps = torch.sigmoid(self.texture_bkg), torch.sigmoid(self.texture_ground)
+            self._blocks_SRT = self._pose()
+            eps = self.sq_eps.sigmoid() * 1.8 + 0.1
+            self._blocks_eps = eps[:, :1], eps[:, 1:]
+            self._reg_state_stale = False
+
+    def compute_losses(self, imgs, rec, rgb_loss=None):
+        coarse = self.is_live('coarse_learning')
+        w = self.loss_weights
+        if 'tv' in w or 'overlap' in w:
+            self._refresh_reg_state()
+        terms = {k: torch.zeros((), device=imgs.device) for k in w}
+        if 'rgb' in w:
+            terms['rgb'] = w['rgb'] * (rgb_loss if rgb_loss is not None else self.criterion(imgs, rec))
+        if 'perceptual' in w and self.perceptual_loss is not None:
+            terms['perceptual'] = w['perceptual'] * (1 if coarse else 0.1) * self.perceptual_loss(imgs, rec)
+        if 'parsimony' in w:
+            terms['parsimony'] = w['parsimony'] * L.parsimony(self._alpha_full, coarse)
+        if 'tv' in w:
+            terms['tv'] = w['tv'] * L.total_variation(self._bkg_maps, self._ground_maps, self._blocks_maps, self.tv_norm, coarse)
+        if 'overlap' in w:
+            S, R, T = self._blocks_SRT
+            terms['overlap'] = w['overlap'] * L.overlap(S, R, T, *self._blocks_eps, self._alpha_full, self.ratio_block_scene,
+                                                        coarse, generator=self.noise_generator)
+        terms['total'] = sum(terms.values())
+        return terms
+
+    # ------------------------------------------------------------------ checkpoints / evaluation
     @torch.no_grad()
     def load_state_dict(self, state_dict, **_unused):
-        state = self.state_dict()
-        missing = []
-        for name, param in state_dict.items():
-            name = name.replace('module.', '').replace('spq_', 'sq_')         # dbw.py:444-445 backward compatibility
-            if name in state:
-                state[name].copy_(param.data if isinstance(param, nn.Parameter) else param)
+        """tolerant loading as dbw.py:440-455: DDP prefixes stripped, `spq_` keys of old checkpoints renamed"""
+        own = self.state_dict()
+        unknown = []
+        for key, value in state_dict.items():
+            key = key.replace('module.', '').replace('spq_', 'sq_')
+            if key in own:
+                own[key].copy_(value.data if isinstance(value, nn.Parameter) else value)
             else:
-                missing.append(name)
-        if missing:
-            print(f'load_state_dict: {missing} not found')
+                unknown.append(key)
+        if unknown:
+            print(f'load_state_dict: {unknown} not found')
 
     @torch.no_grad()
     def quantitative_eval(self, loader, device, hard_inference=True):
-        """PSNR of hard renders over a loader (the SSIM / LPIPS columns of dbw.py:464-493 need networks out of scope)."""
+        """PSNR of hard renders over a loader (the SSIM / LPIPS columns of dbw.py:464-493 need networks out of scope)"""
         self.eval()
         opacities = self.get_opacities()
         scene = self.build_scene(filter_transparent=True)
-        tot, n = 0.0, 0
+        total, count = 0.0, 0
         for inp, labels in loader:
             inp = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inp.items()}
             self._install_cameras(inp)
-            N = len(inp['imgs'])
-            if hard_inference:
-                rec = self.renderer(scene.extend(N), inp['R'], inp['T'], viz_purpose=True)[:, :3]
-            else:
-                rec = self.predict(inp, labels, filter_transparent=True)
-            mse = F.mse_loss(inp['imgs'], rec)
-            tot += float(-10.0 * torch.log10(mse)) * N
-            n += N
-        return OrderedDict([('n_blocks', int((opacities > 0.5).sum())), ('PSNR', tot / max(n, 1))]
+            n = len(inp['imgs'])
+            rec = (self.renderer(scene.extend(n), inp['R'], inp['T'], viz_purpose=True)[:, :3] if hard_inference
+                   else self.predict(inp, labels, filter_transparent=True))
+            total += float(-10.0 * torch.log10(F.mse_loss(inp['imgs'], rec))) * n
+            count += n
+        return OrderedDict([('n_blocks', int((opacities > 0.5).sum())), ('PSNR', total / max(count, 1))]
                            + [(f'alpha{k}', a.item()) for k, a in enumerate(opacities)])
 
 
@@ -663,7 +585,7 @@ def _make_perceptual(name):
 
 
 def create_model(cfg, img_size, **kwargs):
-    """model factory with the reference's signature (src/model/__init__.py:12-17)."""
+    """model factory with the reference's signature (src/model/__init__.py:12-17)"""
     kwargs = deepcopy(cfg['model'])
     name = kwargs.pop('name')
     assert name == 'dbw', name
