@@ -616,18 +616,38 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
 // shuffles and ONE lane issues the atomics -- a 16x16 tile typically sees 1-3 distinct faces per layer, so this
 // removes the same-address contention that otherwise serialises the L2 atomic units (every pixel of a big face hitting
 // the same 9 floats).  Must be called by all 32 lanes (key < 0: nothing to add).
-// all N butterflies advance level by level so that the N shuffles of a level are independent (latency overlapped)
-template <int N>
-__device__ __forceinline__ void warp_sum(float (&x)[N]) {
+// Transposed multi-value warp reduction: NP (power of two) values per lane are summed over the 32 lanes with
+// NP-1 + (5 - log2 NP) shuffles instead of 5*NP -- at every level a lane hands HALF of its partial sums to its partner
+// and keeps the other half, so the totals end up spread over the warp: lane l returns the total of value l >> (5 - log2 NP).
+// The totals are then written by NP different lanes in ONE (predicated) atomic instruction instead of NP sequential ones.
+template <int NP>
+__device__ __forceinline__ float warp_sum_spread(float (&x)[NP], int lane) {
+  static_assert(NP == 1 || NP == 2 || NP == 4 || NP == 8 || NP == 16 || NP == 32, "NP must be a power of two <= 32");
+  constexpr int L = NP == 1 ? 0 : NP == 2 ? 1 : NP == 4 ? 2 : NP == 8 ? 3 : NP == 16 ? 4 : 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int l = 0; l < 5; ++l) {
+    const int o = 16 >> l;
+    if (l < L) {
+      const int c = NP >> (l + 1);
+      const bool upper = (lane & o) != 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) x[i] += __shfl_xor_sync(0xffffffffu, x[i], o);
+      for (int j = 0; j < c; ++j) {
+        const float send = upper ? x[j] : x[j + c];
+        const float keep = upper ? x[j + c] : x[j];
+        x[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    } else {
+      x[0] += __shfl_xor_sync(0xffffffffu, x[0], o);
+    }
   }
+  return x[0];
 }
+template <int N> struct Pow2Ceil { static constexpr int v = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
+template <int NP> struct SpreadShift { static constexpr int v = NP == 1 ? 5 : NP == 2 ? 4 : NP == 4 ? 3 : NP == 8 ? 2 : NP == 16 ? 1 : 0; };
 
 template <int N>
 __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride, int key, const float (&v)[N], int lane) {
+  constexpr int NP = Pow2Ceil<N>::v, SH = SpreadShift<NP>::v;
   unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
   while (todo) {
     const int leader = __ffs(todo) - 1;
@@ -640,41 +660,46 @@ __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride
         for (int i = 0; i < N; ++i) if (v[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, v[i]);
       }
     } else {
-      float x[N];
+      float x[NP];
 #pragma unroll
-      for (int i = 0; i < N; ++i) x[i] = mine ? v[i] : 0.f;
-      warp_sum<N>(x);
-      if (lane == leader) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) if (x[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, x[i]);
-      }
+      for (int i = 0; i < NP; ++i) x[i] = (i < N && mine) ? v[i] : 0.f;
+      const float r = warp_sum_spread<NP>(x, lane);
+      const int idx = lane >> SH;
+      if ((lane & ((1 << SH) - 1)) == 0 && idx < N && r != 0.f) atomicAdd(dst + (size_t)lk * stride + idx, r);
     }
     todo &= ~grp;
   }
 }
 
-// same for the distance path, which only touches (x, y) of the three vertices: offsets 0,1, 3,4, 6,7 of the slot's 9 floats
-__device__ __forceinline__ void warp_agg_add_xy(float* __restrict__ dst, int key, const float (&v)[6], int lane) {
+// Pass-2 aggregation of one layer, keyed by triangle slot: values 0..5 are the distance-path gradient of (x, y) of the three
+// vertices (offsets 0,1, 3,4, 6,7 of the slot's 9 floats), value 6 the gradient of the face's opacity (the face of slot s
+// is s or s - F); g_alpha may be null.  One 8-wide spread reduction serves both.
+__device__ __forceinline__ void warp_agg_add_xya(float* __restrict__ g_tri, float* __restrict__ g_alpha, int F, int key,
+                                                 const float (&v)[7], int lane) {
   unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
   while (todo) {
     const int leader = __ffs(todo) - 1;
     const int lk = __shfl_sync(0xffffffffu, key, leader);
     const bool mine = (key == lk);
     const unsigned grp = __ballot_sync(0xffffffffu, mine);
-    float* d = dst + (size_t)lk * 9;
+    float* d = g_tri + (size_t)lk * 9;
+    float* da = g_alpha ? g_alpha + (lk >= F ? lk - F : lk) : nullptr;
     if (__popc(grp) <= 2) {
       if (mine) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) if (v[i] != 0.f) atomicAdd(d + i + (i >> 1), v[i]);
+        if (da && v[6] != 0.f) atomicAdd(da, v[6]);
       }
     } else {
-      float x[6];
+      float x[8];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) x[i] = mine ? v[i] : 0.f;
-      warp_sum<6>(x);
-      if (lane == leader) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) if (x[i] != 0.f) atomicAdd(d + i + (i >> 1), x[i]);
+      for (int i = 0; i < 7; ++i) x[i] = mine ? v[i] : 0.f;
+      x[7] = 0.f;
+      const float r = warp_sum_spread<8>(x, lane);
+      const int idx = lane >> 2;
+      if ((lane & 3) == 0 && r != 0.f) {
+        if (idx < 6) atomicAdd(d + idx + (idx >> 1), r);
+        else if (idx == 6 && da) atomicAdd(da, r);
       }
     }
     todo &= ~grp;
@@ -683,7 +708,8 @@ __device__ __forceinline__ void warp_agg_add_xy(float* __restrict__ dst, int key
 
 // Texture-gradient scatter of one fragment: 4 bilinear taps x RGB.  Under magnification (the environment maps seen
 // through a narrow field of view: hundreds of pixels per texel) whole warps hit the same 2x2 texel footprint, so
-// lanes that share the footprint with >= 8 others are reduced with shuffles first; the rest issue plain atomics.
+// lanes that share the footprint with >= 8 others are reduced (16-wide spread reduction: total i lands in lane 2i and
+// is added to channel i % 3 of tap i / 3); the rest issue plain vector reds.
 // Coherence is probed from the first pending lane only (no match.any): an incoherent warp pays two ballots.
 __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int key, int i01, int i10, int i11,
                                                  const float (&v)[12], int lane) {
@@ -695,16 +721,16 @@ __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int ke
     const bool mine = !done && key == lk;
     const unsigned grp = __ballot_sync(0xffffffffu, mine);
     if (__popc(grp) < 8) break;
-    float x[12];
+    float x[16];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) x[i] = mine ? v[i] : 0.f;
-    warp_sum<12>(x);
-    if (lane == leader) {
-      red_add_v4(gm + key, x[0], x[1], x[2]);
-      if (i01 >= 0) red_add_v4(gm + i01, x[3], x[4], x[5]);
-      if (i10 >= 0) red_add_v4(gm + i10, x[6], x[7], x[8]);
-      if (i11 >= 0) red_add_v4(gm + i11, x[9], x[10], x[11]);
-    }
+    for (int i = 0; i < 16; ++i) x[i] = (i < 12 && mine) ? v[i] : 0.f;
+    const float r = warp_sum_spread<16>(x, lane);
+    // the footprint (i00 = key, i01, i10, i11) is the same for every lane of the group: fetch it from the leader
+    const int l01 = __shfl_sync(0xffffffffu, i01, leader), l10 = __shfl_sync(0xffffffffu, i10, leader);
+    const int l11 = __shfl_sync(0xffffffffu, i11, leader);
+    const int idx = lane >> 1, tap = idx / 3, ch = idx - tap * 3;
+    const int texel = tap == 0 ? lk : (tap == 1 ? l01 : (tap == 2 ? l10 : l11));
+    if ((lane & 1) == 0 && idx < 12 && texel >= 0 && r != 0.f) atomicAdd(reinterpret_cast<float*>(gm + texel) + ch, r);
     done = done || mine;
     todo &= ~grp;
   }
@@ -841,9 +867,8 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
   for (int k = n_warp - 1; k >= 0; --k) {
-    int akey = -1, vkey = -1;
-    float ga1[1] = {0.f};
-    float gv6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int key = -1;
+    float gv7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // (x, y) of the three vertices, then the face opacity
     if (k < n) {
       const float a = s_alpha[k * NTHREADS + tid], cdot = s_cdot[k * NTHREADS + tid], e = s_e[k * NTHREADS + tid];
       const float occ_k = s_occ[k * NTHREADS + tid];
@@ -856,7 +881,7 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
         float fa = 1.f;
         if (ALPHA) {
           fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
-          if (P.g_faces_alpha) { akey = t.face; ga1[0] = g_alpha * e; }
+          if (P.g_faces_alpha) { key = slot; gv7[6] = g_alpha * e; }
         }
         if (P.sigma > 0.f && P.g_tri) {
           Bary b;
@@ -869,17 +894,16 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
           if (g_dist != 0.f) {
             f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
             tri_dist_backward(p, t, g_dist, g0, g1, g2);
-            vkey = slot;
-            gv6[0] = g0.x; gv6[1] = g0.y; gv6[2] = g1.x; gv6[3] = g1.y; gv6[4] = g2.x; gv6[5] = g2.y;
+            key = slot;
+            gv7[0] = g0.x; gv7[1] = g0.y; gv7[2] = g1.x; gv7[3] = g1.y; gv7[4] = g2.x; gv7[5] = g2.y;
           }
         }
       }
     }
-    if (ALPHA && P.g_faces_alpha) warp_agg_add<1>(P.g_faces_alpha + (size_t)view * P.alpha_stride, 1, akey, ga1, lane);
-    if (P.sigma > 0.f) {
-      // (x, y) of the three vertices live at offsets 0,1, 3,4, 6,7 of the slot's 9 floats
-      if (__ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_xy(P.g_tri + slot_base * 9, vkey, gv6, lane);
-    }
+    // one aggregation per layer for both gradients (the opacity rides in the spare lane group of the 8-wide reduction)
+    if (__ballot_sync(0xffffffffu, key >= 0))
+      warp_agg_add_xya(P.g_tri ? P.g_tri + slot_base * 9 : nullptr,
+                       (ALPHA && P.g_faces_alpha) ? P.g_faces_alpha + (size_t)view * P.alpha_stride : nullptr, P.F, key, gv7, lane);
   }
 }
 

@@ -30,6 +30,11 @@ class GraphedStep:
 
     def _capture(self, warmup=1):
         self.phase = self._phase()
+        # the parameters (and their AccumulateGrad nodes) were created on the default stream, the capture runs on a side
+        # stream: intended, and ordered by the wait_stream calls below -- silence autograd's stream-mismatch warning
+        _warn_off = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+        if _warn_off is not None:
+            _warn_off(False)
         side = torch.cuda.Stream()                 # eager run(s) of the new control flow first (lazy state, allocator warm-up)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
