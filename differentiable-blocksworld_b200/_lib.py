@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdbw_render.so')
+# DBW_RENDER_LIB: explicit path of another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get('DBW_RENDER_LIB') or os.path.join(_HERE, 'libdbw_render.so')
 
 ABI_VERSION = 4
 

@@ -142,8 +142,12 @@ __global__ void fold_gmaps_kernel(const float4* __restrict__ g4, float* __restri
 
 // ------------------------------------------------------------------------------------------------ projection (A1)
 __global__ void project_verts_kernel(const float* __restrict__ vw, const float* __restrict__ R, const float* __restrict__ T,
-                                     float fx, float fy, float px, float py, float eps, int B, int V, float* __restrict__ out) {
+                                     float fx, float fy, float px, float py, float eps, int B, int V, float* __restrict__ out,
+                                     int* __restrict__ view_bbox, int* __restrict__ view_flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // per-view state face_setup accumulates into (it runs after this kernel on the same stream): reset here, no extra launch
+  if (i < B * 4) view_bbox[i] = (i & 1) ? (int)0x807fffff : (int)0x7f800000;     // f2ord(-inf) : f2ord(+inf)
+  if (i < B) view_flags[i] = 0;
   if (i >= B * V) return;
   const int b = i / V, v = i - b * V;
   const float X = vw[v * 3], Y = vw[v * 3 + 1], Z = vw[v * 3 + 2];
@@ -288,9 +292,10 @@ __device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float4* re
   }
 }
 
-__global__ void init_view_bbox_kernel(int* vb, int B) {
+__global__ void init_view_bbox_kernel(int* vb, int* flags, int B) {      // only when the vertices come in as NDC
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * 4) vb[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
+  if (i < B) flags[i] = 0;
 }
 
 __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
@@ -369,10 +374,25 @@ struct RasterParams {
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
 };
 
+// Raster CTAs: the 8x4-pixel patches of a CTA's warps tile a 16 x (NT / 16) pixel tile.  Measured on B200 (cfg 2): the
+// backward kernels and the K > 4 forward are fastest with 128 threads (finer scheduling granularity, less waiting on the
+// slowest warp of a tile), the K <= 4 forward with 256 (the bin scan is amortised over more pixels).
+#ifndef DBW_FWD_NT_SMALLK
+#define DBW_FWD_NT_SMALLK 256
+#endif
+#ifndef DBW_FWD_NT
+#define DBW_FWD_NT 128
+#endif
+#ifndef DBW_BWD_NT
+#define DBW_BWD_NT 128
+#endif
 #define TILE_W 16
-#define TILE_H 16
-#define NTHREADS 256
-#define LIST_CAP 512
+#ifndef LIST_CAP
+#define LIST_CAP 256           // faces a tile lists at once (more: chunked path); 21 KB of shared memory per CTA
+#endif
+#ifndef DBW_AGG_MIN
+#define DBW_AGG_MIN 2         // groups of at most this many lanes use plain atomics instead of a warp reduction
+#endif
 
 __device__ __forceinline__ unsigned long long make_key(float pz, int slot) {
   return ((unsigned long long)__float_as_uint(pz + 0.f) << 32) | (unsigned)slot;
@@ -419,8 +439,26 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
   s.color.z = s.c00.z * s.tap.w00 + s.c01.z * s.tap.w01 + s.c10.z * s.tap.w10 + s.c11.z * s.tap.w11;
 }
 
-template <int K>
-__global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 25 ? 2 : 1)))) raster_forward_kernel(const RasterParams P) {
+// Resident CTAs per SM each raster kernel is compiled for (register cap = 65536 / (threads * CTAs)), tuned on B200 at cfg 2:
+// occupancy wins until the cap forces spills of the per-pixel state (3 registers per layer of the K nearest fragments).
+#ifndef DBW_FWD_SMALLK_MINB
+#define DBW_FWD_SMALLK_MINB 6     // K <= 4, CTAs of DBW_FWD_NT_SMALLK threads (40 registers)
+#endif
+#ifndef DBW_FWD_K10_MINB
+#define DBW_FWD_K10_MINB 6        // 4 < K <= 10, CTAs of DBW_FWD_NT threads (80 registers)
+#endif
+#ifndef DBW_BWD_DETACH_MINB
+#define DBW_BWD_DETACH_MINB 10    // backward without the barycentric path, CTAs of DBW_BWD_NT threads (48 registers)
+#endif
+#ifndef DBW_BWD_BARY_MINB
+#define DBW_BWD_BARY_MINB 6       // backward with the barycentric path: more live state (80 registers)
+#endif
+__host__ __device__ constexpr int max_i(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int fwd_min_ctas(int K, int NT) {
+  return K <= 4 ? DBW_FWD_SMALLK_MINB : (K <= 10 ? DBW_FWD_K10_MINB : max_i(1, (K <= 25 ? 2 : 1) * 256 / NT));
+}
+template <int K, int NT>
+__global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel(const RasterParams P) {
   __shared__ float4 s_bbox[LIST_CAP];
   __shared__ float4 s_rec[LIST_CAP * 4];
   __shared__ int s_slot[LIST_CAP];
@@ -428,6 +466,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
   __shared__ __align__(8) uint64_t s_bar;      // mbarrier of the TMA record gather
   uint32_t bar_phase = 0;
 
+  constexpr int TILE_H = NT / 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
   const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
@@ -464,7 +503,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     // ---- stage the records of the listed faces in shared memory: one 64 B TMA bulk copy per face, all landing on s_bar
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic reads of s_rec precede the async writes
     if (tid == 0) mbar_arrive_expect_tx(&s_bar, (uint32_t)cnt * 64u);
-    for (int j = tid; j < cnt; j += NTHREADS) bulk_copy_g2s(&s_rec[j * 4], &rec[(size_t)s_slot[j] * 4], 64u, &s_bar);
+    for (int j = tid; j < cnt; j += NT) bulk_copy_g2s(&s_rec[j * 4], &rec[(size_t)s_slot[j] * 4], 64u, &s_bar);
     mbar_wait(&s_bar, bar_phase);
     bar_phase ^= 1u;
     // ---- per pixel: test every listed face, keep the K nearest
@@ -512,13 +551,15 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
         if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
       }
     }
+#ifdef DBW_EXP_LISTSYNC
     __syncthreads();
+#endif
   };
 
   // ---- bin: which face slots of the view touch the tile?  Fast path: every batch of 256 slots is tested and compacted
   // with NO block barrier in between (ballot + one shared atomic per warp); hits beyond the list capacity are counted
   // but not stored, and only then the chunked path below (barrier per batch) is taken.
-  for (int base = 0; base < nslots; base += NTHREADS) {
+  for (int base = 0; base < nslots; base += NT) {
     const int s = base + tid;
     bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
     if (s < nslots) {
@@ -541,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     __syncthreads();
     if (tid == 0) s_count = 0;
     __syncthreads();
-    for (int base = 0; base < nslots; base += NTHREADS) {
+    for (int base = 0; base < nslots; base += NT) {
       const int s = base + tid;
       bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
       if (s < nslots) {
@@ -558,9 +599,10 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
       }
       __syncthreads();
       const int cnt = s_count;
-      const bool last = base + NTHREADS >= nslots;
-      if (cnt > LIST_CAP - NTHREADS || last) {
+      const bool last = base + NT >= nslots;
+      if (cnt > LIST_CAP - NT || last) {
         raster_list(cnt);
+        __syncthreads();              // every warp is done with the list before it is reset and refilled
         if (tid == 0) s_count = 0;
         __syncthreads();
       }
@@ -603,7 +645,11 @@ __global__ void __launch_bounds__(NTHREADS, (K <= 4 ? 5 : (K <= 10 ? 3 : (K <= 2
     r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
     occ *= (1.f - a);
   }
+#ifdef DBW_EXP_SENTINEL
+  for (int k = n_frag; k < min(n_frag + 1, P.K); ++k) {
+#else
   for (int k = n_frag; k < P.K; ++k) {
+#endif
     ids[(size_t)k * plane] = -1;
     if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = -1.f;
   }
@@ -654,7 +700,7 @@ __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride
     const int lk = __shfl_sync(0xffffffffu, key, leader);
     const bool mine = (key == lk);
     const unsigned grp = __ballot_sync(0xffffffffu, mine);
-    if (__popc(grp) <= 2) {              // (almost) alone: plain atomics are cheaper than a reduction
+    if (__popc(grp) <= DBW_AGG_MIN) {              // (almost) alone: plain atomics are cheaper than a reduction
       if (mine) {
 #pragma unroll
         for (int i = 0; i < N; ++i) if (v[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, v[i]);
@@ -684,7 +730,7 @@ __device__ __forceinline__ void warp_agg_add_xya(float* __restrict__ g_tri, floa
     const unsigned grp = __ballot_sync(0xffffffffu, mine);
     float* d = g_tri + (size_t)lk * 9;
     float* da = g_alpha ? g_alpha + (lk >= F ? lk - F : lk) : nullptr;
-    if (__popc(grp) <= 2) {
+    if (__popc(grp) <= DBW_AGG_MIN) {
       if (mine) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) if (v[i] != 0.f) atomicAdd(d + i + (i >> 1), v[i]);
@@ -747,12 +793,12 @@ __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int ke
 // division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
 // Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
 template <bool DETACH, bool ALPHA, bool SAVED>
-__global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kernel(const RasterParams P) {
+__global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW_BWD_BARY_MINB) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
   const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
-  const int yi = blockIdx.y * TILE_H + (warp >> 1) * 4 + (lane >> 3);
+  const int yi = blockIdx.y * (DBW_BWD_NT / 16) + (warp >> 1) * 4 + (lane >> 3);
   const bool live = xi < P.W && yi < P.H;
   const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
   const size_t plane = (size_t)P.H * P.W;
@@ -762,9 +808,9 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
   if (live) { gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane]; }
   const int* ids = P.topk + (size_t)view * P.K * plane + pix;
   float* s_alpha = s_store;
-  float* s_cdot = s_store + (size_t)P.K * NTHREADS;
-  float* s_e = s_store + 2 * (size_t)P.K * NTHREADS;
-  float* s_occ = s_store + 3 * (size_t)P.K * NTHREADS;
+  float* s_cdot = s_store + (size_t)P.K * DBW_BWD_NT;
+  float* s_e = s_store + 2 * (size_t)P.K * DBW_BWD_NT;
+  float* s_occ = s_store + 3 * (size_t)P.K * DBW_BWD_NT;
   const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
   const size_t slot_base = (size_t)view * 2 * P.F;
 
@@ -804,8 +850,8 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
       fa = ALPHA ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
       a = e * fa;
       cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
-      s_alpha[k * NTHREADS + tid] = a; s_cdot[k * NTHREADS + tid] = cdot; s_e[k * NTHREADS + tid] = e;
-      s_occ[k * NTHREADS + tid] = occ;
+      s_alpha[k * DBW_BWD_NT + tid] = a; s_cdot[k * DBW_BWD_NT + tid] = cdot; s_e[k * DBW_BWD_NT + tid] = e;
+      s_occ[k * DBW_BWD_NT + tid] = occ;
       const float w = occ * a;                 // d RGB / d colour_k
       if (w != 0.f) {
         const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
@@ -870,8 +916,8 @@ __global__ void __launch_bounds__(NTHREADS, DETACH ? 4 : 3) raster_backward_kern
     int key = -1;
     float gv7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // (x, y) of the three vertices, then the face opacity
     if (k < n) {
-      const float a = s_alpha[k * NTHREADS + tid], cdot = s_cdot[k * NTHREADS + tid], e = s_e[k * NTHREADS + tid];
-      const float occ_k = s_occ[k * NTHREADS + tid];
+      const float a = s_alpha[k * DBW_BWD_NT + tid], cdot = s_cdot[k * DBW_BWD_NT + tid], e = s_e[k * DBW_BWD_NT + tid];
+      const float occ_k = s_occ[k * DBW_BWD_NT + tid];
       const float g_alpha = occ_k * (cdot - Tacc);
       Tacc = a * cdot + (1.f - a) * Tacc;
       if (g_alpha != 0.f) {
@@ -1076,8 +1122,10 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
 }
 
 template <int K>
-static void launch_forward(const RasterParams& P, dim3 grid, cudaStream_t st) {
-  raster_forward_kernel<K><<<grid, NTHREADS, 0, st>>>(P);
+static void launch_forward(const RasterParams& P, cudaStream_t st) {
+  constexpr int NT = K <= 4 ? DBW_FWD_NT_SMALLK : DBW_FWD_NT;
+  const dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16), P.B);
+  raster_forward_kernel<K, NT><<<grid, NT, 0, st>>>(P);
 }
 
 extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
@@ -1102,13 +1150,15 @@ extern "C" int dbw_render_forward_ex(const DbwRenderSettings* s, const float* ve
   const int B = s->n_views, V = s->n_verts, F = s->n_faces;
   const float* verts_ndc = verts;
   if (!s->verts_are_ndc) {
-    project_verts_kernel<<<(B * V + 255) / 256, 256, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V, w.verts_ndc);
+    const int n_thr = B * (V > 4 ? V : 4);          // the kernel also resets the per-view bbox / flags (4 ints per view)
+    project_verts_kernel<<<(n_thr + 255) / 256, 256, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V, w.verts_ndc,
+                                                              w.view_bbox, w.view_flags);
     LAUNCH_CK("project_verts_kernel");
     verts_ndc = w.verts_ndc;
+  } else {
+    init_view_bbox_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(w.view_bbox, w.view_flags, B);
+    LAUNCH_CK("init_view_bbox_kernel");
   }
-  CK(cudaMemsetAsync(w.view_flags, 0, B * sizeof(int), st));
-  init_view_bbox_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(w.view_bbox, B);
-  LAUNCH_CK("init_view_bbox_kernel");
   face_setup_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
                                                          sqrtf(s->blur_radius), faces_uvs, face_map, map_table, w.bbox, w.rec,
                                                          w.rec2, w.conv, w.view_flags, w.view_bbox);
@@ -1122,16 +1172,15 @@ extern "C" int dbw_render_forward_ex(const DbwRenderSettings* s, const float* ve
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.out_rgba = out_rgba; P.topk = topk_ids; P.face_shade = face_shade; P.out_dists = out_dists;
-  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
   const int K = s->faces_per_pixel;
   ScopedTimer timer(0, K, st);
-  if (K <= 1) launch_forward<1>(P, grid, st);
-  else if (K <= 4) launch_forward<4>(P, grid, st);
-  else if (K <= 10) launch_forward<10>(P, grid, st);
-  else if (K <= 16) launch_forward<16>(P, grid, st);
-  else if (K <= 25) launch_forward<25>(P, grid, st);
-  else if (K <= 32) launch_forward<32>(P, grid, st);
-  else launch_forward<64>(P, grid, st);
+  if (K <= 1) launch_forward<1>(P, st);
+  else if (K <= 4) launch_forward<4>(P, st);
+  else if (K <= 10) launch_forward<10>(P, st);
+  else if (K <= 16) launch_forward<16>(P, st);
+  else if (K <= 25) launch_forward<25>(P, st);
+  else if (K <= 32) launch_forward<32>(P, st);
+  else launch_forward<64>(P, st);
   LAUNCH_CK("raster_forward_kernel");
   return 0;
 }
@@ -1155,13 +1204,13 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
-  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + TILE_H - 1) / TILE_H, B);
-  const size_t smem = 4 * (size_t)s->faces_per_pixel * NTHREADS * sizeof(float);
+  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16), B);
+  const size_t smem = 4 * (size_t)s->faces_per_pixel * DBW_BWD_NT * sizeof(float);
   {
     auto launch = [&](auto kern) -> cudaError_t {
       if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
       ScopedTimer timer(1, s->faces_per_pixel, st);
-      kern<<<grid, NTHREADS, smem, st>>>(P);
+      kern<<<grid, DBW_BWD_NT, smem, st>>>(P);
       return cudaSuccess;
     };
     const bool det = s->detach_bary != 0, al = faces_alpha != nullptr, sv = det && s->save_fragment_state;

@@ -94,9 +94,15 @@ class _RenderFn(torch.autograd.Function):
         L = _lib.lib()
         g_out = g_out.contiguous().float()
         need_v, need_m, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and fa is not None
-        g_verts = torch.zeros_like(verts) if need_v else None
+        g_verts = g_fa = None
+        if need_v and need_a:      # one zero-fill for both small gradients
+            flat = torch.zeros(verts.numel() + fa.numel(), device=verts.device, dtype=torch.float32)
+            g_verts, g_fa = flat[:verts.numel()].view_as(verts), flat[verts.numel():].view_as(fa)
+        elif need_v:
+            g_verts = torch.zeros_like(verts)
+        elif need_a:
+            g_fa = torch.zeros_like(fa)
         g_maps = torch.zeros_like(maps) if need_m else None
-        g_fa = torch.zeros_like(fa) if need_a else None
         scratch = torch.empty(ctx.bwd_bytes, dtype=torch.uint8, device=verts.device)
         _lib.check(L.dbw_render_backward(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
                                          _c(map_table), _c(R), _c(T), _c(fa), _c(ids), _c(ws), ws.numel(), _c(g_out),

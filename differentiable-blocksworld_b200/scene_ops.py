@@ -39,7 +39,12 @@ class _SceneGeometryFn(torch.autograd.Function):
     def backward(ctx, g_out):
         args = ctx.saved_tensors
         g = _geom_struct(ctx.static, *args)
-        grads = [torch.zeros_like(t) for t in args]
+        # one zero-fill for all six gradients (views of a flat buffer) instead of six launches
+        flat = torch.zeros(sum(t.numel() for t in args), device=g_out.device, dtype=torch.float32)
+        grads, o = [], 0
+        for t in args:
+            grads.append(flat[o:o + t.numel()].view_as(t))
+            o += t.numel()
         _lib.check(_lib.lib().dbw_scene_geometry_backward(ctypes.byref(g), _c(g_out.contiguous().float()), *[_c(t) for t in grads],
                                                           _stream()), 'dbw_scene_geometry_backward')
         return (*grads, None)
