@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DBW_RENDER_LIB: explicit path of another build of the same library (kernel experiments); never a fallback
 LIB_PATH = os.environ.get('DBW_RENDER_LIB') or os.path.join(_HERE, 'libdbw_render.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class DbwRenderSettings(ctypes.Structure):
@@ -33,12 +33,18 @@ class DbwSceneGeometry(ctypes.Structure):
                 ('R_world', ctypes.c_float * 9), ('T_world', ctypes.c_float * 3)]
 
 
+class DbwLossEpilogue(ctypes.Structure):
+    _fields_ = [('env_rgba', ctypes.c_void_p), ('target', ctypes.c_void_p), ('g_env', ctypes.c_void_p), ('rec', ctypes.c_void_p),
+                ('loss_partials', ctypes.c_void_p), ('n_partials', ctypes.c_int32), ('inv_count', ctypes.c_float)]
+
+
 class DbwMapDesc(ctypes.Structure):
     _fields_ = [('offset', ctypes.c_int32), ('height', ctypes.c_int32), ('width', ctypes.c_int32),
                 ('reserved', ctypes.c_int32)]
 
 
 EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_forward_ex', 'dbw_render_backward',
+           'dbw_render_forward_loss', 'dbw_render_backward_scaled',
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
            'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward']
@@ -66,6 +72,8 @@ def lib():
         L.dbw_render_forward.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 12 + [sz, vp]
         L.dbw_render_forward_ex.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 12 + [sz, vp, vp, vp]
         L.dbw_render_backward.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 11 + [sz] + [vp] * 5 + [sz, vp]
+        L.dbw_render_forward_loss.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 12 + [sz, ctypes.POINTER(DbwLossEpilogue), vp]
+        L.dbw_render_backward_scaled.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 11 + [sz] + [vp] * 6 + [sz, vp]
         L.dbw_composite_mse.argtypes = [ctypes.c_int32] * 3 + [vp] * 3 + [ctypes.c_float] + [vp] * 5
         L.dbw_composite_mse_backward.argtypes = [ctypes.c_int32] * 3 + [vp] * 3 + [ctypes.c_float] + [vp] * 5
         L.dbw_render_forward_host.argtypes = [ctypes.POINTER(DbwRenderSettings)] + [vp] * 5 + [sz] + [vp] * 6

@@ -372,6 +372,10 @@ struct RasterParams {
   const float* face_shade;   // (B,F,3) per-view per-face colour multiplier (flat shading) or NULL
   float* out_dists;          // (B,K,H,W) signed squared distances of the kept fragments (-1 = empty) or NULL
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
+  const float* grad_scale;   // device scalar multiplied into grad_rgba (the upstream gradient of a fused loss) or NULL
+  // fused compositing + MSE epilogue of the forward (DbwLossEpilogue); ep_target == NULL: plain render
+  const float* ep_env; const float* ep_target; float* ep_g_env; float* ep_rec; float* ep_partials;
+  float ep_inv_count; int ep_part_mask;
 };
 
 // Raster CTAs: the 8x4-pixel patches of a CTA's warps tile a 16 x (NT / 16) pixel tile.  Measured on B200 (cfg 2): the
@@ -609,7 +613,8 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
     }
   }
 
-  if (!live) return;
+  float ep_sq = 0.f;          // this pixel's squared error (fused loss epilogue)
+  if (live) {
   // ---- shade + blend the sorted fragments front to back (layered_rgb_blend, Appendix B)
   float occ = 1.f, r = 0.f, g = 0.f, bl = 0.f;
   const size_t plane = (size_t)P.H * P.W;
@@ -645,16 +650,47 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
     r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
     occ *= (1.f - a);
   }
-#ifdef DBW_EXP_SENTINEL
-  for (int k = n_frag; k < min(n_frag + 1, P.K); ++k) {
-#else
   for (int k = n_frag; k < P.K; ++k) {
-#endif
     ids[(size_t)k * plane] = -1;
     if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = -1.f;
   }
   float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
-  o[0] = r + occ * P.bg0; o[plane] = g + occ * P.bg1; o[2 * plane] = bl + occ * P.bg2; o[3 * plane] = 1.f - occ;
+  const float fc[3] = {r + occ * P.bg0, g + occ * P.bg1, bl + occ * P.bg2};
+  const float m = 1.f - occ;
+  if (!P.ep_target) {
+    o[0] = fc[0]; o[plane] = fc[1]; o[2 * plane] = fc[2]; o[3 * plane] = m;
+  } else {
+    // fused epilogue (same arithmetic as composite_mse_kernel): composite over the environment render, squared error
+    // against the target, and the gradients of the MSE w.r.t. both layers -- out_rgba receives d loss / d (this render)
+    const float* e = P.ep_env + (size_t)view * 4 * plane + pix;
+    const float* im = P.ep_target + (size_t)view * 3 * plane + pix;
+    float* ge = P.ep_g_env + (size_t)view * 4 * plane + pix;
+    float gm = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float ec = e[(size_t)c * plane];
+      const float rc = fc[c] * m + (1.f - m) * ec;
+      const float diff = rc - im[(size_t)c * plane];
+      ep_sq += diff * diff;
+      if (P.ep_rec) P.ep_rec[(size_t)view * 3 * plane + (size_t)c * plane + pix] = rc;
+      const float gr = 2.f * diff * P.ep_inv_count;
+      o[(size_t)c * plane] = gr * m;
+      ge[(size_t)c * plane] = gr * (1.f - m);
+      gm += gr * (fc[c] - ec);
+    }
+    o[3 * plane] = gm;
+    ge[3 * plane] = 0.f;
+  }
+  }   // live
+  if (P.ep_target) {
+    // one atomic per warp into a strip of partial sums (the caller adds them up): no single hot address
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ep_sq += __shfl_xor_sync(0xffffffffu, ep_sq, off);
+    if (lane == 0 && ep_sq != 0.f) {
+      const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      atomicAdd(&P.ep_partials[(cta * (NT / 32) + warp) & P.ep_part_mask], ep_sq * P.ep_inv_count);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -806,6 +842,7 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
   const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
   float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
   if (live) { gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane]; }
+  if (P.grad_scale) { const float gs = __ldg(P.grad_scale); gr *= gs; gg *= gs; gb *= gs; ga *= gs; }
   const int* ids = P.topk + (size_t)view * P.K * plane + pix;
   float* s_alpha = s_store;
   float* s_cdot = s_store + (size_t)P.K * DBW_BWD_NT;
@@ -1136,10 +1173,37 @@ extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts
                                workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
+static int render_forward_impl(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                               const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                               const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
+                               size_t workspace_bytes, const float* face_shade, float* out_dists, const DbwLossEpilogue* ep,
+                               void* stream);
+
 extern "C" int dbw_render_forward_ex(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
                                      const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
                                      const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
                                      size_t workspace_bytes, const float* face_shade, float* out_dists, void* stream) {
+  return render_forward_impl(s, verts, faces, faces_uvs, face_map, maps, map_table, R, T, faces_alpha, out_rgba, topk_ids,
+                             workspace, workspace_bytes, face_shade, out_dists, nullptr, stream);
+}
+
+extern "C" int dbw_render_forward_loss(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                       const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                                       const float* T, const float* faces_alpha, float* out_g_rgba, int32_t* topk_ids,
+                                       void* workspace, size_t workspace_bytes, const DbwLossEpilogue* ep, void* stream) {
+  if (!ep) return fail("dbw_render_forward_loss: null epilogue");
+  if (!ep->env_rgba || !ep->target || !ep->g_env || !ep->loss_partials)
+    return fail("dbw_render_forward_loss: env_rgba, target, g_env and loss_partials are required");
+  if (ep->n_partials < 1 || (ep->n_partials & (ep->n_partials - 1))) return fail("dbw_render_forward_loss: n_partials must be a power of two");
+  return render_forward_impl(s, verts, faces, faces_uvs, face_map, maps, map_table, R, T, faces_alpha, out_g_rgba, topk_ids,
+                             workspace, workspace_bytes, nullptr, nullptr, ep, stream);
+}
+
+static int render_forward_impl(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                               const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                               const float* T, const float* faces_alpha, float* out_rgba, int32_t* topk_ids, void* workspace,
+                               size_t workspace_bytes, const float* face_shade, float* out_dists, const DbwLossEpilogue* ep,
+                               void* stream) {
   if (validate(s)) return -1;
   if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba || !topk_ids || !workspace)
     return fail("dbw_render_forward: null pointer argument");
@@ -1172,6 +1236,11 @@ extern "C" int dbw_render_forward_ex(const DbwRenderSettings* s, const float* ve
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
   P.out_rgba = out_rgba; P.topk = topk_ids; P.face_shade = face_shade; P.out_dists = out_dists;
+  if (ep) {
+    CK(cudaMemsetAsync(ep->loss_partials, 0, (size_t)ep->n_partials * sizeof(float), st));
+    P.ep_env = ep->env_rgba; P.ep_target = ep->target; P.ep_g_env = ep->g_env; P.ep_rec = ep->rec;
+    P.ep_partials = ep->loss_partials; P.ep_inv_count = ep->inv_count; P.ep_part_mask = ep->n_partials - 1;
+  }
   const int K = s->faces_per_pixel;
   ScopedTimer timer(0, K, st);
   if (K <= 1) launch_forward<1>(P, st);
@@ -1190,6 +1259,17 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
                                    const float* T, const float* faces_alpha, const int32_t* topk_ids, const void* workspace,
                                    size_t workspace_bytes, const float* grad_rgba, float* g_verts, float* g_faces_alpha,
                                    float* g_maps, void* bwd_scratch, size_t bwd_scratch_bytes, void* stream) {
+  return dbw_render_backward_scaled(s, verts, faces, faces_uvs, face_map, maps, map_table, R, T, faces_alpha, topk_ids, workspace,
+                                    workspace_bytes, grad_rgba, nullptr, g_verts, g_faces_alpha, g_maps, bwd_scratch,
+                                    bwd_scratch_bytes, stream);
+}
+
+extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
+                                          const int32_t* face_map, const float* maps, const DbwMapDesc* map_table, const float* R,
+                                          const float* T, const float* faces_alpha, const int32_t* topk_ids, const void* workspace,
+                                          size_t workspace_bytes, const float* grad_rgba, const float* grad_scale, float* g_verts,
+                                          float* g_faces_alpha, float* g_maps, void* bwd_scratch, size_t bwd_scratch_bytes,
+                                          void* stream) {
   if (validate(s)) return -1;
   if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !topk_ids || !workspace || !grad_rgba || !bwd_scratch)
     return fail("dbw_render_backward: null pointer argument");
@@ -1202,7 +1282,7 @@ extern "C" int dbw_render_backward(const DbwRenderSettings* s, const float* vert
   CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
-  P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
+  P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16), B);
   const size_t smem = 4 * (size_t)s->faces_per_pixel * DBW_BWD_NT * sizeof(float);

@@ -22,6 +22,7 @@ import torch.nn.functional as F
 
 from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
+from .fused_loss import ScenePass, scene_mse
 from .scene_ops import scene_geometry, texture_atlas
 from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
@@ -110,6 +111,8 @@ class DifferentiableBlocksWorld(nn.Module):
         # execution options of this implementation
         self.static_topology = True       # disable filtered blocks via face_map = -1 instead of slicing (no host sync)
         self.fused_scene = True           # scene_ops kernels for mesh build + texture prep
+        self.fused_loss = True            # compositing + MSE in the rasterizer's epilogue (fused_loss.py) when nothing else reads rec
+        self._passes = None
         self.overlap_passes = False       # environment pass on a side stream (measured: +1 %)
         self.n_total_views = None         # data-parallel context (parallel.py): views of the whole step
         self.noise_generator = None       # RNG shared by all ranks for opacity noise / overlap samples
@@ -215,8 +218,10 @@ class DifferentiableBlocksWorld(nn.Module):
 
     # ------------------------------------------------------------------ one step
     def forward(self, inp, labels=None):
-        env_rgba, fg_rgba = self._render_layers(inp)
         imgs = inp['imgs']
+        if self._fused_loss_ok(imgs):
+            return self.compute_losses(imgs, None, rgb_loss=self._scene_mse_fused(inp))
+        env_rgba, fg_rgba = self._render_layers(inp)
         n_total = self.n_total_views or len(imgs)
         if fg_rgba is not None and isinstance(self.criterion, nn.MSELoss) and imgs.is_cuda:
             rec, mse = _CompositeMSE.apply(fg_rgba, env_rgba, imgs, n_total)
@@ -322,21 +327,34 @@ class DifferentiableBlocksWorld(nn.Module):
             return torch.randn(self.alpha_logit.shape, generator=self.noise_generator, device=self.alpha_logit.device)
         return torch.randn_like(self.alpha_logit)
 
-    def _render_decoupled_fused(self, R, T, hard_filter, renderer):
-        """leaf parameters -> scene kernels -> environment pass + blocks pass"""
+    def _scene_tensors(self, hard_filter):
+        """leaf parameters -> scene kernels -> raw tensors of the two passes:
+        (env verts, env atlas, env map table), (block verts, block atlas, block map table, face_map, per-face opacities)"""
         st = self._static_arrays()
         n_block_verts = self.n_blocks * st['geom']['verts_per_block']
         coarse_training = self.training and self.is_live('coarse_learning')
         decim_env = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
         decim_blocks = self.decim_factor if (coarse_training and self.is_live('decimate_txt')) else 1
         verts = scene_geometry(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground, st['geom'])
-
         # environment: constant background sphere + posed ground, two square maps in one atlas
         env_verts = torch.cat([st['bkg_world'], verts[n_block_verts:]])
         env_atlas = torch.cat([texture_atlas(self.texture_bkg, 0, 0, decim_env).reshape(-1, 4),
                                texture_atlas(self.texture_ground, 0, 0, decim_env).reshape(-1, 4)])
         side = self.texture_bkg.shape[1]
         env_table = [(0, side, side), (side * side * 3, side, side)]
+        # blocks
+        fmap = self._opacities(hard_filter, coarse_training)
+        atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
+        rows, cols = atlas.shape[1], atlas.shape[2]
+        table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
+        alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
+        self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
+        return (env_verts, env_atlas, env_table), (verts[:n_block_verts], atlas.reshape(-1, 4), table, fmap, alpha)
+
+    def _render_decoupled_fused(self, R, T, hard_filter, renderer):
+        """environment pass + blocks pass over the fused scene tensors -> (env RGBA, blocks RGBA)"""
+        st = self._static_arrays()
+        (env_verts, env_atlas, env_table), (blk_verts, atlas, table, fmap, alpha) = self._scene_tensors(hard_filter)
         main = torch.cuda.current_stream()
         stream = main
         if self.overlap_passes:
@@ -346,20 +364,30 @@ class DifferentiableBlocksWorld(nn.Module):
         with torch.cuda.stream(stream):
             env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
                                     R, T, None, texels4=True)
-
-        # blocks
-        fmap = self._opacities(hard_filter, coarse_training)
-        atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
-        rows, cols = atlas.shape[1], atlas.shape[2]
-        table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
-        alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
-        fg_rgba = self._raster(renderer, verts[:n_block_verts], st['faces_b'], st['fvu_b'], fmap, atlas.reshape(-1, 4), table,
-                               R, T, alpha, texels4=True)
+        fg_rgba = self._raster(renderer, blk_verts, st['faces_b'], st['fvu_b'], fmap, atlas, table, R, T, alpha, texels4=True)
         if stream is not main:
             main.wait_stream(stream)
             env_rgba.record_stream(main)
-        self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
         return env_rgba, fg_rgba
+
+    def _fused_loss_ok(self, imgs):
+        """the loss epilogue of the rasterizer applies: decoupled static scene on the GPU, plain MSE, nothing else reads `rec`"""
+        return (self.fused_loss and self.decouple_rendering and self.static_topology and self.fused_scene and imgs.is_cuda
+                and isinstance(self.criterion, nn.MSELoss) and 'rgb' in self.loss_weights
+                and not ('perceptual' in self.loss_weights and self.perceptual_loss is not None))
+
+    def _scene_mse_fused(self, inp):
+        """render both layers, composite and take the MSE inside the rasterizer (fused_loss.scene_mse)"""
+        self._install_cameras(inp)
+        _, hard_filter, renderer = self._phase()
+        st = self._static_arrays()
+        (env_verts, env_atlas, env_table), (blk_verts, atlas, table, fmap, alpha) = self._scene_tensors(hard_filter)
+        key = (id(renderer), id(st['faces_b']), tuple(env_table), tuple(table))
+        if self._passes is None or self._passes[0] != key:
+            self._passes = (key, ScenePass(st['faces_e'], st['fvu_e'], st['fmap_e'], env_table, self.renderer_env),
+                            ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer))
+        return scene_mse(env_verts, env_atlas, blk_verts, atlas, alpha, inp['R'], inp['T'], inp['imgs'], self._passes[1],
+                         self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']))
 
     def _blocks_static(self, hard_filter):
         """eager (PyTorch ops) construction of the blocks scene with fixed shapes -- the reference's arithmetic

@@ -1,0 +1,136 @@
+"""Decoupled render + compositing + RGB loss as ONE autograd node ("MSE fused into blend"):
+
+    env  = render(environment)                      src/model/dbw.py:219      (renderer_env, K=1)
+    fg   = render(blocks)                           src/model/dbw.py:220-221  (renderer / renderer_fine, K=10)
+    rec  = fg_rgb * fg_a + (1 - fg_a) * env_rgb     src/model/dbw.py:223
+    loss = mean((imgs - rec)^2)                     src/model/dbw.py:366-367  (nn.MSELoss)
+
+The blocks pass runs with the loss epilogue of include/dbw_render.h (dbw_render_forward_loss): compositing, squared error
+and the MSE gradients w.r.t. both layers happen per pixel inside the rasterizer while the blended colour is in registers.
+Neither `fg` nor `rec` nor the two image-sized gradient round trips of a separate composite kernel ever touch HBM; the
+backward is the two raster backward kernels reading those gradients, scaled on the fly by the upstream gradient of the loss
+(dbw_render_backward_scaled).  Not usable when another loss consumes `rec` with gradient (LPIPS): the model then keeps
+the separate composite kernel (dbw._CompositeMSE), which accepts a gradient on `rec`."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import DbwLossEpilogue
+from .renderer import _c, _stream, scene_settings
+
+N_PARTIALS = 1024
+
+
+class ScenePass:
+    """static description of one render pass: topology, UVs, map layout and the renderer's shading options"""
+
+    def __init__(self, faces, faces_uvs, face_map, map_table_host, renderer):
+        self.faces = faces.to(torch.int32).contiguous()
+        self.faces_uvs = faces_uvs.contiguous().float()
+        self.face_map = face_map.to(torch.int32).contiguous()
+        self.map_table_host, self.r = map_table_host, renderer
+
+    def settings(self, verts, maps, B, faces_alpha):
+        r = self.r
+        return scene_settings(verts, self.faces, maps, self.map_table_host, B, r.cameras.intrinsics(), r.img_size, r.sigma,
+                              r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color, faces_alpha,
+                              r.perspective_correct, False, r.blur_radius, True)
+
+
+def _workspace(cfg, dev):
+    fwd, bwd = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    _lib.check(_lib.lib().dbw_workspace_bytes(ctypes.byref(cfg), ctypes.byref(fwd), ctypes.byref(bwd)), 'dbw_workspace_bytes')
+    return torch.empty(fwd.value, dtype=torch.uint8, device=dev), bwd.value
+
+
+class _SceneMSEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, env_verts, env_maps, blk_verts, blk_maps, blk_alpha, R, T, imgs, env_pass, blk_pass, blk_face_map,
+                cfgs, inv_count, want_rec):
+        L = _lib.lib()
+        dev = blk_verts.device
+        B, _, H, W = imgs.shape
+        f32 = lambda t: t.detach().contiguous().float()
+        env_verts, env_maps, blk_verts, blk_maps = f32(env_verts), f32(env_maps), f32(blk_verts), f32(blk_maps)
+        R, T, imgs = f32(R), f32(T), f32(imgs)
+        fa = f32(blk_alpha) if blk_alpha is not None else None
+        fmap_b = blk_face_map.to(torch.int32).contiguous()
+        (cfg_e, table_e), (cfg_b, table_b) = cfgs
+        ws_e, bwd_e = _workspace(cfg_e, dev)
+        ws_b, bwd_b = _workspace(cfg_b, dev)
+        Ke, Kb = cfg_e.faces_per_pixel, cfg_b.faces_per_pixel
+        env_rgba = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)
+        ids_e = torch.empty(B, Ke, H, W, dtype=torch.int32, device=dev)
+        _lib.check(L.dbw_render_forward_ex(ctypes.byref(cfg_e), _c(env_verts), _c(env_pass.faces), _c(env_pass.faces_uvs),
+                                           _c(env_pass.face_map), _c(env_maps), _c(table_e), _c(R), _c(T), None, _c(env_rgba),
+                                           _c(ids_e), _c(ws_e), ws_e.numel(), None, None, _stream()), 'dbw_render_forward_ex')
+        g_fg = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)       # d loss / d blocks RGBA (unscaled)
+        g_env = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)      # d loss / d env RGBA (unscaled)
+        ids_b = torch.empty(B, Kb, H, W, dtype=torch.int32, device=dev)
+        partials = torch.empty(N_PARTIALS, dtype=torch.float32, device=dev)
+        rec = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_rec else None
+        ep = DbwLossEpilogue()
+        ep.env_rgba, ep.target, ep.g_env = env_rgba.data_ptr(), imgs.data_ptr(), g_env.data_ptr()
+        ep.rec = rec.data_ptr() if rec is not None else None
+        ep.loss_partials, ep.n_partials, ep.inv_count = partials.data_ptr(), N_PARTIALS, float(inv_count)
+        _lib.check(L.dbw_render_forward_loss(ctypes.byref(cfg_b), _c(blk_verts), _c(blk_pass.faces), _c(blk_pass.faces_uvs),
+                                             _c(fmap_b), _c(blk_maps), _c(table_b), _c(R), _c(T), _c(fa), _c(g_fg), _c(ids_b),
+                                             _c(ws_b), ws_b.numel(), ctypes.byref(ep), _stream()), 'dbw_render_forward_loss')
+        loss = partials.sum()
+        ctx.save_for_backward(env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ids_e, ids_b,
+                              ws_e, ws_b, g_fg, g_env)
+        ctx.meta = (env_pass, blk_pass, cfg_e, cfg_b, bwd_e, bwd_b)
+        if want_rec:
+            ctx.mark_non_differentiable(rec)
+            return loss, rec
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_rec=None):
+        (env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ids_e, ids_b, ws_e, ws_b, g_fg,
+         g_env) = ctx.saved_tensors
+        env_pass, blk_pass, cfg_e, cfg_b, bwd_e, bwd_b = ctx.meta
+        L = _lib.lib()
+        dev = blk_verts.device
+        gl = g_loss.detach().contiguous().float()
+        need = ctx.needs_input_grad
+
+        def run(cfg, p, fmap, verts, maps, table, alpha, ids, ws, grad, bwd_bytes, need_v, need_m, need_a):
+            need_a = need_a and alpha is not None
+            g_verts = g_alpha = None
+            if need_v and need_a:          # one zero-fill for both small gradients
+                flat = torch.zeros(verts.numel() + alpha.numel(), device=dev, dtype=torch.float32)
+                g_verts, g_alpha = flat[:verts.numel()].view_as(verts), flat[verts.numel():].view_as(alpha)
+            elif need_v:
+                g_verts = torch.zeros_like(verts)
+            elif need_a:
+                g_alpha = torch.zeros_like(alpha)
+            g_maps = torch.zeros_like(maps) if need_m else None
+            if g_verts is None and g_maps is None and g_alpha is None:
+                return None, None, None
+            scratch = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.dbw_render_backward_scaled(ctypes.byref(cfg), _c(verts), _c(p.faces), _c(p.faces_uvs), _c(fmap), _c(maps),
+                                                    _c(table), _c(R), _c(T), _c(alpha), _c(ids), _c(ws), ws.numel(), _c(grad),
+                                                    _c(gl), _c(g_verts), _c(g_alpha), _c(g_maps), _c(scratch), scratch.numel(),
+                                                    _stream()), 'dbw_render_backward_scaled')
+            return g_verts, g_maps, g_alpha
+
+        gv_b, gm_b, ga_b = run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ids_b, ws_b, g_fg, bwd_b,
+                               need[2], need[3], need[4])
+        gv_e, gm_e, _ = run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ids_e, ws_e, g_env, bwd_e,
+                            need[0], need[1], False)
+        return gv_e, gm_e, gv_b, gm_b, ga_b, None, None, None, None, None, None, None, None, None
+
+
+def scene_mse(env_verts, env_atlas, blk_verts, blk_atlas, blk_alpha, R, T, imgs, env_pass, blk_pass, blk_face_map,
+              n_total_views=None, return_rec=False):
+    """MSE between `imgs` (B,3,H,W) and the blocks composited over the environment, both rendered from raw scene tensors
+    (float4 texel atlases from scene_ops.texture_atlas).  `n_total_views`: size of the GLOBAL batch the mean runs over
+    (view-sharded data parallelism).  Returns the loss, or (loss, rec) with a non-differentiable `rec`."""
+    B, _, H, W = imgs.shape
+    inv = 1.0 / (float(n_total_views or B) * 3 * H * W)
+    # settings are made out here: inside Function.forward grad mode is off and the passes would not save fragment state
+    cfgs = (env_pass.settings(env_verts, env_atlas, B, None), blk_pass.settings(blk_verts, blk_atlas, B, blk_alpha))
+    return _SceneMSEFn.apply(env_verts, env_atlas, blk_verts, blk_atlas, blk_alpha, R, T, imgs, env_pass, blk_pass,
+                             blk_face_map, cfgs, inv, bool(return_rec))

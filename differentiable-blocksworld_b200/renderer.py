@@ -142,20 +142,13 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     return s
 
 
-def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
-                 z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
-                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False,
-                 face_shade=None, return_dists=False):
-    """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
-    verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
-    map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
-    maps_are_texels4: `maps` is a float4 (RGB+pad) texel atlas from scene_ops.texture_atlas (offsets stay 3*texel)."""
+def scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip=None,
+                   detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None, perspective_correct=True,
+                   verts_are_ndc=False, blur_radius=None, maps_are_texels4=False):
+    """(DbwRenderSettings, device map table) of one render pass over raw scene tensors"""
     H, W = image_size
-    B = R.shape[0] if R is not None else verts.shape[0]
-    V = verts.shape[-2]
-    Fn = faces.shape[0]
-    dev = verts.device
-    map_table = _device_map_table(map_table_host, dev)
+    V, Fn = verts.shape[-2], faces.shape[0]
+    map_table = _device_map_table(map_table_host, verts.device)
     alpha_stride = 0
     if faces_alpha is not None:
         if faces_alpha.numel() == B * Fn and B > 1:
@@ -170,6 +163,22 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
                         maps_are_texels4=maps_are_texels4,
                         # a detach_bary backward can stream saved fragment colours / UVs instead of re-deriving them
                         save_fragment_state=bool(detach_bary) and torch.is_grad_enabled())
+    return cfg, map_table
+
+
+def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
+                 z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
+                 perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False,
+                 face_shade=None, return_dists=False):
+    """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
+    verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
+    map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
+    maps_are_texels4: `maps` is a float4 (RGB+pad) texel atlas from scene_ops.texture_atlas (offsets stay 3*texel)."""
+    dev = verts.device
+    B = R.shape[0] if R is not None else verts.shape[0]
+    cfg, map_table = scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip,
+                                    detach_bary, clip_inside, background, faces_alpha, perspective_correct, verts_are_ndc,
+                                    blur_radius, maps_are_texels4)
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)

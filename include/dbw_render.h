@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 4
+#define DBW_ABI_VERSION 5
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -136,6 +136,40 @@ int dbw_composite_mse(int32_t n_views, int32_t height, int32_t width, const floa
 int dbw_composite_mse_backward(int32_t n_views, int32_t height, int32_t width, const float* fg, const float* env,
                                const float* imgs, float inv_count, const float* g_loss, const float* g_rec, float* g_fg,
                                float* g_env, void* stream);
+
+/*
+ * Fused loss epilogue ("MSE fused into blend").  dbw_render_forward_loss is dbw_render_forward for the
+ * LAST layer of a decoupled render (the blocks, src/model/dbw.py:219-223) with the compositing over the already rendered
+ * environment and the RGB loss (dbw.py:366-367, nn.MSELoss) done in the rasterizer's epilogue, per pixel, while the blended
+ * colour is still in registers:
+ *     rec = rgb * a + (1 - a) * rgb_env ;  loss = sum((rec - target)^2) * inv_count
+ * Instead of the image, `out_rgba` receives d loss / d (this layer's RGBA) and `g_env` d loss / d env_rgba (alpha plane 0),
+ * i.e. exactly the grad_rgba inputs of the two dbw_render_backward calls (scaled there by the upstream gradient of the
+ * loss through `grad_scale`): no composite kernel, no image round trip through HBM in either direction.
+ */
+typedef struct DbwLossEpilogue {
+  const float* env_rgba;      /* (B,4,H,W) render of the layer behind (dbw_render_forward output)                          */
+  const float* target;        /* (B,3,H,W) ground-truth images                                                             */
+  float* g_env;               /* (B,4,H,W) out: d loss / d env_rgba                                                        */
+  float* rec;                 /* (B,3,H,W) out: composited image, or NULL                                                  */
+  float* loss_partials;       /* (n_partials) out: zero-filled by the call, then partial sums; loss = their sum            */
+  int32_t n_partials;         /* power of two, >= 1                                                                        */
+  float inv_count;            /* weight / (B_total * 3 * H * W): the mean of nn.MSELoss over the GLOBAL batch              */
+} DbwLossEpilogue;
+
+int dbw_render_forward_loss(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                            const float* faces_uvs, const int32_t* face_map, const float* maps,
+                            const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                            float* out_g_rgba, int32_t* topk_ids, void* workspace, size_t workspace_bytes,
+                            const DbwLossEpilogue* epilogue, void* stream);
+
+/* dbw_render_backward with grad_rgba multiplied by the device scalar *grad_scale (NULL = 1) as it is read. */
+int dbw_render_backward_scaled(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
+                               const float* faces_uvs, const int32_t* face_map, const float* maps,
+                               const DbwMapDesc* map_table, const float* R, const float* T, const float* faces_alpha,
+                               const int32_t* topk_ids, const void* workspace, size_t workspace_bytes,
+                               const float* grad_rgba, const float* grad_scale, float* g_verts, float* g_faces_alpha,
+                               float* g_maps, void* bwd_scratch, size_t bwd_scratch_bytes, void* stream);
 
 /*
  * Fused scene construction (src/model/dbw.py:267-352), so that a training step needs no eager tensor ops between the

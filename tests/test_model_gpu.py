@@ -204,6 +204,47 @@ def test_fused_scene_path_equals_eager_path(fine):
         assert (a - b).norm() <= 2e-4 * b.norm() + 1e-10, (n, (a - b).norm().item(), b.norm().item())
 
 
+@pytest.mark.parametrize('fine', [False, True])
+def test_loss_epilogue_in_the_rasterizer_equals_composite_kernel(fine):
+    """fused_loss.scene_mse (compositing + MSE + their gradients in the blocks pass' epilogue, dbw_render_forward_loss /
+    dbw_render_backward_scaled) against the separate render -> dbw_composite_mse path, incl. a non-unit upstream gradient
+    and the global-batch normalisation of a view shard."""
+    model, tpl, p, dev = _model_and_oracle(fine=fine)
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    model.n_total_views = 7                      # this batch is a 3-view shard of a 7-view step
+    outs = []
+    for fused in (True, False):
+        model.fused_loss = fused
+        assert model._fused_loss_ok(inp['imgs']) == fused
+        model.zero_grad(set_to_none=True)
+        losses = model(inp, None)
+        (0.37 * losses['total']).backward()
+        outs.append((losses['rgb'].item(), {n: prm.grad.clone() for n, prm in model.named_parameters() if prm.grad is not None}))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[1][0])
+    assert set(outs[0][1]) == set(outs[1][1])
+    for n in outs[1][1]:
+        a, b = outs[0][1][n], outs[1][1][n]
+        assert (a - b).norm() <= 1e-4 * b.norm() + 1e-12, (n, (a - b).norm().item(), b.norm().item())
+
+
+def test_loss_epilogue_returns_the_composited_image():
+    from dbw_b200.fused_loss import scene_mse
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.eval()
+    with torch.no_grad():
+        rec_ref = model.predict(inp)
+        model._install_cameras(inp)
+        model._scene_mse_fused(inp)             # builds the pass descriptions
+        _, hard_filter, _ = model._phase()
+        (ev, ea, _), (bv, ba, _, fmap, alpha) = model._scene_tensors(hard_filter)
+        loss, rec = scene_mse(ev, ea, bv, ba, alpha, inp['R'], inp['T'], inp['imgs'], model._passes[1], model._passes[2], fmap,
+                              return_rec=True)
+    assert torch.allclose(rec, rec_ref, atol=1e-6)
+    assert abs(loss.item() - ((rec_ref - inp['imgs']) ** 2).mean().item()) < 1e-6
+
+
 def test_composite_mse_fused_matches_torch():
     """dbw_composite_mse / _backward vs the eager expressions of dbw.py:223,366-367, incl. a gradient arriving at rec."""
     from dbw_b200.dbw import _CompositeMSE
