@@ -449,7 +449,7 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
 #define DBW_FWD_SMALLK_MINB 6     // K <= 4, CTAs of DBW_FWD_NT_SMALLK threads (40 registers)
 #endif
 #ifndef DBW_FWD_K10_MINB
-#define DBW_FWD_K10_MINB 6        // 4 < K <= 10, CTAs of DBW_FWD_NT threads (80 registers)
+#define DBW_FWD_K10_MINB 7        // 4 < K <= 10, CTAs of DBW_FWD_NT threads (72 registers)
 #endif
 #ifndef DBW_BWD_DETACH_MINB
 #define DBW_BWD_DETACH_MINB 10    // backward without the barycentric path, CTAs of DBW_BWD_NT threads (48 registers)
@@ -461,7 +461,8 @@ __host__ __device__ constexpr int max_i(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int fwd_min_ctas(int K, int NT) {
   return K <= 4 ? DBW_FWD_SMALLK_MINB : (K <= 10 ? DBW_FWD_K10_MINB : max_i(1, (K <= 25 ? 2 : 1) * 256 / NT));
 }
-template <int K, int NT>
+// EP: with the compositing + MSE loss epilogue (DbwLossEpilogue); a template flag so that plain renders carry none of it
+template <int K, int NT, bool EP>
 __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel(const RasterParams P) {
   __shared__ float4 s_bbox[LIST_CAP];
   __shared__ float4 s_rec[LIST_CAP * 4];
@@ -657,20 +658,24 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
   float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
   const float fc[3] = {r + occ * P.bg0, g + occ * P.bg1, bl + occ * P.bg2};
   const float m = 1.f - occ;
-  if (!P.ep_target) {
+  if (!EP) {
     o[0] = fc[0]; o[plane] = fc[1]; o[2 * plane] = fc[2]; o[3 * plane] = m;
   } else {
     // fused epilogue (same arithmetic as composite_mse_kernel): composite over the environment render, squared error
     // against the target, and the gradients of the MSE w.r.t. both layers -- out_rgba receives d loss / d (this render)
-    const float* e = P.ep_env + (size_t)view * 4 * plane + pix;
-    const float* im = P.ep_target + (size_t)view * 3 * plane + pix;
+    float ep_e[3], ep_t[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ep_e[c] = __ldg(P.ep_env + (size_t)view * 4 * plane + (size_t)c * plane + pix);
+      ep_t[c] = __ldg(P.ep_target + (size_t)view * 3 * plane + (size_t)c * plane + pix);
+    }
     float* ge = P.ep_g_env + (size_t)view * 4 * plane + pix;
     float gm = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float ec = e[(size_t)c * plane];
+      const float ec = ep_e[c];
       const float rc = fc[c] * m + (1.f - m) * ec;
-      const float diff = rc - im[(size_t)c * plane];
+      const float diff = rc - ep_t[c];
       ep_sq += diff * diff;
       if (P.ep_rec) P.ep_rec[(size_t)view * 3 * plane + (size_t)c * plane + pix] = rc;
       const float gr = 2.f * diff * P.ep_inv_count;
@@ -682,7 +687,7 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
     ge[3 * plane] = 0.f;
   }
   }   // live
-  if (P.ep_target) {
+  if (EP) {
     // one atomic per warp into a strip of partial sums (the caller adds them up): no single hot address
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ep_sq += __shfl_xor_sync(0xffffffffu, ep_sq, off);
@@ -1162,7 +1167,8 @@ template <int K>
 static void launch_forward(const RasterParams& P, cudaStream_t st) {
   constexpr int NT = K <= 4 ? DBW_FWD_NT_SMALLK : DBW_FWD_NT;
   const dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16), P.B);
-  raster_forward_kernel<K, NT><<<grid, NT, 0, st>>>(P);
+  if (P.ep_target) raster_forward_kernel<K, NT, true><<<grid, NT, 0, st>>>(P);
+  else raster_forward_kernel<K, NT, false><<<grid, NT, 0, st>>>(P);
 }
 
 extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
