@@ -45,9 +45,9 @@ def peaks():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very
-# workload at N=1 (profiles/ncu_full_r1d_summary.txt); None for other shard sizes
-NCU_TRAFFIC_BYTES = {'raster_forward[env K=1]': 110.9e6, 'raster_forward[blocks K=10]': 409.5e6,
-                     'raster_backward[blocks K=10]': 301.1e6, 'raster_backward[env K=1]': 161.7e6}
+# workload at N=1 (profiles/ncu_full_r1f_summary.txt); None for other shard sizes
+NCU_TRAFFIC_BYTES = {'raster_forward[env K=1]': 108.9e6, 'raster_forward[blocks K=10]': 1402.5e6,
+                     'raster_backward[blocks K=10]': 1001.7e6, 'raster_backward[env K=1]': 162.3e6}
 
 
 def algorithmic_bytes_per_view(K, H, W):
@@ -250,7 +250,7 @@ def run_ours(args):
             'clocks': clocks,
             'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': NCU_TRAFFIC_BYTES.get(names[dom]) if world == 1 else None,
-                         'traffic_source': 'profiles/ncu_full_r1d_summary.txt (bytes per launch at N=1)', 'peak_source': peak_src,
+                         'traffic_source': 'profiles/ncu_full_r1f_summary.txt (bytes per launch at N=1)', 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': dom_ms,
                          'kernels_ms_per_step': {names[k]: kt[k][0] / args.steps for k in kt}},
         }

@@ -1,7 +1,7 @@
 """Turn gpurun_out/{launches_TAG.csv, prof_TAG.ncu-rep} into the committed summaries under profiles/."""
 import collections, csv, os, subprocess, sys
 tag = sys.argv[1]
-steps_in_run = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: infer from the once-per-step composite kernel
+steps_in_run = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # 0: infer from the once-per-step scene geometry kernel
 os.makedirs('profiles', exist_ok=True)
 lines = [l for l in open(f'gpurun_out/launches_{tag}.csv') if not l.startswith('==')]
 agg = collections.OrderedDict()
@@ -11,7 +11,7 @@ for row in csv.DictReader(lines):
     a = agg.setdefault(row['Kernel Name'][:90], [0, 0.0]); a[0] += 1; a[1] += v
 tot = sum(a[1] for a in agg.values())
 if not steps_in_run:
-    steps_in_run = max(1, sum(a[0] for k, a in agg.items() if k.startswith('composite_mse_kernel')))
+    steps_in_run = max(1, sum(a[0] for k, a in agg.items() if k.startswith('scene_geometry_forward_kernel')))
 with open(f'profiles/launches_{tag}_summary.txt', 'w') as f:
     f.write(f'# ncu --metrics gpu__time_duration.sum --clock-control none python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n')
     f.write(f'# {sum(a[0] for a in agg.values())} launches over {steps_in_run} steps; per-step averages; cold-cache serialised times: compare SHARES\n')
@@ -29,8 +29,8 @@ want = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dra
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
 idx = {h: i for i, h in enumerate(hdr)}
 with open(f'profiles/ncu_full_{tag}_summary.txt', 'w') as f:
-    f.write(f'# ncu --set full --clock-control none --import-source on -k regex:raster_ -s 12 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n')
-    f.write('# one step at cfg 2 (49 views 400x400, 10 blocks): env forward (K=1), blocks forward (K=10), then the two backward launches\n')
+    f.write(f'# ncu --set full --clock-control none --import-source on -k regex:raster_ -s 16 -c 4 python bench.py --steps 1 --warmup 3 --no-cpu-baseline\n')
+    f.write('# one step at cfg 2 (49 views 400x400, 10 blocks): env forward (K=1), blocks forward (K=10, with the loss epilogue), blocks backward, env backward\n')
     for w in want:
         if w in idx:
             f.write(f'{w:70s} [{units[idx[w]]:>14s}] ' + ' | '.join(r[idx[w]][:24] for r in data) + '\n')
