@@ -392,7 +392,7 @@ struct RasterParams {
 #endif
 #define TILE_W 16
 #ifndef LIST_CAP
-#define LIST_CAP 256           // faces a tile lists at once (more: chunked path); 21 KB of shared memory per CTA
+#define LIST_CAP 256           // default capacity of a tile's face list (21 KB of shared memory per CTA)
 #endif
 #ifndef DBW_AGG_MIN
 #define DBW_AGG_MIN 2         // groups of at most this many lanes use plain atomics instead of a warp reduction
@@ -464,9 +464,13 @@ __host__ __device__ constexpr int fwd_min_ctas(int K, int NT) {
 // EP: with the compositing + MSE loss epilogue (DbwLossEpilogue); a template flag so that plain renders carry none of it
 template <int K, int NT, bool EP>
 __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel(const RasterParams P) {
-  __shared__ float4 s_bbox[LIST_CAP];
-  __shared__ float4 s_rec[LIST_CAP * 4];
-  __shared__ int s_slot[LIST_CAP];
+  // faces a tile lists at once (more: chunked path).  Small-K scenes list few faces per tile, and every KB of shared
+  // memory not taken is L1 for the texel / record fetches: 128 entries (10.5 KB) for the 128-thread K <= 10 kernels
+  constexpr int CAP = (NT <= 128 && K <= 10) ? 128 : LIST_CAP;
+  static_assert(CAP >= NT, "a scan batch adds up to NT entries");
+  __shared__ float4 s_bbox[CAP];
+  __shared__ float4 s_rec[CAP * 4];
+  __shared__ int s_slot[CAP];
   __shared__ int s_count;
   __shared__ __align__(8) uint64_t s_bar;      // mbarrier of the TMA record gather
   uint32_t bar_phase = 0;
@@ -576,14 +580,14 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
     if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-    if (hit && pos < LIST_CAP) { s_slot[pos] = s; s_bbox[pos] = bb; }
+    if (hit && pos < CAP) { s_slot[pos] = s; s_bbox[pos] = bb; }
   }
   __syncthreads();
   const int total = s_count;
-  if (total <= LIST_CAP) {
+  if (total <= CAP) {
     if (total > 0) raster_list(total);
   } else {
-    // chunked path (more than LIST_CAP faces touch this tile): re-scan, flushing the list whenever it may overflow
+    // chunked path (more than CAP faces touch this tile): re-scan, flushing the list whenever it may overflow
     __syncthreads();
     if (tid == 0) s_count = 0;
     __syncthreads();
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
       __syncthreads();
       const int cnt = s_count;
       const bool last = base + NT >= nslots;
-      if (cnt > LIST_CAP - NT || last) {
+      if (cnt > CAP - NT || last) {
         raster_list(cnt);
         __syncthreads();              // every warp is done with the list before it is reset and refilled
         if (tid == 0) s_count = 0;

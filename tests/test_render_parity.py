@@ -186,9 +186,11 @@ def test_verts_are_ndc_entry():
     _check_image(out.cpu(), ref)
 
 
-def test_stress_shape_many_faces_k25():
+@pytest.mark.parametrize('faces_per_pixel', [25, 10])
+def test_stress_shape_many_faces(faces_per_pixel):
     """BASELINE configs[4] shape at reduced resolution: 50 blocks (4000 faces), K = 25 -- exercises the chunked tile
-    lists (more listed faces than the shared-memory list holds at once) and the K = 25 register top-K."""
+    lists (more listed faces than the shared-memory list holds at once: 256 entries for K = 25, 128 for the K <= 10
+    kernels) and the K = 25 register top-K."""
     dev = _dev()
     tpl = D.SceneTemplate(n_blocks=50, txt_size=16)
     p = D.init_params(50, 16, seed=7, boxy=True)
@@ -196,10 +198,10 @@ def test_stress_shape_many_faces_k25():
     R, T, K = D.ring_cameras(2, jitter=0.3, seed=7, dist=2.0)
     blocks, alpha = tpl.build_blocks(p)
     fa = alpha.repeat_interleave(tpl.BNF)
-    ref, fr = D.render(blocks, R, T, K, (96, 128), sigma=1e-4, faces_per_pixel=25, z_clip=0.001, detach_bary=True,
+    ref, fr = D.render(blocks, R, T, K, (96, 128), sigma=1e-4, faces_per_pixel=faces_per_pixel, z_clip=0.001, detach_bary=True,
                        faces_alpha=fa, return_fragments=True)
     sc = scene_to_device(blocks, dev)
-    out, ids = render_product(sc, R.to(dev), T.to(dev), K, (96, 128), 1e-4, 25, z_clip=0.001, detach_bary=True,
+    out, ids = render_product(sc, R.to(dev), T.to(dev), K, (96, 128), 1e-4, faces_per_pixel, z_clip=0.001, detach_bary=True,
                               faces_alpha=fa.to(dev), return_ids=True)
     assert (fr.pix_to_face[..., -1] >= 0).float().mean() > 0.01       # K really is exceeded somewhere
     _check_image(out.cpu(), ref, max_bad_frac=3e-4)
