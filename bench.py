@@ -255,7 +255,7 @@ def run_ours(args):
                          'kernels_ms_per_step': {names[k]: kt[k][0] / args.steps for k in kt}},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(n_views=2)
+            line['cpu_baseline'] = cpu_baseline(n_views=16)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -285,7 +285,7 @@ def cpu_threads():
     return min(os.cpu_count(), 32)
 
 
-def cpu_baseline(n_views=2):
+def cpu_baseline(n_views=16):
     torch.set_num_threads(cpu_threads())
     oracle_step(1)                                   # warm-up (page in the library, thread pools)
     dt = oracle_step(n_views)
