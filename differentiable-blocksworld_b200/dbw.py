@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
 from .fused_loss import ScenePass, scene_mse
-from .scene_ops import scene_geometry, texture_atlas
+from .scene_ops import scene_geometry, scene_geometry_parts, texture_atlas
 from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
 # accepted keys and defaults of the config sub-dicts (configs/*/*.yml -> model.{mesh,rend_optim,loss}); unknown keys are
@@ -299,25 +299,28 @@ class DifferentiableBlocksWorld(nn.Module):
                 fmap_b=torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(self.BNF),
                 faces_e=torch.cat([bf, gf + bv.shape[0]]).to(torch.int32).contiguous(),
                 fvu_e=torch.cat([self.bkg_verts_uvs[bf], self.ground_verts_uvs[gf]]).contiguous(),
-                fmap_e=torch.cat([torch.zeros(len(bf)), torch.ones(len(gf))]).to(dev).to(torch.int32))
+                fmap_e=torch.cat([torch.zeros(len(bf)), torch.ones(len(gf))]).to(dev).to(torch.int32),
+                minus_one=torch.full((), -1, dtype=torch.int32, device=dev))
         return self._static
 
     def _fused_arrays(self):          # name used by tests / scene_ops callers
         return self._static_arrays()
 
     def _opacities(self, hard_filter, coarse_training):
-        """per-block opacities (+ exploration noise while coarse) and the face_map that disables filtered blocks"""
+        """per-block opacities (+ exploration noise while coarse) and the face_map that disables filtered blocks
+        (dbw.py:300-316 with static shapes); written for few launches: it runs every step"""
         st = self._static_arrays()
         logit = self.alpha_logit
         if self.opacity_noise and coarse_training:
-            logit = logit + self.opacity_noise * self._draw_opacity_noise()
+            logit = torch.add(logit, self._draw_opacity_noise(), alpha=float(self.opacity_noise))
         self._alpha = torch.sigmoid(logit)
-        self._alpha_full = self._alpha.clone()
+        self._alpha_full = self._alpha
         fmap = st['fmap_b']
         if hard_filter or self.kill_blocks:
-            keep = torch.sigmoid(self.alpha_logit) > (0.5 if hard_filter else 0.01)
-            self._alpha_full = self._alpha_full * keep
-            fmap = torch.where(keep.repeat_interleave(self.BNF), fmap, torch.full_like(fmap, -1))
+            with torch.no_grad():
+                keep = torch.sigmoid(self.alpha_logit) > (0.5 if hard_filter else 0.01)
+                fmap = torch.where(keep[:, None], fmap.view(self.n_blocks, self.BNF), st['minus_one']).reshape(-1)
+            self._alpha_full = self._alpha * keep
         return fmap
 
     def _draw_opacity_noise(self):
@@ -331,13 +334,13 @@ class DifferentiableBlocksWorld(nn.Module):
         """leaf parameters -> scene kernels -> raw tensors of the two passes:
         (env verts, env atlas, env map table), (block verts, block atlas, block map table, face_map, per-face opacities)"""
         st = self._static_arrays()
-        n_block_verts = self.n_blocks * st['geom']['verts_per_block']
         coarse_training = self.training and self.is_live('coarse_learning')
         decim_env = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
         decim_blocks = self.decim_factor if (coarse_training and self.is_live('decimate_txt')) else 1
-        verts = scene_geometry(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground, st['geom'])
+        blk_verts, ground_verts = scene_geometry_parts(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground,
+                                                       st['geom'])
         # environment: constant background sphere + posed ground, two square maps in one atlas
-        env_verts = torch.cat([st['bkg_world'], verts[n_block_verts:]])
+        env_verts = torch.cat([st['bkg_world'], ground_verts])
         env_atlas = torch.cat([texture_atlas(self.texture_bkg, 0, 0, decim_env).reshape(-1, 4),
                                texture_atlas(self.texture_ground, 0, 0, decim_env).reshape(-1, 4)])
         side = self.texture_bkg.shape[1]
@@ -347,9 +350,9 @@ class DifferentiableBlocksWorld(nn.Module):
         atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
         rows, cols = atlas.shape[1], atlas.shape[2]
         table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
-        alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
+        alpha = None if hard_filter else self._alpha[:, None].expand(-1, self.BNF).reshape(-1)
         self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
-        return (env_verts, env_atlas, env_table), (verts[:n_block_verts], atlas.reshape(-1, 4), table, fmap, alpha)
+        return (env_verts, env_atlas, env_table), (blk_verts, atlas.reshape(-1, 4), table, fmap, alpha)
 
     def _render_decoupled_fused(self, R, T, hard_filter, renderer):
         """environment pass + blocks pass over the fused scene tensors -> (env RGBA, blocks RGBA)"""
@@ -549,9 +552,10 @@ class DifferentiableBlocksWorld(nn.Module):
         w = self.loss_weights
         if 'tv' in w or 'overlap' in w:
             self._refresh_reg_state()
-        terms = {k: torch.zeros((), device=imgs.device) for k in w}
+        terms = {}
         if 'rgb' in w:
-            terms['rgb'] = w['rgb'] * (rgb_loss if rgb_loss is not None else self.criterion(imgs, rec))
+            rgb = rgb_loss if rgb_loss is not None else self.criterion(imgs, rec)
+            terms['rgb'] = rgb if w['rgb'] == 1 else w['rgb'] * rgb
         if 'perceptual' in w and self.perceptual_loss is not None:
             terms['perceptual'] = w['perceptual'] * (1 if coarse else 0.1) * self.perceptual_loss(imgs, rec)
         if 'parsimony' in w:
@@ -562,7 +566,13 @@ class DifferentiableBlocksWorld(nn.Module):
             S, R, T = self._blocks_SRT
             terms['overlap'] = w['overlap'] * L.overlap(S, R, T, *self._blocks_eps, self._alpha_full, self.ratio_block_scene,
                                                         coarse, generator=self.noise_generator)
-        terms['total'] = sum(terms.values())
+        vals = list(terms.values())
+        total = vals[0] if vals else torch.zeros((), device=imgs.device)
+        for v in vals[1:]:
+            total = total + v
+        for k in w:                                   # weights whose term is not produced (perceptual without a network)
+            terms.setdefault(k, torch.zeros((), device=imgs.device))
+        terms['total'] = total
         return terms
 
     # ------------------------------------------------------------------ checkpoints / evaluation

@@ -46,10 +46,8 @@ class GraphedStep:
             self.losses = self._body()
 
     def _body(self):
-        self.vp.bucket.zero_()
         losses = self.model(self.static_inp, None)
-        total = self.vp.weighted_total(losses, len(self.static_inp['imgs']), self.n_total)
-        total.backward()
+        self.vp.bucket.backward(self.vp.weighted_total(losses, len(self.static_inp['imgs']), self.n_total))
         if self.capture_all_reduce:
             self.vp.bucket.all_reduce(self.vp.group)
         return losses

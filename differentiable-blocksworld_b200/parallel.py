@@ -30,13 +30,36 @@ class GradBucket:
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
-        off = 0
+        self._zeros = {}
+        off, self.views = 0, []
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            p.grad = self.views[-1]
             off += p.numel()
 
     def zero_(self):
         self.flat.zero_()
+
+    def backward(self, total):
+        """Back-propagate `total` and leave every parameter's gradient in the flat bucket with ONE gather kernel: the
+        parameters enter the backward without .grad, so autograd hands over each gradient tensor as it is (no zero-fill
+        of the bucket, no accumulate-add per parameter); a single cat then writes them into the flat buffer and the
+        .grad attributes become the bucket views again.  CUDA-graph capturable."""
+        for p in self.params:
+            p.grad = None
+        total.backward()
+        pieces = []
+        for p in self.params:
+            g = p.grad
+            if g is None:                                # unused in this phase (e.g. opacities once they are frozen)
+                if id(p) not in self._zeros:
+                    self._zeros[id(p)] = torch.zeros(p.numel(), dtype=self.flat.dtype, device=self.flat.device)
+                g = self._zeros[id(p)]
+            pieces.append(g.reshape(-1))
+        with torch.no_grad():
+            torch.cat(pieces, out=self.flat)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def all_reduce(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -83,9 +106,8 @@ class ViewParallel:
         self.model.n_total_views = n_total_views
         self._sync_rng(inp['imgs'].device)
         self._step += 1
-        self.bucket.zero_()
         losses = self.model(inp, labels)
-        self.weighted_total(losses, len(inp['imgs']), n_total_views).backward()
+        self.bucket.backward(self.weighted_total(losses, len(inp['imgs']), n_total_views))
         self.bucket.all_reduce(self.group)
         return losses
 

@@ -33,27 +33,36 @@ class _SceneGeometryFn(torch.autograd.Function):
         _lib.check(_lib.lib().dbw_scene_geometry_forward(ctypes.byref(g), _c(out), _stream()), 'dbw_scene_geometry_forward')
         ctx.save_for_backward(*args)
         ctx.static = static
-        return out
+        nb = static['n_blocks'] * static['verts_per_block']
+        # two outputs (views of the one buffer the kernel wrote): the blocks pass and the environment pass each take theirs,
+        # and the backward receives their gradients directly -- no slice-backward zero-fills / copies / adds
+        return out[:nb], out[nb:]
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_blocks, g_ground):
         args = ctx.saved_tensors
         g = _geom_struct(ctx.static, *args)
+        g_out = torch.cat([g_blocks.reshape(-1, 3).float(), g_ground.reshape(-1, 3).float()])
         # one zero-fill for all six gradients (views of a flat buffer) instead of six launches
         flat = torch.zeros(sum(t.numel() for t in args), device=g_out.device, dtype=torch.float32)
         grads, o = [], 0
         for t in args:
             grads.append(flat[o:o + t.numel()].view_as(t))
             o += t.numel()
-        _lib.check(_lib.lib().dbw_scene_geometry_backward(ctypes.byref(g), _c(g_out.contiguous().float()), *[_c(t) for t in grads],
+        _lib.check(_lib.lib().dbw_scene_geometry_backward(ctypes.byref(g), _c(g_out), *[_c(t) for t in grads],
                                                           _stream()), 'dbw_scene_geometry_backward')
         return (*grads, None)
+
+
+def scene_geometry_parts(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static):
+    """(block vertices (N*Vb, 3), ground vertices (Vg, 3)) in world space, from one kernel launch."""
+    return _SceneGeometryFn.apply(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static)
 
 
 def scene_geometry(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static):
     """World-space vertices (N*Vb + Vg, 3): the N superquadric blocks, then the ground plane.  `static` holds the
     buffers / constants of the scene template (see DifferentiableBlocksWorld._geometry_static)."""
-    return _SceneGeometryFn.apply(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static)
+    return torch.cat(_SceneGeometryFn.apply(sq_eps, S, R_6d, T, R_6d_ground, T_ground, static))
 
 
 class _TextureAtlasFn(torch.autograd.Function):
