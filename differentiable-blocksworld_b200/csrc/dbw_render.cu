@@ -560,9 +560,8 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
         if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
       }
     }
-#ifdef DBW_EXP_LISTSYNC
-    __syncthreads();
-#endif
+    // no barrier here: on the fast path nothing rewrites the list, and warps that finish early start shading (and hide
+    // the texel latency of the others); the chunked path synchronises at its call site before refilling the list
   };
 
   // ---- bin: which face slots of the view touch the tile?  Fast path: every batch of 256 slots is tested and compacted

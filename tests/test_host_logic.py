@@ -200,3 +200,27 @@ def test_view_parallel_gradients_equal_single_process_gloo():
     assert torch.allclose(out[0], out[1], atol=0)                 # every rank holds the same reduced gradient
     assert torch.allclose(out[0], ref, rtol=1e-5, atol=1e-6)
     assert vp.bucket.flat.data_ptr() == model.w.grad.data_ptr()   # grads are views into the single bucket
+
+
+def test_grad_bucket_backward_gathers_like_accumulation():
+    """GradBucket.backward (parameters enter the backward without .grad, ONE cat gathers the gradients into the flat
+    buffer) == zero the bucket + autograd's accumulate-adds; parameters the loss does not reach read as zero; the .grad
+    attributes are the bucket views again afterwards, and a second step does not accumulate onto the first."""
+    from dbw_b200.parallel import GradBucket
+    torch.manual_seed(3)
+    a, b, unused = (torch.nn.Parameter(torch.randn(s)) for s in ((4, 3), (5,), (2, 2)))
+    loss_fn = lambda: (a.sin().sum() * b.pow(2).sum() + (a[:, 0] * b[:4]).sum())
+    bucket = GradBucket([a, b, unused])
+    bucket.backward(loss_fn())
+    got = bucket.flat.clone()
+    ga, gb = torch.autograd.grad(loss_fn(), [a, b])
+    ref = torch.cat([ga.reshape(-1), gb.reshape(-1), torch.zeros(4)])
+    assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
+    for p in (a, b, unused):
+        assert p.grad is not None and p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr()
+    assert torch.equal(a.grad, ga) and torch.equal(unused.grad, torch.zeros(2, 2))
+    bucket.backward(2 * loss_fn())                                   # overwrites, does not accumulate
+    assert torch.allclose(bucket.flat, 2 * ref, rtol=1e-6, atol=1e-7)
+    bucket.zero_()                                                   # the classic path still works on the same views
+    loss_fn().backward()
+    assert torch.allclose(bucket.flat, ref, rtol=1e-6, atol=1e-7)
