@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
 from .fused_loss import ScenePass, scene_mse
-from .scene_ops import scene_geometry, scene_geometry_parts, texture_atlas
+from .scene_ops import scene_geometry_parts, texture_atlas
 from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
 # accepted keys and defaults of the config sub-dicts (configs/*/*.yml -> model.{mesh,rend_optim,loss}); unknown keys are
