@@ -53,6 +53,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// reciprocal of the CONTINUOUS normalisations (perspective correction, barycentric clipping): the 1-ulp MUFU
+// approximation -- together with -prec-div=false (Makefile) worth 3.5 % of the step on B200.  Everything a discrete decision
+// depends on (edge functions, pixel coordinates) uses the explicitly rounded intrinsics (__fmul_rn, __fdiv_rn, ...) and is
+// not affected by either.  -DDBW_PRECISE_RCP restores the correctly rounded reciprocal.
+#ifdef DBW_PRECISE_RCP
+#define DBW_RCP(x) __frcp_rn(x)
+#else
+#define DBW_RCP(x) __fdividef(1.f, (x))
+#endif
+
 struct TriGeom {
   f2 v0, v1, v2;
   float z0, z1, z2;
@@ -95,14 +105,14 @@ __device__ __forceinline__ Edges eval_edges(f2 p, const TriGeom& t) {
 
 __device__ __forceinline__ f3 persp_forward(f3 b, float z0, float z1, float z2) {
   const float t0 = b.x * z1 * z2, t1 = z0 * b.y * z2, t2 = z0 * z1 * b.z;
-  const float inv = __frcp_rn(fmaxf(t0 + t1 + t2, DBW_KEPS));     // correctly rounded reciprocal, no slow-path division
+  const float inv = DBW_RCP(fmaxf(t0 + t1 + t2, DBW_KEPS));     // one reciprocal, no slow-path division
   return {t0 * inv, t1 * inv, t2 * inv};
 }
 
 __device__ __forceinline__ f3 clip_forward(f3 b) {
   f3 w = {fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f)};
   const float sum = fmaxf(w.x + w.y + w.z, 1e-5f);
-  const float inv = __frcp_rn(sum);
+  const float inv = DBW_RCP(sum);
   // Beyond a vertex two barycentrics are negative, the third is renormalised to EXACTLY 1 by a true division, and
   // every face sharing that vertex then ties at pz = z_vertex (broken by face index).  w * (1/w) is not
   // always 1, so keep that case exact; elsewhere one reciprocal replaces three divisions.
