@@ -68,3 +68,31 @@ def test_renderer_refuses_cpu_tensors():
     with pytest.raises(DbwError):
         render_scene(v, torch.zeros(1, 3, dtype=torch.int32), torch.zeros(1, 3, 2), torch.zeros(1, dtype=torch.int32),
                      torch.zeros(12), [(0, 2, 2)], torch.eye(3)[None], torch.zeros(1, 3), (1, 1, 0, 0), (8, 8), 1e-4, 4)
+
+
+def test_ctypes_mirrors_have_the_layout_the_c_compiler_gives_the_header(tmp_path):
+    """every struct of include/dbw_render.h: size and field offsets as gcc lays them out == the ctypes mirrors in _lib.py
+    (the header is plain C: it must also compile as C, not only as CUDA C++)"""
+    import shutil
+    import subprocess
+    from dbw_b200 import _lib
+    gcc = '/usr/bin/gcc' if os.path.exists('/usr/bin/gcc') else shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('no C compiler')
+    structs = {'DbwRenderSettings': _lib.DbwRenderSettings, 'DbwMapDesc': _lib.DbwMapDesc,
+               'DbwSceneGeometry': _lib.DbwSceneGeometry, 'DbwLossEpilogue': _lib.DbwLossEpilogue}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dbw_render.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'layout'
+    subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(got[name]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(got[f'{name}.{field}']) == getattr(cls, field).offset, f'{name}.{field}'
