@@ -224,3 +224,29 @@ def test_grad_bucket_backward_gathers_like_accumulation():
     bucket.zero_()                                                   # the classic path still works on the same views
     loss_fn().backward()
     assert torch.allclose(bucket.flat, ref, rtol=1e-6, atol=1e-7)
+
+
+def test_scene_settings_of_a_render_pass():
+    """host-side bookkeeping of one pass (no kernel runs): per-face vs per-view-and-face opacity strides, texel-atlas map
+    sizes, the blur radius of renderer.py:51, and the saved-fragment-state switch following grad mode."""
+    import numpy as np
+    from dbw_b200.renderer import scene_settings
+    from dbw_b200._lib import DbwError
+    V, F, B = 12, 20, 3
+    verts, faces = torch.zeros(V, 3), torch.zeros(F, 3, dtype=torch.int32)
+    atlas = torch.zeros(2 * 8 * 8, 4)                                  # two 8x8 float4 maps
+    table = [(0, 8, 8), (8 * 8 * 3, 8, 8)]
+    intr = (2.0, 2.0, 0.0, 0.0)
+    cfg, dev_table = scene_settings(verts, faces, atlas, table, B, intr, (16, 24), 1e-4, 10, 0.001, detach_bary=True,
+                                    faces_alpha=torch.ones(F), maps_are_texels4=True)
+    assert (cfg.n_views, cfg.height, cfg.width, cfg.faces_per_pixel, cfg.n_verts, cfg.n_faces, cfg.n_maps) == (B, 16, 24, 10, V, F, 2)
+    assert cfg.alpha_view_stride == 0 and cfg.maps_are_texels4 == 1 and cfg.n_map_floats == 2 * 8 * 8 * 3
+    assert abs(cfg.blur_radius - np.log(1. / 1e-4 - 1.) * 1e-4) < 1e-9 and abs(cfg.z_clip - 0.001) < 1e-9
+    assert cfg.save_fragment_state == 1                                # detach_bary pass, grad mode on
+    assert dev_table.reshape(-1, 4)[:, :3].tolist() == [[0, 8, 8], [192, 8, 8]]
+    with torch.no_grad():
+        cfg2, _ = scene_settings(verts, faces, atlas, table, B, intr, (16, 24), 1e-4, 10, None, detach_bary=True,
+                                 faces_alpha=torch.ones(B * F), maps_are_texels4=True)
+    assert cfg2.save_fragment_state == 0 and cfg2.alpha_view_stride == F and cfg2.z_clip == -1.0
+    with pytest.raises(DbwError):
+        scene_settings(verts, faces, atlas, table, B, intr, (16, 24), 1e-4, 10, faces_alpha=torch.ones(F + 1))
