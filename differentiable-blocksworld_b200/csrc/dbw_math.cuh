@@ -4,8 +4,12 @@
 // reference's MeshRasterizer executes (src/model/renderer.py:50-54).  Arithmetic that feeds a DISCRETE decision
 // (edge-function signs -> inside test, pixel NDC coordinates) is written with non-contracting intrinsics so that it
 // is bit-identical to an IEEE-754 evaluation without FMA; everything else may be contracted by the compiler.
+// The header also compiles as plain C++ (tests/host_math: the same functions checked against the oracle on the CPU);
+// the parts that only exist on the device (PTX: TMA, mbarrier, vector RED) are fenced with __CUDACC__.
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define DBW_KEPS 1e-8f
@@ -26,6 +30,7 @@ __device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
   return __fadd_rn(-offset, __fdiv_rn(__fadd_rn(__fmul_rn(range, (float)i), offset), (float)S1));
 }
 
+#ifdef __CUDACC__
 // ------------------------------------------------------------------ TMA (bulk async copy) + mbarrier helpers (sm_90+)
 // The per-tile face records are gathered global -> shared with cp.async.bulk (SASS: UBLKCP), one 64 B bulk copy per listed
 // face, all completing on one shared-memory mbarrier (complete_tx::bytes) -- no register staging, no LDG/STS pairs.
@@ -52,6 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+#endif  // __CUDACC__
 
 // reciprocal of the CONTINUOUS normalisations (perspective correction, barycentric clipping): the 1-ulp MUFU
 // approximation -- together with -prec-div=false (Makefile) worth 3.5 % of the step on B200.  Everything a discrete decision
@@ -258,7 +264,9 @@ __device__ __forceinline__ f3 ld_texel(const float4* __restrict__ m, int i) {
   return {t.x, t.y, t.z};
 }
 
+#ifdef __CUDACC__
 // vector reduction: one RED.128 per tap instead of three RED.32 (sm_90+)
 __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }
+#endif  // __CUDACC__

@@ -1,0 +1,135 @@
+"""CPU: the DEVICE math of the rasterization kernels (differentiable-blocksworld_b200/csrc/dbw_math.cuh) compiled for the
+host (tests/host_math/dbw_math_host.cpp, g++ -ffp-contract=off) and checked against the oracle: the per-(pixel, face)
+candidate test, barycentrics / depth / signed distance, their backward pieces, and the bilinear texture tap.  The CUDA
+kernels inline exactly these functions, so a regression in the math shows up here without a GPU; the kernels' own
+orchestration (binning, top-K, atomics, blending) is covered by the `-m gpu` parity tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import pt3d
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'host_math', 'dbw_math_host.cpp')
+BLUR = float(np.log(1. / 1e-4 - 1.) * 1e-4)        # renderer.py:51 at sigma = 1e-4
+
+
+@pytest.fixture(scope='module')
+def hm():
+    out_dir = os.path.join(HERE, 'host_math', '_build')
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, 'libdbw_math_host.so')
+    gxx = '/usr/bin/g++' if os.path.exists('/usr/bin/g++') else 'g++'
+    subprocess.run([gxx, '-O2', '-ffp-contract=off', '-std=c++17', '-fPIC', '-shared', '-Wall', '-Werror', SRC, '-o', so], check=True)
+    return ctypes.CDLL(so)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _triangles(seed, n):
+    """random screen-space triangles (NDC x, NDC y, view z): big, small, slivers, partly off-screen, both windings"""
+    g = np.random.default_rng(seed)
+    tris = []
+    for i in range(n):
+        c = g.uniform(-1.1, 1.1, 2)
+        r = [0.9, 0.3, 0.08][i % 3]
+        xy = c + g.uniform(-r, r, (3, 2))
+        if i % 5 == 4:                               # sliver
+            xy[2] = xy[0] + (xy[1] - xy[0]) * g.uniform(0.2, 0.8) + g.uniform(-2e-3, 2e-3, 2)
+        z = g.uniform(0.5, 6.0, 3)
+        tris.append(np.concatenate([xy, z[:, None]], 1).astype(np.float32))
+    return tris
+
+
+def _oracle(fv, H, W, blur, persp, clipb, dtype):
+    t = torch.from_numpy(fv.astype(np.float64)).to(dtype)[None].clone().requires_grad_(True)
+    p2f, zbuf, bary, dists = pt3d._RasterizeFaceVerts.apply(t, torch.zeros(1, dtype=torch.long), torch.ones(1, dtype=torch.long),
+                                                            None, (H, W), blur, 1, persp, clipb, False)
+    return t, p2f[0, ..., 0], zbuf[0, ..., 0], bary[0, ..., 0, :], dists[0, ..., 0]
+
+
+def _device(hm, fv, H, W, blur, persp, clipb):
+    hit = np.zeros((H, W), np.int32)
+    zbuf, dists, bary = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32), np.zeros((H, W, 3), np.float32)
+    hm.hm_forward(_p(np.ascontiguousarray(fv)), H, W, ctypes.c_float(blur), int(persp), int(clipb), _p(hit), _p(zbuf), _p(bary), _p(dists))
+    return hit, zbuf, bary, dists
+
+
+@pytest.mark.parametrize('persp,clipb', [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize('blur', [BLUR, 0.0])
+def test_candidate_test_and_fragment_values_match_the_oracle(hm, persp, clipb, blur):
+    H, W = 24, 40
+    n_px = n_flip = 0
+    for i, fv in enumerate(_triangles(11, 30)):
+        hit, zbuf, bary, dists = _device(hm, fv, H, W, blur, persp, clipb)
+        _, p2f32, z32, b32, d32 = (x.detach() for x in _oracle(fv, H, W, blur, persp, clipb, torch.float32))
+        _, p2f, z64, b64, d64 = (x.detach() for x in _oracle(fv, H, W, blur, persp, clipb, torch.float64))
+        ref32 = (p2f32 >= 0).numpy()
+        # discrete decisions: identical to the fp32 oracle except where `dist >= blur` is decided by the last bit (the
+        # device multiplies by reciprocals where the oracle divides)
+        flips = hit.astype(bool) != ref32
+        n_px += H * W; n_flip += int(flips.sum())
+        if blur == 0.0:                       # the inside test itself is exact: no flips at all without a halo
+            assert not flips.any()
+        sliver = i % 5 == 4
+        # continuous values: against the fp64 oracle for well-conditioned triangles; slivers (area ~ 1e-3 of the squared
+        # edge length) amplify fp32 rounding by that ratio, so they are compared with the fp32 oracle, loosely
+        both = hit.astype(bool) & (p2f >= 0).numpy() & ref32
+        rz, rb, rd = (z32, b32, d32) if sliver else (z64, b64, d64)
+        tol = 2e-3 if sliver else 2e-5
+        for got, ref, name in ((zbuf, rz, 'zbuf'), (dists, rd, 'dists')):
+            err = np.abs(got[both] - ref.numpy()[both])
+            assert (err <= tol * (0.1 + np.abs(ref.numpy()[both]))).all(), (name, i, err.max(initial=0))
+        rbn = rb.numpy()[both]
+        assert (np.abs(bary[both] - rbn) <= tol * (1 + np.abs(rbn))).all(), i     # unclipped barycentrics are unbounded
+    assert n_flip <= 2e-4 * n_px, (n_flip, n_px)
+
+
+def test_backward_pieces_match_the_oracle(hm):
+    H, W = 24, 40
+    g = np.random.default_rng(5)
+    checked = 0
+    for fv in _triangles(23, 24):
+        hit, *_ = _device(hm, fv, H, W, BLUR, True, True)
+        t, p2f, zbuf, bary, dists = _oracle(fv, H, W, BLUR, True, True, torch.float64)
+        both = hit.astype(bool) & (p2f >= 0).numpy()
+        if both.sum() < 4:
+            continue
+        gz = (g.standard_normal((H, W)) * both).astype(np.float32)
+        gb = (g.standard_normal((H, W, 3)) * both[..., None]).astype(np.float32)
+        gd = (g.standard_normal((H, W)) * both * 50).astype(np.float32)
+        got = np.zeros(9, np.float32)
+        hm.hm_backward(_p(np.ascontiguousarray(fv)), H, W, 1, 1, _p(both.astype(np.int32)), _p(gz), _p(gb), _p(gd), _p(got))
+        loss = (zbuf * torch.from_numpy(gz).double()).sum() + (bary * torch.from_numpy(gb).double()).sum() \
+            + (dists * torch.from_numpy(gd).double()).sum()
+        loss.backward()
+        ref = t.grad[0].reshape(-1).numpy()
+        rel = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-12)
+        assert rel < 2e-3, (rel, got, ref)
+        checked += 1
+    assert checked >= 10
+
+
+def test_bilinear_tap_matches_grid_sample(hm):
+    """tex_tap == TexturesUV.sample_textures: grid = 2 uv - 1 on the H-flipped map, bilinear, align_corners=True, border"""
+    g = torch.Generator().manual_seed(3)
+    for Hm, Wm in ((8, 8), (5, 13)):
+        tex = torch.rand(Hm, Wm, 3, generator=g, dtype=torch.float64)
+        uv = torch.rand(200, 2, generator=g, dtype=torch.float64) * 1.3 - 0.15          # some taps beyond the border
+        uv.requires_grad_(True)
+        grid = (uv * 2 - 1)[None, None]
+        out = F.grid_sample(tex.flip(0).permute(2, 0, 1)[None], grid, mode='bilinear', align_corners=True, padding_mode='border')[0, :, 0].t()
+        jac = torch.stack([torch.autograd.grad(out[:, c].sum(), uv, retain_graph=True)[0] for c in range(3)], 1)   # (n, 3, 2)
+        m = np.ascontiguousarray(tex.numpy().astype(np.float32))
+        for i in range(uv.shape[0]):
+            rgb, du, dv = (np.zeros(3, np.float32) for _ in range(3))
+            hm.hm_sample(_p(m), Hm, Wm, ctypes.c_float(float(uv[i, 0].detach())), ctypes.c_float(float(uv[i, 1].detach())), _p(rgb), _p(du), _p(dv))
+            assert np.abs(rgb - out[i].detach().numpy()).max() < 2e-5
+            assert np.abs(du - jac[i, :, 0].numpy()).max() < 2e-3 and np.abs(dv - jac[i, :, 1].numpy()).max() < 2e-3
