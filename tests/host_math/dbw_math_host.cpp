@@ -24,6 +24,7 @@ static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f
 static inline float4 __ldg(const float4* p) { return *p; }
 
 #include "../../differentiable-blocksworld_b200/csrc/dbw_math.cuh"
+#include "../../differentiable-blocksworld_b200/csrc/dbw_clip.cuh"
 
 // record of one triangle as face_setup's write_slot packs it (dbw_render.cu, write_slot): reciprocal of the eps-shifted area
 // and of the squared edge lengths (-1 = degenerate edge)
@@ -107,6 +108,23 @@ void hm_sample(const float* map, int H, int W, float u, float v, float* rgb, flo
     const float gix = (c[1][ch] - c[0][ch]) * ey + (c[3][ch] - c[2][ch]) * wy;      // as raster_backward_kernel's barycentric path
     const float giy = (c[2][ch] - c[0][ch]) * ex + (c[3][ch] - c[1][ch]) * wx;
     d_du[ch] = gix * t.mx; d_dv[ch] = giy * t.my;
+  }
+}
+
+// z-clip of n faces (fv: n x 9 floats) as face_setup_kernel does it: per face the number of triangles (0/1/2), their vertices
+// (n x 2 x 9) and the barycentric conversion matrices (n x 2 x 9, identity for an untouched face)
+void hm_clip(const float* fv, int n, float z_clip, int persp, int* ntri, float* tri, float* conv) {
+  for (int f = 0; f < n; ++f) {
+    float a[3][3];
+    for (int i = 0; i < 3; ++i) for (int c = 0; c < 3; ++c) a[i][c] = fv[f * 9 + i * 3 + c];
+    ClipResult r;
+    clip_face(a, z_clip, persp != 0, r);
+    ntri[f] = r.ntri;
+    for (int k = 0; k < 2; ++k)
+      for (int i = 0; i < 9; ++i) {
+        tri[(f * 2 + k) * 9 + i] = k < r.ntri ? r.tri[k][i] : 0.f;
+        conv[(f * 2 + k) * 9 + i] = k < r.ntri ? (r.clipped ? r.conv[k][i] : (i % 4 == 0 ? 1.f : 0.f)) : 0.f;
+      }
   }
 }
 
