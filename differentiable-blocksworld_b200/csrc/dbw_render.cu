@@ -339,9 +339,7 @@ struct RasterParams {
 #define DBW_AGG_MIN 2         // groups of at most this many lanes use plain atomics instead of a warp reduction
 #endif
 
-__device__ __forceinline__ unsigned long long make_key(float pz, int slot) {
-  return ((unsigned long long)__float_as_uint(pz + 0.f) << 32) | (unsigned)slot;
-}
+#include "dbw_topk.cuh"
 
 // opacity of one fragment from its signed squared distance (layered_rgb_blend, src/model/renderer.py:252-257)
 __device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_inside) {
@@ -473,32 +471,7 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
         if (b.pz < 0.f) continue;
         const float sd = b.inside ? -dist : dist;
         const int slot = s_slot[j];
-        if (t.neighbor >= 0) {
-          // the other half of a z-clipped quad: only the half with the smaller |dist| may stay (A3).  Every index below is a
-          // compile-time constant of a fully unrolled loop, so that key[] / dk[] stay in registers.
-          int found = -1; float d_found = 0.f;
-#pragma unroll
-          for (int k = 0; k < K; ++k)
-            if ((int)(unsigned)key[k] == t.neighbor && key[k] != ~0ull) { found = k; d_found = dk[k]; }
-          if (found >= 0) {
-            if (dist < fabsf(d_found)) {
-#pragma unroll
-              for (int q = 0; q < K - 1; ++q) if (q >= found) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
-              key[K - 1] = ~0ull; dk[K - 1] = 0.f;
-            } else continue;
-          }
-        }
-        const unsigned long long nk = make_key(b.pz, slot);
-        if (nk >= key[K - 1]) continue;
-        // sorted insertion with static indexing
-#pragma unroll
-        for (int k = K - 1; k >= 1; --k) {
-          const bool up = nk < key[k - 1];
-          const bool here = !up && nk < key[k];
-          key[k] = up ? key[k - 1] : (here ? nk : key[k]);
-          dk[k] = up ? dk[k - 1] : (here ? sd : dk[k]);
-        }
-        if (nk < key[0]) { key[0] = nk; dk[0] = sd; }
+        topk_offer<K>(key, dk, b.pz, slot, sd, dist, t.neighbor);
       }
     }
     // no barrier here: on the fast path nothing rewrites the list, and warps that finish early start shading (and hide

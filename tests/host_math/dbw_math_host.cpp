@@ -20,11 +20,13 @@ static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline float4 __ldg(const float4* p) { return *p; }
 
 #include "../../differentiable-blocksworld_b200/csrc/dbw_math.cuh"
 #include "../../differentiable-blocksworld_b200/csrc/dbw_clip.cuh"
+#include "../../differentiable-blocksworld_b200/csrc/dbw_topk.cuh"
 
 // record of one triangle as face_setup's write_slot packs it (dbw_render.cu, write_slot): reciprocal of the eps-shifted area
 // and of the squared edge lengths (-1 = degenerate edge)
@@ -128,4 +130,26 @@ void hm_clip(const float* fv, int n, float z_clip, int persp, int* ntri, float* 
   }
 }
 
+}  // extern "C"
+
+template <int K>
+static void run_topk(int n, const float* pz, const int* slot, const float* sd, const int* neighbor, int* out_slot, float* out_sd) {
+  unsigned long long key[K];
+  float dk[K];
+  for (int k = 0; k < K; ++k) { key[k] = ~0ull; dk[k] = 0.f; }
+  for (int i = 0; i < n; ++i) topk_offer<K>(key, dk, pz[i], slot[i], sd[i], fabsf(sd[i]), neighbor[i]);
+  for (int k = 0; k < K; ++k) { out_slot[k] = key[k] != ~0ull ? (int)(unsigned)key[k] : -1; out_sd[k] = dk[k]; }
+}
+
+extern "C" {
+// a stream of n candidates of one pixel offered to the register top-K of raster_forward_kernel<K>; K in {1, 4, 10, 25}
+int hm_topk(int K, int n, const float* pz, const int* slot, const float* sd, const int* neighbor, int* out_slot, float* out_sd) {
+  switch (K) {
+    case 1: run_topk<1>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
+    case 4: run_topk<4>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
+    case 10: run_topk<10>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
+    case 25: run_topk<25>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
+  }
+  return -1;
+}
 }  // extern "C"

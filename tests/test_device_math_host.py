@@ -160,3 +160,49 @@ def test_z_clip_of_faces_matches_the_oracle(hm, persp):
             assert np.abs(conv[f, k] - ref.conversion[c].numpy()).max() < 1e-5, (f, k)
         if ntri[f] == 2:
             assert int(ref.neighbor[u2c[f]]) == u2c[f] + 1 and int(ref.neighbor[u2c[f] + 1]) == u2c[f]
+
+
+def _oracle_queue(K, cands):
+    """the per-pixel queue of oracle/raster_oracle.c (RasterizeMeshesNaiveCpu + the clipped-quad rule of clip.py):
+    tuples ordered by (depth, face, distance); a half of a z-clipped quad evicts / yields to its other half by |distance|"""
+    q = []
+    for z, f, d, nb in cands:
+        handled = False
+        if nb >= 0:
+            for i, (_, qf, qd) in enumerate(q):
+                if qf == nb:
+                    if abs(d) < abs(qd):
+                        q.pop(i)
+                    else:
+                        handled = True
+                    break
+        if handled:
+            continue
+        q.append((z, f, d))
+        q.sort()
+        del q[K:]
+    return q
+
+
+@pytest.mark.parametrize('K', [1, 4, 10, 25])
+def test_register_top_k_matches_the_oracle_queue(hm, K):
+    """topk_offer (dbw_topk.cuh): ordering by (depth, slot) incl. exact depth ties, overflow beyond K, and the mutual
+    exclusion of the two halves of a z-clipped quad, against the oracle's queue on random candidate streams"""
+    g = np.random.default_rng(K)
+    for trial in range(300):
+        n = int(g.integers(0, 3 * K + 4))
+        slots = g.permutation(200)[:n].astype(np.int32)
+        pz = g.choice(np.float32([0.5, 0.75, 1.0, 1.5, 2.0, 3.0]), n) if trial % 3 == 0 else g.uniform(0.1, 5.0, n).astype(np.float32)
+        sd = (g.uniform(1e-6, 9e-4, n) * g.choice([-1.0, 1.0], n)).astype(np.float32)
+        nb = np.full(n, -1, np.int32)
+        for i in range(0, n - 1, 5):                       # some consecutive candidates are the two halves of a quad
+            if g.random() < 0.6:
+                nb[i], nb[i + 1] = slots[i + 1], slots[i]
+                if g.random() < 0.5:
+                    pz[i + 1] = pz[i]
+        pz = np.ascontiguousarray(pz, np.float32)
+        out_slot, out_sd = np.zeros(K, np.int32), np.zeros(K, np.float32)
+        assert hm.hm_topk(K, n, _p(pz), _p(slots), _p(sd), _p(nb), _p(out_slot), _p(out_sd)) == 0
+        ref = _oracle_queue(K, [(float(pz[i]), int(slots[i]), float(sd[i]), int(nb[i])) for i in range(n)])
+        got = [(int(s), float(d)) for s, d in zip(out_slot, out_sd) if s >= 0]
+        assert got == [(f, d) for _, f, d in ref], (trial, got, ref)
