@@ -27,6 +27,7 @@ static inline float4 __ldg(const float4* p) { return *p; }
 #include "../../differentiable-blocksworld_b200/csrc/dbw_math.cuh"
 #include "../../differentiable-blocksworld_b200/csrc/dbw_clip.cuh"
 #include "../../differentiable-blocksworld_b200/csrc/dbw_topk.cuh"
+#include "../../differentiable-blocksworld_b200/csrc/dbw_scene_math.cuh"
 
 // record of one triangle as face_setup's write_slot packs it (dbw_render.cu, write_slot): reciprocal of the eps-shifted area
 // and of the squared edge lengths (-1 = degenerate edge)
@@ -151,5 +152,21 @@ int hm_topk(int K, int n, const float* pz, const int* slot, const float* sd, con
     case 25: run_topk<25>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
   }
   return -1;
+}
+}  // extern "C"
+
+extern "C" {
+// rotation_6d_to_matrix and its backward (dbw_scene_math.cuh), n rotations
+void hm_rot6d(const float* d6, int n, float* R) { for (int i = 0; i < n; ++i) rot6d(d6 + i * 6, R + i * 9); }
+void hm_rot6d_backward(const float* d6, const float* gR, int n, float* gd6) {
+  for (int i = 0; i < n; ++i) rot6d_backward(d6 + i * 6, gR + i * 9, gd6 + i * 6);
+}
+// unit-scale superquadric vertices of N blocks x Vb vertices (local_vertex): out (N, Vb, 3), aux (N, Vb, 6)
+void hm_superquadric(const float* sq_eta, const float* sq_omega, const float* sq_eps, int N, int Vb, float ratio, float* out, float* aux) {
+  GeomParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_blocks = N; P.verts_per_block = Vb; P.sq_eta = sq_eta; P.sq_omega = sq_omega; P.sq_eps = sq_eps; P.ratio = ratio;
+  for (int b = 0; b < N; ++b)
+    for (int v = 0; v < Vb; ++v) local_vertex(P, b, v, out + (b * Vb + v) * 3, aux + (b * Vb + v) * 6);
 }
 }  // extern "C"

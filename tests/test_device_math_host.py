@@ -206,3 +206,34 @@ def test_register_top_k_matches_the_oracle_queue(hm, K):
         ref = _oracle_queue(K, [(float(pz[i]), int(slots[i]), float(sd[i]), int(nb[i])) for i in range(n)])
         got = [(int(s), float(d)) for s, d in zip(out_slot, out_sd) if s >= 0]
         assert got == [(f, d) for _, f, d in ref], (trial, got, ref)
+
+
+def test_scene_vertex_math_matches_torch(hm):
+    """dbw_scene_math.cuh (the per-vertex code of the fused scene-geometry kernels): 6D rotation forward / backward against
+    rotation_6d_to_matrix + autograd, the parametric superquadric against the oracle's restatement of superquadric.py:10-14"""
+    from oracle import dbw_path as D
+    g = torch.Generator().manual_seed(4)
+    n = 64
+    d6 = torch.randn(n, 6, generator=g, dtype=torch.float64, requires_grad=True)
+    R_ref = pt3d.rotation_6d_to_matrix(d6)
+    gR = torch.randn(n, 3, 3, generator=g, dtype=torch.float64)
+    (R_ref * gR).sum().backward()
+    d6f = np.ascontiguousarray(d6.detach().numpy().astype(np.float32))
+    R, gd6 = np.zeros((n, 9), np.float32), np.zeros((n, 6), np.float32)
+    hm.hm_rot6d(_p(d6f), n, _p(R))
+    hm.hm_rot6d_backward(_p(d6f), _p(np.ascontiguousarray(gR.numpy().astype(np.float32).reshape(n, 9))), n, _p(gd6))
+    assert np.abs(R.reshape(n, 3, 3) - R_ref.detach().numpy()).max() < 1e-5
+    ref_g = d6.grad.numpy()
+    assert np.abs(gd6 - ref_g).max() <= 1e-4 * max(1.0, np.abs(ref_g).max())
+    # superquadric vertices on the icosphere's (eta, omega) of the scene template
+    tpl = D.SceneTemplate(n_blocks=3, txt_size=8)
+    eta, omega = tpl.sq_eta.double(), tpl.sq_omega.double()
+    raw = torch.tensor([[-2.0, 0.3], [0.0, 0.0], [1.5, -0.7]], dtype=torch.float64)
+    eps = torch.sigmoid(raw) * 1.8 + 0.1                                  # dbw.py:349
+    ref = D.parametric_sq(eta, omega, eps[:, :1], eps[:, 1:]) * 0.25
+    N, Vb = eta.shape
+    out, aux = np.zeros((N, Vb, 3), np.float32), np.zeros((N, Vb, 6), np.float32)
+    hm.hm_superquadric(_p(np.ascontiguousarray(eta.numpy().astype(np.float32))), _p(np.ascontiguousarray(omega.numpy().astype(np.float32))),
+                       _p(np.ascontiguousarray(raw.numpy().astype(np.float32))), N, Vb, ctypes.c_float(0.25), _p(out), _p(aux))
+    assert np.abs(out - ref.numpy()).max() < 1e-5
+    assert np.abs(aux[:, 0, 4:] - eps.numpy()).max() < 1e-6
