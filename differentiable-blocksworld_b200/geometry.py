@@ -94,6 +94,47 @@ def unit_plane():
     return verts, faces
 
 
+def load_obj(path):
+    """(verts (V,3) float32, faces (F,3) int64) of a Wavefront OBJ: `v x y z` and `f a[/t[/n]] b.. c..` records, polygons
+    fan-triangulated -- what the reference reads its primitives with (load_objs_as_meshes(load_textures=False),
+    src/utils/mesh.py:173,211)."""
+    verts, faces = [], []
+    with open(path) as fh:
+        for line in fh:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == 'v':
+                verts.append([float(t) for t in tok[1:4]])
+            elif tok[0] == 'f':
+                idx = [int(t.split('/')[0]) for t in tok[1:]]
+                idx = [i - 1 if i > 0 else len(verts) + i for i in idx]
+                faces += [[idx[0], idx[k], idx[k + 1]] for k in range(1, len(idx) - 1)]
+    return torch.tensor(verts, dtype=torch.float32), torch.tensor(faces, dtype=torch.long)
+
+
+def unit_cube():
+    """primitives/cube.obj of the reference (src/utils/mesh.py:172-173): the cube [-1,1]^3, 8 vertices, 12 triangles, in
+    the file's vertex / face order (bottom, top, +x, +z, -x, -z; first triangles of the six quads, then the second ones)."""
+    verts = torch.tensor([[1., -1., -1.], [1., -1., 1.], [-1., -1., 1.], [-1., -1., -1.],
+                          [1., 1., -1.], [1., 1., 1.], [-1., 1., 1.], [-1., 1., -1.]])
+    faces = torch.tensor([[1, 3, 0], [7, 5, 4], [4, 1, 0], [5, 2, 1], [2, 7, 3], [0, 7, 4],
+                          [1, 2, 3], [7, 6, 5], [4, 5, 1], [5, 6, 2], [2, 6, 7], [0, 3, 7]], dtype=torch.long)
+    return verts, faces
+
+
+def cube_uvs():
+    """(faces_uvs (12,3), verts_uvs (14,2)) of the cube primitive (src/utils/mesh.py:176-207): the six faces unfolded as a
+    cross in a 4x8 grid of the unit square (four side quads in a row at v in [3/8, 5/8], top and bottom above / below the
+    second one)."""
+    q, e = 1 / 4, 1 / 8
+    verts_uvs = torch.tensor([[0, 3 * e], [0, 5 * e], [q, 5 * e], [q, 3 * e], [3 * q, 3 * e], [3 * q, 5 * e], [2 * q, 5 * e],
+                              [2 * q, 3 * e], [1, 3 * e], [1, 5 * e], [q, 7 * e], [2 * q, 7 * e], [q, e], [2 * q, e]], dtype=torch.float32)
+    faces_uvs = torch.tensor([[1, 3, 0], [7, 5, 4], [4, 9, 8], [11, 2, 10], [2, 7, 3], [12, 7, 13],
+                              [1, 2, 3], [7, 6, 5], [4, 5, 9], [11, 6, 2], [2, 6, 7], [12, 3, 7]], dtype=torch.long)
+    return faces_uvs, verts_uvs
+
+
 def _rot(axis, deg):
     a = math.radians(float(deg))
     R = torch.eye(3)

@@ -125,6 +125,40 @@ def get_plane():
     return verts, faces
 
 
+def get_cube():
+    """src/utils/mesh.py:172-173 (load_objs_as_meshes of primitives/cube.obj): 8 vertices of [-1,1]^3 and 12 triangles in
+    the file's order; pinned against the file itself in tests/test_oracle_golden.py."""
+    verts = torch.tensor([[1, -1, -1], [1, -1, 1], [-1, -1, 1], [-1, -1, -1], [1, 1, -1], [1, 1, 1], [-1, 1, 1], [-1, 1, -1]],
+                         dtype=torch.float32)
+    faces = torch.tensor([[1, 3, 0], [7, 5, 4], [4, 1, 0], [5, 2, 1], [2, 7, 3], [0, 7, 4], [1, 2, 3], [7, 6, 5], [4, 5, 1],
+                          [5, 6, 2], [2, 6, 7], [0, 3, 7]], dtype=torch.long)
+    return verts, faces
+
+
+def get_cube_uvs():
+    """src/utils/mesh.py:176-207: the unfolded-cross UV layout of the cube primitive."""
+    faces_uvs = torch.tensor([[1, 3, 0], [7, 5, 4], [4, 9, 8], [11, 2, 10], [2, 7, 3], [12, 7, 13], [1, 2, 3], [7, 6, 5], [4, 5, 9],
+                              [11, 6, 2], [2, 6, 7], [12, 3, 7]], dtype=torch.long)
+    verts_uvs = torch.tensor([[0., 3 / 8], [0., 5 / 8], [1 / 4, 5 / 8], [1 / 4, 3 / 8], [3 / 4, 3 / 8], [3 / 4, 5 / 8], [2 / 4, 5 / 8],
+                              [2 / 4, 3 / 8], [1., 3 / 8], [1., 5 / 8], [1 / 4, 7 / 8], [2 / 4, 7 / 8], [1 / 4, 1 / 8], [2 / 4, 1 / 8]],
+                             dtype=torch.float32)
+    return faces_uvs, verts_uvs
+
+
+def cube_scene(texture, scale=0.5, R=None, T=None):
+    """BASELINE configs[0]: ONE cube primitive with a (Ht,Wt,3) texture map in [0,1], posed by (v * scale) @ R + T."""
+    verts, faces = get_cube()
+    dt = texture.dtype
+    verts = verts.to(dt) * scale
+    if R is not None:
+        verts = verts @ R.to(dt)
+    if T is not None:
+        verts = verts + T.to(dt)
+    faces_uvs, verts_uvs = get_cube_uvs()
+    return {'verts': verts, 'faces': faces, 'faces_verts_uvs': verts_uvs.to(dt)[faces_uvs],
+            'face_map': torch.zeros(len(faces), dtype=torch.long), 'maps': [texture]}
+
+
 # ------------------------------------------------------------------ renderer (renderer.py)
 
 def blur_radius_from_sigma(sigma):

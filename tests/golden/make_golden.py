@@ -3,6 +3,8 @@
   ref_functions.npz   outputs of the REFERENCE'S OWN pure-torch functions on seeded inputs, obtained by extracting them
                       with `ast` from /root/reference (layered_rgb_blend, parametric_sq/signed_pow, get_icosphere_uvs,
                       point_to_uv_sphericalmap, elev/azim/roll rotations).  These pin the oracle's restatements.
+  render_cube.npz     oracle render of BASELINE configs[0] (one cube primitive, 2 views 64x64, K=10): soft + hard pass and
+                      their gradients to the texture and the vertices, fp32.
   render_small.npz    oracle render of a small seeded scene (2 views 40x48, 3 blocks): blocks pass, env pass, composite,
                       loss and parameter gradients, fp32.  These pin the oracle against drift and give the CUDA path a
                       committed target.  (PARITY UNPINNED upstream: the reference ships no vectors)
@@ -49,6 +51,39 @@ def render_small(dtype=torch.float32):
     return {k: v.detach().numpy() for k, v in out.items()}
 
 
+def cube_case(dtype=torch.float32):
+    """BASELINE configs[0]: one cube primitive, 2 views 64x64, K=10 (coarse settings)."""
+    g = torch.Generator().manual_seed(3)
+    tex = torch.sigmoid(torch.randn(32, 64, 3, generator=g)).to(dtype)
+    Rm = pt3d.rotation_6d_to_matrix(torch.tensor([[0.9, 0.3, -0.2, -0.1, 0.8, 0.4]]))[0].to(dtype)
+    R, T, K = D.ring_cameras(2, dtype=dtype, jitter=0.3, seed=3)
+    return tex, Rm, torch.tensor([0.1, -0.05, 0.0], dtype=dtype), R, T, K
+
+
+def render_cube(dtype=torch.float32):
+    tex, Rm, Tm, R, T, K = cube_case(dtype)
+    tex = tex.clone().requires_grad_(True)
+    scene = D.cube_scene(tex, scale=0.45, R=Rm, T=Tm)
+    scene['verts'].requires_grad_(True)
+    out = D.render(scene, R, T, K, (64, 64), sigma=1e-4, faces_per_pixel=10, z_clip=0.001, detach_bary=True)
+    hard = D.render(scene, R, T, K, (64, 64), sigma=0, faces_per_pixel=1, z_clip=0.001, detach_bary=False)
+    (out.square().sum() + hard[:, :3].sum()).backward()
+    return {k: v.detach().numpy() for k, v in dict(soft=out, hard=hard, grad_tex=tex.grad, grad_verts=scene['verts'].grad).items()}
+
+
+def _read_obj(path):
+    """minimal OBJ reader of the GENERATOR (v / f records, fan triangulation), independent of the product's loader"""
+    vs, fs = [], []
+    for line in open(path):
+        t = line.split()
+        if t[:1] == ['v']:
+            vs.append([float(x) for x in t[1:4]])
+        elif t[:1] == ['f']:
+            ix = [int(x.split('/')[0]) - 1 for x in t[1:]]
+            fs += [[ix[0], ix[k], ix[k + 1]] for k in range(1, len(ix) - 1)]
+    return np.asarray(vs, np.float32), np.asarray(fs, np.int64)
+
+
 def ref_functions():
     assert have_reference()
     out = {}
@@ -78,6 +113,10 @@ def ref_functions():
     for lvl in (1, 2):
         f, uv = nsm['get_icosphere_uvs'](lvl, fix_continuity=True, fix_poles=True)
         out[f'ico{lvl}_faces_uvs'], out[f'ico{lvl}_verts_uvs'] = f, uv
+    cf, cuv = extract('src/utils/mesh.py', ['get_cube_uvs'])['get_cube_uvs']()
+    out['cube_faces_uvs'], out['cube_verts_uvs'] = cf, cuv
+    out['cube_verts'], out['cube_faces'] = _read_obj(os.path.join('/root/reference', 'primitives', 'cube.obj'))
+    out['plane_verts'], out['plane_faces'] = _read_obj(os.path.join('/root/reference', 'primitives', 'plane.obj'))
     nst = extract('src/model/tools.py', ['azim_to_rotation_matrix', 'elev_to_rotation_matrix', 'roll_to_rotation_matrix'])
     out['R_world_115_20_m30'] = (nst['elev_to_rotation_matrix'](115) @ nst['azim_to_rotation_matrix'](20) @ nst['roll_to_rotation_matrix'](-30))[None]
     return {k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()}
@@ -86,6 +125,8 @@ def ref_functions():
 if __name__ == '__main__':
     np.savez_compressed(os.path.join(HERE, 'render_small.npz'), **render_small())
     print('wrote render_small.npz')
+    np.savez_compressed(os.path.join(HERE, 'render_cube.npz'), **render_cube())
+    print('wrote render_cube.npz')
     if have_reference():
         np.savez_compressed(os.path.join(HERE, 'ref_functions.npz'), **ref_functions())
         print('wrote ref_functions.npz')

@@ -1,0 +1,245 @@
+"""GPU parity AT THE BASELINE.json SHAPES: the CUDA path (through the C-ABI) against the fp64 oracle on the very
+configurations that are benched -- not on toy sizes.
+
+  cfg 1  one cube primitive, 2 views 64x64, K=10                                   (BASELINE configs[0])
+  cfg 2  10 blocks, 256^2 textures (256x279 padded, decimate 8), 400x400, K=10     (configs[1]/[2]; views 0/24/48 of the 49-ring)
+  cfg 4  10 blocks, 576x768, K=10                                                  (configs[3], one view)
+  cfg 5  50 blocks (4000 faces), 800x800, K=25, txt_size 128, txt_bkg_upscale 2    (configs[4], one view)
+
+Bars (north_star): image within 1e-4 abs, gradients within 1e-3 relative -- for verts / maps / faces_alpha of a render
+pass and for EVERY leaf parameter through model(inp).  Pixels where fp32 takes a different DISCRETE decision than the fp64
+oracle (inside test / halo cut-off / K-th face / depth near-ties) are identified from the kept face ids, excluded on BOTH
+sides, counted, printed and bounded (tests/test_render_parity.py::_grad_parity)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dbw_path as D
+from tests.helpers import scene_to_device, render_product, intrinsics
+from tests.test_render_parity import _grad_parity, _check_image, _rel, GRAD_REL
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+SEED = 227391            # configs/dtu/default.yml:42, the seed bench.py uses
+RING_VIEWS = [0, 24, 48]
+
+
+def _params(n_blocks, txt, upscale=1, boxy=False):
+    p = D.init_params(n_blocks, txt, txt_bkg_upscale=upscale, seed=SEED, boxy=boxy, dtype=torch.float64)
+    return {k: v.clone().requires_grad_(True) for k, v in p.items()}
+
+
+def _ring(views, n_views=49):
+    R, T, K = D.ring_cameras(n_views, dtype=torch.float64)
+    return R[views], T[views], K
+
+
+# ------------------------------------------------------------------------------------------------ cfg 1: cube
+def test_cfg1_cube_two_views_forward_backward():
+    from tests.golden.make_golden import cube_case
+    dev = torch.device('cuda:0')
+    g = np.load(os.path.join(GOLD, 'render_cube.npz'))
+    tex, Rm, Tm, R, T, K = cube_case()
+    scene = D.cube_scene(tex, scale=0.45, R=Rm, T=Tm)
+    sc = scene_to_device(scene, dev, requires_grad=True)
+    soft = render_product(sc, R.to(dev), T.to(dev), K, (64, 64), 1e-4, 10, z_clip=0.001, detach_bary=True)
+    hard = render_product(sc, R.to(dev), T.to(dev), K, (64, 64), 0.0, 1, z_clip=0.001)
+    _check_image(soft.detach().cpu(), torch.from_numpy(g['soft']))
+    _check_image(hard.detach().cpu(), torch.from_numpy(g['hard']))
+    (soft.square().sum() + hard[:, :3].sum()).backward()
+    gt = sc['maps'].grad.cpu().reshape(g['grad_tex'].shape)
+    assert _rel(gt, torch.from_numpy(g['grad_tex'])) < 2e-3           # fp32 golden vs fp32 CUDA (different summation order)
+    assert _rel(sc['verts'].grad.cpu(), torch.from_numpy(g['grad_verts'])) < 2e-3
+    # and decision-masked against the fp64 oracle at the 1e-3 bar
+    tex64, Rm, Tm, R, T, K = cube_case(torch.float64)
+    scene64 = D.cube_scene(tex64.clone().requires_grad_(True), scale=0.45, R=Rm, T=Tm)
+    scene64['verts'].requires_grad_(True)
+    amb = _grad_parity(scene64, R, T, K, (64, 64), 1e-4, 10, 0.001, True, None, True, seed=1)
+    print(f'cfg1 cube: ambiguous pixels {amb * 100:.4f}%')
+
+
+# ------------------------------------------------------------------------------------------------ cfg 2: DTU shape as benched
+@pytest.fixture(scope='module')
+def cfg2():
+    tpl = D.SceneTemplate(n_blocks=10, txt_size=256)
+    return tpl, _ring(RING_VIEWS)
+
+
+@pytest.mark.parametrize('boxy', [False, True])
+def test_cfg2_blocks_pass_coarse_400x400(cfg2, boxy):
+    """the blocks pass exactly as bench.py runs it: 256x279 padded decimated atlas, K=10, sigma=1e-4, per-face opacities"""
+    tpl, (R, T, K) = cfg2
+    p = _params(10, 256, boxy=boxy)
+    blocks, alpha = tpl.build_blocks(p, decimate=8)
+    assert blocks['maps'][0].shape == (256, 279, 3)
+    fa = alpha.repeat_interleave(tpl.BNF)
+    amb = _grad_parity(blocks, R, T, K, (400, 400), 1e-4, 10, 0.001, True, fa, True, seed=1)
+    print(f'cfg2 blocks coarse (boxy={boxy}): ambiguous pixels {amb * 100:.4f}%')
+
+
+def test_cfg2_blocks_pass_fine_400x400(cfg2):
+    tpl, (R, T, K) = cfg2
+    p = _params(10, 256, boxy=True)
+    blocks, _ = tpl.build_blocks(p)
+    amb = _grad_parity(blocks, R[:2], T[:2], K, (400, 400), 5e-6, 10, 0.001, True, None, True, seed=2)
+    print(f'cfg2 blocks fine: ambiguous pixels {amb * 100:.4f}%')
+
+
+def test_cfg2_env_pass_400x400(cfg2):
+    tpl, (R, T, K) = cfg2
+    p = _params(10, 256)
+    env = tpl.build_env(p, decimate=8)
+    amb = _grad_parity(env, R, T, K, (400, 400), 0.0, 1, 0.001, False, None, True, seed=3)
+    print(f'cfg2 env: ambiguous pixels {amb * 100:.4f}%')
+
+
+def _bench_model(size, n_blocks=10, txt=256, K=10, upscale=1, noise=True):
+    import dbw_b200  # noqa: F401
+    from dbw_b200.dbw import DifferentiableBlocksWorld
+    cfg = {'mesh': {'n_blocks': n_blocks, 'S_world': 0.5, 'R_world': [115, 0, 0], 'txt_size': txt, 'txt_bkg_upscale': upscale},
+           'renderer': {'faces_per_pixel': K, 'cameras': {'name': 'perspective'}, 'detach_bary': True, 'z_clip': 0.001},
+           'rend_optim': {'coarse_learning': 1500, 'decimate_txt': 750, 'decimate_factor': 8, 'kill_blocks': True,
+                          'decouple_rendering': True, 'opacity_noise': noise},
+           'loss': {'rgb_weight': 1}}
+    torch.manual_seed(SEED)
+    model = DifferentiableBlocksWorld(size, **cfg).to(torch.device('cuda:0'))
+    model.train()
+    return model
+
+
+def _leaf_gradient_parity(model, tpl, size, R, T, K, Kf, sigma, fine, max_masked=3e-3):
+    """model(inp)['total'].backward() vs the fp64 oracle's predict + MSE, for every leaf parameter.  Pixels whose composited
+    colour differs by more than 1e-4 (a different discrete decision somewhere in their layer stack) get a target equal to
+    each side's own reconstruction, i.e. zero residual and zero gradient on BOTH sides; their share is bounded."""
+    dev = torch.device('cuda:0')
+    B = R.shape[0]
+    p = {k: v.detach().cpu().double().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    g = torch.Generator().manual_seed(7)
+    imgs = torch.rand(B, 3, *size, generator=g, dtype=torch.float64)
+    noise = None
+    if not fine and model.opacity_noise:
+        noise = torch.randn(model.n_blocks, generator=g, dtype=torch.float64)
+        model.opacity_noise_buffer = noise.float().to(dev)
+    inp = {'imgs': imgs.float().to(dev), 'R': R.float().to(dev), 'T': T.float().to(dev), 'K': K.float()[None].expand(B, -1, -1).to(dev)}
+    a = torch.sigmoid(p['alpha_logit'].detach())
+    keep = a > (0.5 if fine else 0.01)
+    rec_ref = D.predict(tpl, p, R, T, K, size, sigma=sigma, faces_per_pixel=Kf, z_clip=0.001, fine=fine, keep=keep,
+                        decimate=0 if fine else 8, alpha_noise=noise)
+    with torch.no_grad():
+        rec = model.predict(inp).cpu().double()
+    bad = ((rec - rec_ref.detach()).abs() > 1e-4).any(1, keepdim=True)
+    masked = bad.double().mean().item()
+    assert masked <= max_masked, f'{masked * 100:.3f}% of pixels deviate by more than 1e-4'
+    inp['imgs'] = torch.where(bad, rec, imgs).float().to(dev)
+    losses = model(inp, None)
+    loss_ref = D.mse_loss(torch.where(bad, rec_ref.detach(), imgs), rec_ref)
+    assert abs(losses['rgb'].item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    losses['total'].backward()
+    loss_ref.backward()
+    worst = {}
+    for name, prm in model.named_parameters():
+        g_ref = p[name].grad
+        if g_ref is None or g_ref.abs().max() == 0:
+            assert prm.grad is None or prm.grad.abs().max().item() < 1e-12, name
+            continue
+        worst[name] = _rel(prm.grad.cpu().double(), g_ref)
+    print(f'leaf gradients ({size[0]}x{size[1]}, {"fine" if fine else "coarse"}): masked pixels {masked * 100:.4f}%; rel err '
+          + ', '.join(f'{k} {v:.1e}' for k, v in worst.items()))
+    for name, rel in worst.items():
+        assert rel < GRAD_REL, f'{name}: rel grad err {rel:.3e}'
+
+
+@pytest.mark.parametrize('fine', [False, True])
+def test_cfg2_model_leaf_gradients_400x400(cfg2, fine):
+    """every leaf parameter through model(inp) at the benched configuration (fused scene kernels, loss epilogue, texture prep)"""
+    tpl, (R, T, K) = cfg2
+    model = _bench_model((400, 400))
+    if fine:
+        model.set_cur_epoch(2000)
+        with torch.no_grad():
+            model.alpha_logit.copy_(torch.tensor([2., -2., 1., 3., -1., 0.7, 1.5, -0.3, 2.5, 0.9]))
+            model.sq_eps.copy_(torch.randn_like(model.sq_eps))
+    _leaf_gradient_parity(model, tpl, (400, 400), R, T, K, 10, 5e-6 if fine else 1e-4, fine)
+
+
+# ------------------------------------------------------------------------------------------------ cfg 4: BlendedMVS shape
+def test_cfg4_bmvs_576x768_one_view():
+    tpl = D.SceneTemplate(n_blocks=10, txt_size=256)
+    p = _params(10, 256, boxy=True)
+    R, T, K = _ring([5], 64)
+    blocks, alpha = tpl.build_blocks(p, decimate=8)
+    fa = alpha.repeat_interleave(tpl.BNF)
+    amb = _grad_parity(blocks, R, T, K, (576, 768), 1e-4, 10, 0.001, True, fa, True, seed=4)
+    print(f'cfg4 blocks 576x768: ambiguous pixels {amb * 100:.4f}%')
+    amb = _grad_parity(tpl.build_env(_params(10, 256), decimate=8), R, T, K, (576, 768), 0.0, 1, 0.001, False, None, True, seed=5)
+    print(f'cfg4 env 576x768: ambiguous pixels {amb * 100:.4f}%')
+
+
+def test_cfg4_model_leaf_gradients_576x768():
+    tpl = D.SceneTemplate(n_blocks=10, txt_size=256)
+    R, T, K = _ring([5], 64)
+    _leaf_gradient_parity(_bench_model((576, 768)), tpl, (576, 768), R, T, K, 10, 1e-4, False)
+
+
+# ------------------------------------------------------------------------------------------------ cfg 5: stress shape
+def test_cfg5_stress_800x800_50_blocks_K25():
+    """configs/bmvs/gundam_50.yml:8-14 shape: 50 blocks (4000 faces), K=25, txt_size 128, txt_bkg_upscale 2"""
+    tpl = D.SceneTemplate(n_blocks=50, txt_size=128, txt_bkg_upscale=2)
+    p = _params(50, 128, upscale=2, boxy=True)
+    R, T, K = _ring([17], 256)
+    blocks, alpha = tpl.build_blocks(p, decimate=8)
+    fa = alpha.repeat_interleave(tpl.BNF)
+    amb = _grad_parity(blocks, R, T, K, (800, 800), 1e-4, 25, 0.001, True, fa, True, seed=6)
+    print(f'cfg5 blocks 800x800 K=25: ambiguous pixels {amb * 100:.4f}%')
+    env = tpl.build_env(p, decimate=8)
+    assert env['maps'][0].shape == (256, 256, 3)
+    amb = _grad_parity(env, R, T, K, (800, 800), 0.0, 1, 0.001, False, None, True, seed=7)
+    print(f'cfg5 env 800x800: ambiguous pixels {amb * 100:.4f}%')
+
+
+def test_cfg5_model_leaf_gradients_800x800():
+    tpl = D.SceneTemplate(n_blocks=50, txt_size=128, txt_bkg_upscale=2)
+    R, T, K = _ring([17], 256)
+    _leaf_gradient_parity(_bench_model((800, 800), n_blocks=50, txt=128, K=25, upscale=2), tpl, (800, 800), R, T, K, 25, 1e-4, False)
+
+
+# ------------------------------------------------------------------------------------------------ the host-buffer plugin entry
+def test_forward_host_entry_matches_device_entry():
+    """dbw_render_forward_host (the call a host-side plugin makes, numpy / host pointers in and out)
+    == dbw_render_forward on device tensors, bit for bit."""
+    import dbw_b200  # noqa: F401
+    from dbw_b200 import _lib
+    from dbw_b200.renderer import make_settings
+    from dbw_b200._lib import DbwMapDesc
+    dev = torch.device('cuda:0')
+    tpl = D.SceneTemplate(n_blocks=4, txt_size=32)
+    p = D.init_params(4, 32, seed=3)
+    R, T, K = D.ring_cameras(3, jitter=0.3, seed=3)
+    blocks, alpha = tpl.build_blocks(p)
+    fa = alpha.repeat_interleave(tpl.BNF)
+    H, W, Kf = 72, 96, 10
+    ref = render_product(scene_to_device(blocks, dev), R.to(dev), T.to(dev), K, (H, W), 1e-4, Kf, z_clip=0.001, detach_bary=True,
+                         faces_alpha=fa.to(dev))
+    verts = blocks['verts'].float().contiguous().numpy()
+    faces = blocks['faces'].to(torch.int32).contiguous().numpy()
+    fuv = blocks['faces_verts_uvs'].float().contiguous().numpy()
+    fmap = blocks['face_map'].to(torch.int32).contiguous().numpy()
+    maps = np.concatenate([m.float().reshape(-1).numpy() for m in blocks['maps']])
+    table, off = [], 0
+    for m in blocks['maps']:
+        table.append(DbwMapDesc(off, m.shape[0], m.shape[1], 0)); off += m.numel()
+    table = (DbwMapDesc * len(table))(*table)
+    blur = float(np.log(1. / 1e-4 - 1.) * 1e-4)
+    cfg = make_settings(3, H, W, Kf, verts.shape[0], faces.shape[0], len(blocks['maps']), 0, intrinsics(K), 1e-4, blur, 0.001,
+                        (0., 0., 0.), detach_bary=True, n_map_floats=maps.size)
+    out = np.empty((3, 4, H, W), np.float32)
+    Rn, Tn, fan = R.float().contiguous().numpy(), T.float().contiguous().numpy(), fa.float().contiguous().numpy()
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib().dbw_render_forward_host(ctypes.byref(cfg), ptr(verts), ptr(faces), ptr(fuv), ptr(fmap), ptr(maps),
+                                                  ctypes.c_size_t(maps.size), table, ptr(Rn), ptr(Tn), ptr(fan), ptr(out),
+                                                  ctypes.c_void_p(0)), 'dbw_render_forward_host')
+    assert np.array_equal(out, ref.cpu().numpy())
+    _lib.lib().dbw_host_arena_release()

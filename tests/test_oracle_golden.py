@@ -36,6 +36,44 @@ def test_superquadric_and_uv_builders_match_reference_golden():
     assert torch.allclose(D.world_rotation(115, 20, -30), g['R_world_115_20_m30'], atol=1e-6)
 
 
+def test_cube_primitive_matches_reference_golden():
+    """BASELINE configs[0]: the cube primitive (vertices / faces of primitives/cube.obj, UV cross of mesh.py:176-207) of
+    the oracle AND of the product's geometry module, against vectors generated from the reference's files."""
+    import dbw_b200  # noqa: F401
+    from dbw_b200 import geometry as G
+    g = _npz('ref_functions.npz')
+    for verts, faces in (D.get_cube(), G.unit_cube()):
+        assert torch.equal(verts, g['cube_verts']) and torch.equal(faces, g['cube_faces'])
+    for f, uv in (D.get_cube_uvs(), G.cube_uvs()):
+        assert torch.equal(f, g['cube_faces_uvs']) and torch.equal(uv, g['cube_verts_uvs'])
+    pv, pf = G.unit_plane()
+    assert torch.equal(pv, g['plane_verts']) and torch.equal(pf, g['plane_faces'])
+    ov, of = D.get_plane()
+    assert torch.equal(ov.reshape(-1, 3), g['plane_verts']) and torch.equal(of.reshape(-1, 3), g['plane_faces'])
+
+
+@pytest.mark.skipif(not have_reference(), reason='needs the reference checkout (/root/reference)')
+def test_obj_loader_reads_the_reference_primitives():
+    import dbw_b200  # noqa: F401
+    from dbw_b200 import geometry as G
+    for name, (v, f) in (('cube', G.unit_cube()), ('plane', G.unit_plane())):
+        lv, lf = G.load_obj(f'/root/reference/primitives/{name}.obj')
+        assert torch.equal(lv, v) and torch.equal(lf, f), name
+
+
+def test_render_cube_matches_golden():
+    """BASELINE configs[0] on the CPU oracle (the config's own arm: 'PyTorch3D CPU rasterizer, plumbing, no GPU')."""
+    from tests.golden.make_golden import render_cube
+    cur = render_cube()
+    g = np.load(os.path.join(GOLD, 'render_cube.npz'))
+    assert (g['soft'][:, 3] > 0.5).mean() > 0.05 and (g['hard'][:, 3] == 1).mean() > 0.05      # the cube is in view
+    for k in g.files:
+        if k.startswith('grad_'):
+            assert float(np.linalg.norm(cur[k] - g[k])) / max(float(np.linalg.norm(g[k])), 1e-12) < 1e-4, k
+        else:
+            assert np.abs(cur[k] - g[k]).max() <= 2e-6, k
+
+
 def test_render_small_matches_golden():
     from tests.golden.make_golden import render_small
     cur = render_small()
