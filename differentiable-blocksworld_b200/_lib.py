@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DBW_RENDER_LIB: explicit path of another build of the same library (kernel experiments); never a fallback
 LIB_PATH = os.environ.get('DBW_RENDER_LIB') or os.path.join(_HERE, 'libdbw_render.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class DbwRenderSettings(ctypes.Structure):
@@ -21,6 +21,7 @@ class DbwRenderSettings(ctypes.Structure):
         ('clip_inside', ctypes.c_int32), ('perspective_correct', ctypes.c_int32),
         ('clip_barycentric', ctypes.c_int32), ('detach_bary', ctypes.c_int32), ('verts_are_ndc', ctypes.c_int32),
         ('n_map_floats', ctypes.c_int32), ('maps_are_texels4', ctypes.c_int32), ('save_fragment_state', ctypes.c_int32),
+        ('alpha_group', ctypes.c_int32), ('n_static_faces', ctypes.c_int32),
     ]
 
 

@@ -158,6 +158,31 @@ __device__ __forceinline__ float tri_dist2(f2 p, const TriGeom& t) {
   return fminf(fminf(e01, e02), e12);
 }
 
+// same distance, plus WHICH segment realises it (0 = v0v1, 1 = v0v2, 2 = v1v2) with the tie order of tri_dist_backward:
+// the forward records it with the fragment, so that the backward differentiates one segment instead of re-deriving three
+__device__ __forceinline__ float tri_dist2_edge(f2 p, const TriGeom& t, int& edge) {
+  const float e01 = seg_dist2(p, t.v0, t.v1, t.il01), e02 = seg_dist2(p, t.v0, t.v2, t.il02), e12 = seg_dist2(p, t.v1, t.v2, t.il12);
+  edge = (e01 <= e02 && e01 <= e12) ? 0 : ((e02 <= e01 && e02 <= e12) ? 1 : 2);
+  return fminf(fminf(e01, e02), e12);
+}
+
+// Conservative triangle / rectangle overlap for the tile binner: false only if one of the triangle's edge lines has the
+// whole rectangle [x0,x1] x [y0,y1] strictly on its outer side (by more than a 1e-5 NDC margin, far above the rounding of
+// the affine evaluation).  A face kept needlessly costs time, never correctness; degenerate faces are kept.
+__device__ __forceinline__ bool tri_overlaps_rect(f2 v0, f2 v1, f2 v2, float x0, float x1, float y0, float y1) {
+  const float area = (v2.x - v0.x) * (v1.y - v0.y) - (v2.y - v0.y) * (v1.x - v0.x);
+  if (!(fabsf(area) > 1e-12f)) return true;
+  const float sg = area > 0.f ? 1.f : -1.f;
+  const f2 a[3] = {v1, v2, v0}, b[3] = {v2, v0, v1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float cx = sg * (b[i].y - a[i].y), cy = -sg * (b[i].x - a[i].x);     // sg * edge(p; a, b) = cx (p.x - a.x) + cy (p.y - a.y)
+    const float bx = cx > 0.f ? x1 : x0, by = cy > 0.f ? y1 : y0;              // the rectangle corner that maximises it
+    if (cx * (bx - a[i].x) + cy * (by - a[i].y) < -1e-5f * (fabsf(cx) + fabsf(cy))) return false;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------ backward pieces
 
 __device__ __forceinline__ void edge_backward(f2 p, f2 a, f2 b, float g, f2& ga, f2& gb) {

@@ -28,6 +28,7 @@
 
 #include "../../include/dbw_render.h"
 #include "dbw_math.cuh"
+#include "dbw_fraglist.cuh"
 
 // ------------------------------------------------------------------------------------------------ error plumbing
 static thread_local char g_err[512] = "";
@@ -83,7 +84,8 @@ extern "C" void dbw_timing_reset(void) {
 }
 
 struct Workspace {
-  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4; float* frag; size_t total;
+  float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4;
+  float4* frag; unsigned char* nfrag; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
   Workspace w; char* p = (char*)base; size_t off = 0;
@@ -96,7 +98,9 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
   w.view_bbox = (int*)(p + off);   off += align_up(B * 4 * sizeof(int));
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
-  w.frag = (float*)(p + off);      off += s.save_fragment_state ? align_up(B * (size_t)s.faces_per_pixel * 8 * s.height * s.width * sizeof(float)) : 0;
+  const size_t npx = B * (size_t)s.height * s.width;
+  w.frag = (float4*)(p + off);     off += s.save_fragment_state ? align_up(npx * (size_t)s.faces_per_pixel * sizeof(float4)) : 0;
+  w.nfrag = (unsigned char*)(p + off); off += s.save_fragment_state ? align_up(npx) : 0;
   w.total = off; return w;
 }
 struct BwdScratch { float* g_tri; float* g_conv; float* g_verts_ndc; float4* g_maps4; size_t total; };
@@ -122,7 +126,11 @@ static int validate(const DbwRenderSettings* s) {
   if (s->n_views <= 0 || s->height <= 0 || s->width <= 0) return fail("n_views, height, width must be positive");
   if (s->faces_per_pixel <= 0 || s->faces_per_pixel > DBW_MAX_FACES_PER_PIXEL) return fail("faces_per_pixel out of range [1, 64]");
   if (s->n_verts <= 0 || s->n_faces <= 0 || s->n_maps <= 0) return fail("n_verts, n_faces, n_maps must be positive");
-  if (s->alpha_view_stride != 0 && s->alpha_view_stride != s->n_faces) return fail("alpha_view_stride must be 0 or n_faces");
+  const int ag = s->alpha_group > 0 ? s->alpha_group : 1;
+  if (s->n_faces % ag) return fail("n_faces must be a multiple of alpha_group");
+  if (s->alpha_view_stride != 0 && s->alpha_view_stride != s->n_faces / ag) return fail("alpha_view_stride must be 0 or n_faces / alpha_group");
+  if (s->n_static_faces < 0 || s->n_static_faces > s->n_faces) return fail("n_static_faces out of range [0, n_faces]");
+  if (2 * (long long)s->n_faces > DBW_FRAG_SLOT_MASK) return fail("too many faces: triangle slots are stored in 24 bits");
   if (s->sigma < 0.f || s->blur_radius < 0.f) return fail("sigma and blur_radius must be >= 0");
   if (s->n_map_floats <= 0 || s->n_map_floats % 3 != 0) return fail("n_map_floats must be a positive multiple of 3");
   return 0;
@@ -302,16 +310,19 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
 struct RasterParams {
   int B, H, W, K, V, F, M;
   int alpha_stride;
-  float sigma, blur, bg0, bg1, bg2;
+  float inv_alpha_group;     // 1 / (faces sharing one opacity entry): alpha index = floor((face + 0.5) * inv_alpha_group)
+  int n_static_faces;        // faces [0, n_static_faces) have constant vertices: the backward skips their vertex gradient
+  float sigma, blur, sqrt_blur, bg0, bg1, bg2;
   int clip_inside, persp, clipb, detach_bary;
   const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags; const int* view_bbox;
   const float4* maps4;
   const float* faces_alpha;
-  float* out_rgba; int* topk;
-  // backward only
-  float* frag;     // (B,K,H,W,8) saved fragment state or NULL
+  float* out_rgba; int* topk;        // topk may be NULL
+  float4* frag;              // (B,K,H,W) saved fragment records {bits, u, v, signed dist} or NULL
+  unsigned char* nfrag;      // (B,H,W) number of records written per pixel
   const float* face_shade;   // (B,F,3) per-view per-face colour multiplier (flat shading) or NULL
   float* out_dists;          // (B,K,H,W) signed squared distances of the kept fragments (-1 = empty) or NULL
+  // backward only
   const float* grad_rgba; float* g_tri; float* g_conv; float* g_faces_alpha; float4* g_maps4;
   const float* grad_scale;   // device scalar multiplied into grad_rgba (the upstream gradient of a fused loss) or NULL
   // fused compositing + MSE epilogue of the forward (DbwLossEpilogue); ep_target == NULL: plain render
@@ -332,14 +343,9 @@ struct RasterParams {
 #define DBW_BWD_NT 128
 #endif
 #define TILE_W 16
-#ifndef LIST_CAP
-#define LIST_CAP 256           // default capacity of a tile's face list (21 KB of shared memory per CTA)
-#endif
 #ifndef DBW_AGG_MIN
 #define DBW_AGG_MIN 2         // groups of at most this many lanes use plain atomics instead of a warp reduction
 #endif
-
-#include "dbw_topk.cuh"
 
 // opacity of one fragment from its signed squared distance (layered_rgb_blend, src/model/renderer.py:252-257)
 __device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_inside) {
@@ -349,18 +355,35 @@ __device__ __forceinline__ float frag_alpha(float d, float sigma, int clip_insid
   return 1.f / (1.f + __expf(d / sigma));
 }
 
-// shared by forward shading and backward: colour of fragment (slot) at pixel p
+// index of a face's opacity entry: faces_alpha holds one value per group of `alpha_group` consecutive faces
+__device__ __forceinline__ int alpha_index(const RasterParams& P, int view, int face) {
+  return view * P.alpha_stride + __float2int_rd(((float)face + 0.5f) * P.inv_alpha_group);
+}
+
+// bilinear colour of a fragment from its UV (shared by forward shading and the detach_bary backward)
+struct Texel4 { TexTap tap; f3 c00, c01, c10, c11, color; };
+__device__ __forceinline__ void fetch_color(const RasterParams& P, float u, float v, float4 q1, Texel4& s) {
+  const int hw = __float_as_int(q1.w);
+  s.tap = tex_tap(u, v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
+  s.c00 = ld_texel(P.maps4, s.tap.i00); s.c01 = ld_texel(P.maps4, s.tap.i01);
+  s.c10 = ld_texel(P.maps4, s.tap.i10); s.c11 = ld_texel(P.maps4, s.tap.i11);
+  s.color.x = s.c00.x * s.tap.w00 + s.c01.x * s.tap.w01 + s.c10.x * s.tap.w10 + s.c11.x * s.tap.w11;
+  s.color.y = s.c00.y * s.tap.w00 + s.c01.y * s.tap.w01 + s.c10.y * s.tap.w10 + s.c11.y * s.tap.w11;
+  s.color.z = s.c00.z * s.tap.w00 + s.c01.z * s.tap.w01 + s.c10.z * s.tap.w10 + s.c11.z * s.tap.w11;
+}
+
+// geometry of fragment (slot) at pixel p, re-derived from the face records (the barycentric-path backward needs all of it)
 struct Shade {
   TriGeom t; Bary b; f3 bu;       // bu: barycentrics w.r.t. the ORIGINAL face (after un-clipping)
   float4 uv01; float u2, v2;      // per-face-vertex UVs
-  float u, v; TexTap tap; f3 c00, c01, c10, c11, color;
+  float u, v; float4 q1;
 };
 
-__device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
+__device__ __forceinline__ void shade_geometry(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
   const size_t gs = (size_t)view * 2 * P.F + slot;
-  // one level of dependent loads after the face id: geometry record + UV / map record (6 x LDG.128)
   const float4 r0 = __ldg(&P.rec[gs * 4]), r1 = __ldg(&P.rec[gs * 4 + 1]), r2 = __ldg(&P.rec[gs * 4 + 2]), r3 = __ldg(&P.rec[gs * 4 + 3]);
-  const float4 q0 = __ldg(&P.rec2[gs * 2]), q1 = __ldg(&P.rec2[gs * 2 + 1]);
+  const float4 q0 = __ldg(&P.rec2[gs * 2]);
+  s.q1 = __ldg(&P.rec2[gs * 2 + 1]);
   s.t = unpack_tri(r0, r1, r2, r3);
   s.b = eval_bary(p, s.t, P.persp, P.clipb);
   s.bu = s.b.bc;
@@ -370,48 +393,38 @@ __device__ __forceinline__ void shade_fragment(const RasterParams& P, int view, 
     s.bu.y = s.b.bc.x * cv[1] + s.b.bc.y * cv[4] + s.b.bc.z * cv[7];
     s.bu.z = s.b.bc.x * cv[2] + s.b.bc.y * cv[5] + s.b.bc.z * cv[8];
   }
-  s.uv01 = q0; s.u2 = q1.x; s.v2 = q1.y;
-  s.u = s.bu.x * q0.x + s.bu.y * q0.z + s.bu.z * q1.x;
-  s.v = s.bu.x * q0.y + s.bu.y * q0.w + s.bu.z * q1.y;
-  const int hw = __float_as_int(q1.w);
-  s.tap = tex_tap(s.u, s.v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
-  s.c00 = ld_texel(P.maps4, s.tap.i00); s.c01 = ld_texel(P.maps4, s.tap.i01);
-  s.c10 = ld_texel(P.maps4, s.tap.i10); s.c11 = ld_texel(P.maps4, s.tap.i11);
-  s.color.x = s.c00.x * s.tap.w00 + s.c01.x * s.tap.w01 + s.c10.x * s.tap.w10 + s.c11.x * s.tap.w11;
-  s.color.y = s.c00.y * s.tap.w00 + s.c01.y * s.tap.w01 + s.c10.y * s.tap.w10 + s.c11.y * s.tap.w11;
-  s.color.z = s.c00.z * s.tap.w00 + s.c01.z * s.tap.w01 + s.c10.z * s.tap.w10 + s.c11.z * s.tap.w11;
+  s.uv01 = q0; s.u2 = s.q1.x; s.v2 = s.q1.y;
+  s.u = s.bu.x * q0.x + s.bu.y * q0.z + s.bu.z * s.q1.x;
+  s.v = s.bu.x * q0.y + s.bu.y * q0.w + s.bu.z * s.q1.y;
 }
 
-// Resident CTAs per SM each raster kernel is compiled for (register cap = 65536 / (threads * CTAs)), tuned on B200 at cfg 2:
-// occupancy wins until the cap forces spills of the per-pixel state (3 registers per layer of the K nearest fragments).
+// Resident CTAs per SM each raster kernel is compiled for (register cap = 65536 / (threads * CTAs)).
 #ifndef DBW_FWD_SMALLK_MINB
-#define DBW_FWD_SMALLK_MINB 6     // K <= 4, CTAs of DBW_FWD_NT_SMALLK threads (40 registers)
+#define DBW_FWD_SMALLK_MINB 5     // CTAs of DBW_FWD_NT_SMALLK threads
 #endif
-#ifndef DBW_FWD_K10_MINB
-#define DBW_FWD_K10_MINB 7        // 4 < K <= 10, CTAs of DBW_FWD_NT threads (72 registers)
+#ifndef DBW_FWD_MINB
+#define DBW_FWD_MINB 8            // CTAs of DBW_FWD_NT threads
 #endif
 #ifndef DBW_BWD_DETACH_MINB
-#define DBW_BWD_DETACH_MINB 10    // backward without the barycentric path, CTAs of DBW_BWD_NT threads (48 registers)
+#define DBW_BWD_DETACH_MINB 8     // backward without the barycentric path, CTAs of DBW_BWD_NT threads (64 registers)
 #endif
 #ifndef DBW_BWD_BARY_MINB
-#define DBW_BWD_BARY_MINB 6       // backward with the barycentric path: more live state (80 registers)
+#define DBW_BWD_BARY_MINB 5       // backward with the barycentric path: more live state (96 registers)
 #endif
-__host__ __device__ constexpr int max_i(int a, int b) { return a > b ? a : b; }
-__host__ __device__ constexpr int fwd_min_ctas(int K, int NT) {
-  return K <= 4 ? DBW_FWD_SMALLK_MINB : (K <= 10 ? DBW_FWD_K10_MINB : max_i(1, (K <= 25 ? 2 : 1) * 256 / NT));
-}
+
+// One kernel for every K: the per-pixel list of the K nearest fragments lives in (dynamic) shared memory (dbw_fraglist.cuh).
 // EP: with the compositing + MSE loss epilogue (DbwLossEpilogue); a template flag so that plain renders carry none of it
-template <int K, int NT, bool EP>
-__global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel(const RasterParams P) {
-  // faces a tile lists at once (more: chunked path).  Small-K scenes list few faces per tile, and every KB of shared
-  // memory not taken is L1 for the texel / record fetches: 128 entries (10.5 KB) for the 128-thread K <= 10 kernels
-  constexpr int CAP = (NT <= 128 && K <= 10) ? 128 : LIST_CAP;
+template <int NT, bool EP>
+__global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_MINB) raster_forward_kernel(const RasterParams P) {
+  // faces a tile lists at once (more: chunked path)
+  constexpr int CAP = NT <= 128 ? 128 : 256;
   static_assert(CAP >= NT, "a scan batch adds up to NT entries");
   __shared__ float4 s_bbox[CAP];
   __shared__ float4 s_rec[CAP * 4];
   __shared__ int s_slot[CAP];
   __shared__ int s_count;
   __shared__ __align__(8) uint64_t s_bar;      // mbarrier of the TMA record gather
+  extern __shared__ float4 s_dyn[];            // fragment lists: K*NT float4 (pz, bits, sd, u), then K*NT float (v)
   uint32_t bar_phase = 0;
 
   constexpr int TILE_H = NT / 16;
@@ -436,14 +449,15 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
   const int* vb = P.view_bbox + view * 4;
   const bool tile_empty = ord2f(vb[0]) > t_xmax || ord2f(vb[1]) < t_xmin || ord2f(vb[2]) > t_ymax || ord2f(vb[3]) < t_ymin;
 
-  unsigned long long key[K];
-  float dk[K];
-#pragma unroll
-  for (int k = 0; k < K; ++k) { key[k] = ~0ull; dk[k] = 0.f; }
+  const int K = P.K;
+  float4* const lA = s_dyn + tid;                                            // this thread's list column
+  float* const lV = reinterpret_cast<float*>(s_dyn + (size_t)K * NT) + tid;
+  int n = 0;
 
   const int nslots = tile_empty ? 0 : ((P.view_flags[view] & 1) ? 2 * P.F : P.F);
-  const float4* bbox = P.bbox + (size_t)view * 2 * P.F;
-  const float4* rec = P.rec + (size_t)view * 2 * P.F * 4;
+  const size_t slot_base = (size_t)view * 2 * P.F;
+  const float4* bbox = P.bbox + slot_base;
+  const float4* rec = P.rec + slot_base * 4;
   const bool dist_inside = (!P.clip_inside && P.sigma > 0.f) || P.out_dists != nullptr;
 
   // stage the records of the `cnt` listed faces in shared memory, then test every pixel against every listed face
@@ -463,37 +477,57 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
         // cheap, exact part first: edge functions -> inside; pixels outside the face and beyond the halo leave here
         const Edges ed = eval_edges(p, t);
         if (!ed.inside && P.blur == 0.f) continue;      // hard pass: nothing outside a face can be within a zero halo
-        float dist = 1.f;
+        float dist = 1.f; int edge = 0;
         const bool need_dist = !ed.inside || dist_inside || t.neighbor >= 0;
-        if (need_dist) dist = tri_dist2(p, t);
+        if (need_dist) dist = tri_dist2_edge(p, t, edge);
         if (!ed.inside && dist >= P.blur) continue;
         const Bary b = bary_from_edges(ed, t, P.persp, P.clipb);
         if (b.pz < 0.f) continue;
-        const float sd = b.inside ? -dist : dist;
         const int slot = s_slot[j];
-        topk_offer<K>(key, dk, b.pz, slot, sd, dist, t.neighbor);
+        // a full list only admits what sorts before its last entry (the z-clipped halves first settle their exclusion rule)
+        if (n == K && t.neighbor < 0 && !frag_key_less(__float_as_uint(b.pz + 0.f), slot, lA[(K - 1) * NT])) continue;
+        // texture coordinates now, while the barycentrics are in registers: shading never re-derives geometry
+        const size_t gs = slot_base + slot;
+        f3 bu = b.bc;
+        if (t.flags & 1) {
+          const float* cv = P.conv + gs * 9;
+          bu.x = b.bc.x * cv[0] + b.bc.y * cv[3] + b.bc.z * cv[6];
+          bu.y = b.bc.x * cv[1] + b.bc.y * cv[4] + b.bc.z * cv[7];
+          bu.z = b.bc.x * cv[2] + b.bc.y * cv[5] + b.bc.z * cv[8];
+        }
+        const float4 q0 = __ldg(&P.rec2[gs * 2]);
+        const float2 q1 = __ldg(reinterpret_cast<const float2*>(&P.rec2[gs * 2 + 1]));
+        const float u = bu.x * q0.x + bu.y * q0.z + bu.z * q1.x;
+        const float v = bu.x * q0.y + bu.y * q0.w + bu.z * q1.y;
+        n = fraglist_offer(lA, lV, NT, n, K, b.pz, slot, edge, b.inside ? -dist : dist, dist, t.neighbor, u, v);
       }
     }
     // no barrier here: on the fast path nothing rewrites the list, and warps that finish early start shading (and hide
     // the texel latency of the others); the chunked path synchronises at its call site before refilling the list
   };
 
-  // ---- bin: which face slots of the view touch the tile?  Fast path: every batch of 256 slots is tested and compacted
-  // with NO block barrier in between (ballot + one shared atomic per warp); hits beyond the list capacity are counted
-  // but not stored, and only then the chunked path below (barrier per batch) is taken.
+  // ---- bin: which face slots of the view touch the tile?  A slot is listed when its blur-expanded box overlaps the tile
+  // AND no edge line of its triangle has the whole (halo-expanded) tile on its outer side.  Fast path: every batch of NT
+  // slots is tested and compacted with NO block barrier in between (ballot + one shared atomic per warp); hits beyond the
+  // list capacity are counted but not stored, and only then the chunked path below (barrier per batch) is taken.
+  const float rx0 = t_xmin - P.sqrt_blur, rx1 = t_xmax + P.sqrt_blur, ry0 = t_ymin - P.sqrt_blur, ry1 = t_ymax + P.sqrt_blur;
+  auto scan_hit = [&](int s, float4& bb) -> bool {
+    if (s >= nslots) return false;
+    bb = __ldg(&bbox[s]);
+    if (bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin) return false;
+    const float4 r0 = __ldg(&rec[(size_t)s * 4]);
+    const float2 r1 = __ldg(reinterpret_cast<const float2*>(&rec[(size_t)s * 4 + 1]));
+    return tri_overlaps_rect({r0.x, r0.y}, {r0.z, r0.w}, {r1.x, r1.y}, rx0, rx1, ry0, ry1);
+  };
   for (int base = 0; base < nslots; base += NT) {
-    const int s = base + tid;
-    bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
-    if (s < nslots) {
-      bb = __ldg(&bbox[s]);
-      hit = !(bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin);
-    }
+    float4 bb = make_float4(0, 0, 0, 0);
+    const bool hit = scan_hit(base + tid, bb);
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     int wbase = 0;
     if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-    if (hit && pos < CAP) { s_slot[pos] = s; s_bbox[pos] = bb; }
+    if (hit && pos < CAP) { s_slot[pos] = base + tid; s_bbox[pos] = bb; }
   }
   __syncthreads();
   const int total = s_count;
@@ -505,19 +539,15 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
     if (tid == 0) s_count = 0;
     __syncthreads();
     for (int base = 0; base < nslots; base += NT) {
-      const int s = base + tid;
-      bool hit = false; float4 bb = make_float4(0, 0, 0, 0);
-      if (s < nslots) {
-        bb = __ldg(&bbox[s]);
-        hit = !(bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin);
-      }
+      float4 bb = make_float4(0, 0, 0, 0);
+      const bool hit = scan_hit(base + tid, bb);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       int wbase = 0;
       if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
       wbase = __shfl_sync(0xffffffffu, wbase, 0);
       if (hit) {
         const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-        s_slot[pos] = s; s_bbox[pos] = bb;
+        s_slot[pos] = base + tid; s_bbox[pos] = bb;
       }
       __syncthreads();
       const int cnt = s_count;
@@ -537,40 +567,37 @@ __global__ void __launch_bounds__(NT, fwd_min_ctas(K, NT)) raster_forward_kernel
   float occ = 1.f, r = 0.f, g = 0.f, bl = 0.f;
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = (size_t)yi * P.W + xi;
-  int* ids = P.topk + (size_t)view * P.K * plane + pix;
-  int n_frag = 0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) n_frag += (key[k] != ~0ull) ? 1 : 0;
-  if (n_frag > P.K) n_frag = P.K;
+  int n_saved = 0;
 #pragma unroll 1
-  for (int k = 0; k < n_frag; ++k) {
-    const unsigned long long k0 = key[0];
-    const float d0 = dk[0];
-#pragma unroll
-    for (int q = 0; q < K - 1; ++q) { key[q] = key[q + 1]; dk[q] = dk[q + 1]; }
-    const int slot = (int)(unsigned)k0;
-    ids[(size_t)k * plane] = slot;
-    if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = d0;
+  for (int k = 0; k < n; ++k) {
+    const float4 e = lA[k * NT];
+    const int bits = __float_as_int(e.y), slot = bits & DBW_FRAG_SLOT_MASK;
+    const float d0 = e.z;
+    if (P.topk) P.topk[((size_t)view * K + k) * plane + pix] = slot;
+    if (P.out_dists) P.out_dists[((size_t)view * K + k) * plane + pix] = d0;
     if (occ == 0.f) continue;     // behind a fully opaque fragment (fine phase: alpha = 1 inside a face): contributes exactly 0
-    Shade s;
-    shade_fragment(P, view, slot, p, s);
-    float a = frag_alpha(d0, P.sigma, P.clip_inside);
-    if (P.faces_alpha) a *= __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]);
-    if (P.face_shade) {          // flat shading: colour = texel * (ambient + diffuse * relu(n . l)) per (view, face)
-      const float* m = P.face_shade + ((size_t)view * P.F + s.t.face) * 3;
-      s.color.x *= __ldg(m); s.color.y *= __ldg(m + 1); s.color.z *= __ldg(m + 2);
+    const float v = lV[k * NT];
+    if (P.frag) {                 // what the backward streams instead of re-deriving geometry: one 16 B record per fragment
+      P.frag[((size_t)view * K + k) * plane + pix] = make_float4(e.y, e.w, v, d0);
+      n_saved = k + 1;
     }
-    if (P.frag) {
-      float4* fs = reinterpret_cast<float4*>(P.frag) + (((size_t)view * P.K + k) * plane + pix) * 2;
-      fs[0] = make_float4(s.u, s.v, d0, s.color.x); fs[1] = make_float4(s.color.y, s.color.z, 0.f, 0.f);
+    const int face = slot >= P.F ? slot - P.F : slot;
+    Texel4 tx;
+    fetch_color(P, e.w, v, __ldg(&P.rec2[(slot_base + slot) * 2 + 1]), tx);
+    float a = frag_alpha(d0, P.sigma, P.clip_inside);
+    if (P.faces_alpha) a *= __ldg(&P.faces_alpha[alpha_index(P, view, face)]);
+    if (P.face_shade) {          // flat shading: colour = texel * (ambient + diffuse * relu(n . l)) per (view, face)
+      const float* m = P.face_shade + ((size_t)view * P.F + face) * 3;
+      tx.color.x *= __ldg(m); tx.color.y *= __ldg(m + 1); tx.color.z *= __ldg(m + 2);
     }
     const float w = occ * a;
-    r += w * s.color.x; g += w * s.color.y; bl += w * s.color.z;
+    r += w * tx.color.x; g += w * tx.color.y; bl += w * tx.color.z;
     occ *= (1.f - a);
   }
-  for (int k = n_frag; k < P.K; ++k) {
-    ids[(size_t)k * plane] = -1;
-    if (P.out_dists) P.out_dists[((size_t)view * P.K + k) * plane + pix] = -1.f;
+  if (P.nfrag) P.nfrag[(size_t)view * plane + pix] = (unsigned char)n_saved;
+  for (int k = n; k < K; ++k) {
+    if (P.topk) P.topk[((size_t)view * K + k) * plane + pix] = -1;
+    if (P.out_dists) P.out_dists[((size_t)view * K + k) * plane + pix] = -1.f;
   }
   float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
   const float fc[3] = {r + occ * P.bg0, g + occ * P.bg1, bl + occ * P.bg2};
@@ -675,41 +702,6 @@ __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride
   }
 }
 
-// Pass-2 aggregation of one layer, keyed by triangle slot: values 0..5 are the distance-path gradient of (x, y) of the three
-// vertices (offsets 0,1, 3,4, 6,7 of the slot's 9 floats), value 6 the gradient of the face's opacity (the face of slot s
-// is s or s - F); g_alpha may be null.  One 8-wide spread reduction serves both.
-__device__ __forceinline__ void warp_agg_add_xya(float* __restrict__ g_tri, float* __restrict__ g_alpha, int F, int key,
-                                                 const float (&v)[7], int lane) {
-  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int lk = __shfl_sync(0xffffffffu, key, leader);
-    const bool mine = (key == lk);
-    const unsigned grp = __ballot_sync(0xffffffffu, mine);
-    float* d = g_tri + (size_t)lk * 9;
-    float* da = g_alpha ? g_alpha + (lk >= F ? lk - F : lk) : nullptr;
-    if (__popc(grp) <= DBW_AGG_MIN) {
-      if (mine) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) if (v[i] != 0.f) atomicAdd(d + i + (i >> 1), v[i]);
-        if (da && v[6] != 0.f) atomicAdd(da, v[6]);
-      }
-    } else {
-      float x[8];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) x[i] = mine ? v[i] : 0.f;
-      x[7] = 0.f;
-      const float r = warp_sum_spread<8>(x, lane);
-      const int idx = lane >> 2;
-      if ((lane & 3) == 0 && r != 0.f) {
-        if (idx < 6) atomicAdd(d + idx + (idx >> 1), r);
-        else if (idx == 6 && da) atomicAdd(da, r);
-      }
-    }
-    todo &= ~grp;
-  }
-}
-
 // Texture-gradient scatter of one fragment: 4 bilinear taps x RGB.  Under magnification (the environment maps seen
 // through a narrow field of view: hundreds of pixels per texel) whole warps hit the same 2x2 texel footprint, so
 // lanes that share the footprint with >= 8 others are reduced (16-wide spread reduction: total i lands in lane 2i and
@@ -746,13 +738,64 @@ __device__ __forceinline__ void warp_tex_scatter(float4* __restrict__ gm, int ke
   }
 }
 
-// One thread per pixel.  Pass 1 walks the K saved fragments front to back, recomputes colour/opacity, scatters the
-// texture gradient and (unless detach_bary) the barycentric-path vertex gradient; pass 2 walks back to front with the
-// division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k) -> faces_alpha and distance -> vertex grads.
-// Loops are warp-uniform (trip count = warp max) so that the aggregation above runs converged.
-template <bool DETACH, bool ALPHA, bool SAVED>
+// Single-value aggregation keyed by an opacity entry: lanes sharing the key are summed with a 5-step butterfly and one lane
+// issues the atomic.  A patch usually sees one or two blocks per layer, so this loop runs once or twice.
+__device__ __forceinline__ void warp_agg_add1(float* __restrict__ dst, int key, float v, int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = (key == lk);
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    float x = mine ? v : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == leader && x != 0.f) atomicAdd(dst + lk, x);
+    todo &= ~grp;
+  }
+}
+
+// Distance-path vertex gradient of one layer, keyed by (triangle slot, closest edge): 4 values = (x, y) of the edge's two
+// vertices.  4-wide spread reduction (5 shuffles): total i lands in lane 8 i and goes to float off[i] of the slot's 9.
+__device__ __forceinline__ void warp_agg_add_edge(float* __restrict__ g_tri, int key, const float (&v)[4], int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = (key == lk);
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    const int edge = lk & 3;
+    // vertex pair of the edge: 0 = (v0, v1), 1 = (v0, v2), 2 = (v1, v2); vertex j's (x, y) live at floats 3j, 3j+1
+    const int ia = edge == 2 ? 3 : 0, ib = edge == 0 ? 3 : 6;
+    float* d = g_tri + (size_t)(lk >> 2) * 9;
+    if (__popc(grp) <= DBW_AGG_MIN) {
+      if (mine) {
+        if (v[0] != 0.f) atomicAdd(d + ia, v[0]);
+        if (v[1] != 0.f) atomicAdd(d + ia + 1, v[1]);
+        if (v[2] != 0.f) atomicAdd(d + ib, v[2]);
+        if (v[3] != 0.f) atomicAdd(d + ib + 1, v[3]);
+      }
+    } else {
+      float x[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[i] = mine ? v[i] : 0.f;
+      const float r = warp_sum_spread<4>(x, lane);
+      const int idx = lane >> 3;
+      if ((lane & 7) == 0 && r != 0.f) atomicAdd(d + (idx < 2 ? ia + idx : ib + idx - 2), r);
+    }
+    todo &= ~grp;
+  }
+}
+
+// One thread per pixel.  Pass 1 streams the pixel's saved fragment records {slot, u, v, signed distance} front to back,
+// re-fetches the four texels of each (the float4 atlas is L2-resident), scatters the texture gradient and -- unless
+// detach_bary -- re-derives the geometry for the barycentric-path vertex gradient (skipped for faces whose vertices are
+// constants); pass 2 walks back to front with the division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k)
+// -> opacity and distance -> vertex gradients.  Loops are warp-uniform (trip count = warp max) so that the aggregation
+// helpers run converged.
+template <bool DETACH, bool ALPHA>
 __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW_BWD_BARY_MINB) raster_backward_kernel(const RasterParams P) {
-  extern __shared__ float s_store[];            // [k][tid] x {alpha, cdot, e, occ}
+  extern __shared__ float4 s_dyn[];             // [k][tid] (alpha, cdot, e, occ), then [k][tid] record bits
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
   const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
@@ -765,76 +808,68 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
   float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
   if (live) { gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane]; }
   if (P.grad_scale) { const float gs = __ldg(P.grad_scale); gr *= gs; gg *= gs; gb *= gs; ga *= gs; }
-  const int* ids = P.topk + (size_t)view * P.K * plane + pix;
-  float* s_alpha = s_store;
-  float* s_cdot = s_store + (size_t)P.K * DBW_BWD_NT;
-  float* s_e = s_store + 2 * (size_t)P.K * DBW_BWD_NT;
-  float* s_occ = s_store + 3 * (size_t)P.K * DBW_BWD_NT;
+  float4* const s_q = s_dyn + tid;
+  int* const s_bits = reinterpret_cast<int*>(s_dyn + (size_t)P.K * DBW_BWD_NT) + tid;
   const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
   const size_t slot_base = (size_t)view * 2 * P.F;
+  const float4* frag = P.frag + (size_t)view * P.K * plane + pix;
 
-  // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count, so that the
-  // aggregation helpers run converged); the id of layer k+1 is prefetched while layer k is processed
+  // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count); the record of
+  // layer k+1 is prefetched while layer k is processed
+  int n_px = any_grad ? (int)P.nfrag[(size_t)view * plane + pix] : 0;
+  int n_warp = n_px;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n_warp = max(n_warp, __shfl_xor_sync(0xffffffffu, n_warp, o));
   int n = 0;
-  int slot_next = any_grad ? ids[0] : -1;
-  int n_warp = 0;
   float occ = 1.f;
-  for (int k = 0; k < P.K; ++k) {
-    const int slot = slot_next;
-    if (!__any_sync(0xffffffffu, slot >= 0)) break;
-    n_warp = k + 1;
-    slot_next = (slot >= 0 && k + 1 < P.K) ? ids[(size_t)(k + 1) * plane] : -1;
+  float4 rec_next = n_px > 0 ? frag[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < n_warp; ++k) {
+    const float4 fr = rec_next;
+    const bool have = k < n_px && occ != 0.f;      // everything behind a fully opaque fragment has zero weight and zero gradient
+    if (k + 1 < n_px && occ != 0.f) rec_next = frag[(size_t)(k + 1) * plane];
     int key = -1, ckey = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
     float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float gc9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float tv[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (slot >= 0 && occ == 0.f) slot_next = -1;   // everything behind a fully opaque fragment has zero weight and zero gradient
-    if (slot >= 0 && occ != 0.f) {
+    if (have) {
       n = k + 1;
+      const int bits = __float_as_int(fr.x), slot = bits & DBW_FRAG_SLOT_MASK;
+      const int face = slot >= P.F ? slot - P.F : slot;
+      const float d = fr.w;
+      Texel4 tx;
       Shade s;
-      float d, e, fa, a, cdot;
-      if (SAVED) {
-        // stream the fragment's saved state (7 coalesced planar loads) instead of re-deriving geometry and texels
-        const float4* fs = reinterpret_cast<const float4*>(P.frag) + (((size_t)view * P.K + k) * plane + pix) * 2;
-        const float4 f0 = fs[0], f1 = fs[1];
-        s.u = f0.x; s.v = f0.y; d = f0.z;
-        s.color = {f0.w, f1.x, f1.y};
-        s.t.face = slot >= P.F ? slot - P.F : slot;
+      const bool bary_path = !DETACH && face >= P.n_static_faces;
+      if (bary_path) {
+        shade_geometry(P, view, slot, p, s);
+        fetch_color(P, s.u, s.v, s.q1, tx);
       } else {
-        shade_fragment(P, view, slot, p, s);
-        if (s.b.inside && P.clip_inside) d = -1.f;
-        else { d = tri_dist2(p, s.t); if (s.b.inside) d = -d; }
+        fetch_color(P, fr.y, fr.z, __ldg(&P.rec2[(slot_base + slot) * 2 + 1]), tx);
       }
-      e = frag_alpha(d, P.sigma, P.clip_inside);
-      fa = ALPHA ? __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + s.t.face]) : 1.f;
-      a = e * fa;
-      cdot = s.color.x * gr + s.color.y * gg + s.color.z * gb;
-      s_alpha[k * DBW_BWD_NT + tid] = a; s_cdot[k * DBW_BWD_NT + tid] = cdot; s_e[k * DBW_BWD_NT + tid] = e;
-      s_occ[k * DBW_BWD_NT + tid] = occ;
+      const float e = frag_alpha(d, P.sigma, P.clip_inside);
+      const float fa = ALPHA ? __ldg(&P.faces_alpha[alpha_index(P, view, face)]) : 1.f;
+      const float a = e * fa;
+      const float cdot = tx.color.x * gr + tx.color.y * gg + tx.color.z * gb;
+      s_q[k * DBW_BWD_NT] = make_float4(a, cdot, e, occ);
+      s_bits[k * DBW_BWD_NT] = bits;
       const float w = occ * a;                 // d RGB / d colour_k
       if (w != 0.f) {
         const float gcx = w * gr, gcy = w * gg, gcz = w * gb;
         if (P.g_maps4) {
-          if (SAVED) {
-            const float4 q1 = __ldg(&P.rec2[(slot_base + slot) * 2 + 1]);      // map offset / size of the face
-            const int hw = __float_as_int(q1.w);
-            s.tap = tex_tap(s.u, s.v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
-          }
-          tkey = s.tap.i00; t01 = s.tap.i01; t10 = s.tap.i10; t11 = s.tap.i11;
-          tv[0] = gcx * s.tap.w00; tv[1] = gcy * s.tap.w00; tv[2] = gcz * s.tap.w00;
-          tv[3] = gcx * s.tap.w01; tv[4] = gcy * s.tap.w01; tv[5] = gcz * s.tap.w01;
-          tv[6] = gcx * s.tap.w10; tv[7] = gcy * s.tap.w10; tv[8] = gcz * s.tap.w10;
-          tv[9] = gcx * s.tap.w11; tv[10] = gcy * s.tap.w11; tv[11] = gcz * s.tap.w11;
+          tkey = tx.tap.i00; t01 = tx.tap.i01; t10 = tx.tap.i10; t11 = tx.tap.i11;
+          tv[0] = gcx * tx.tap.w00; tv[1] = gcy * tx.tap.w00; tv[2] = gcz * tx.tap.w00;
+          tv[3] = gcx * tx.tap.w01; tv[4] = gcy * tx.tap.w01; tv[5] = gcz * tx.tap.w01;
+          tv[6] = gcx * tx.tap.w10; tv[7] = gcy * tx.tap.w10; tv[8] = gcz * tx.tap.w10;
+          tv[9] = gcx * tx.tap.w11; tv[10] = gcy * tx.tap.w11; tv[11] = gcz * tx.tap.w11;
         }
-        if (!DETACH) {
+        if (bary_path && P.g_tri) {
           // colour -> (ix, iy) -> (u, v) -> barycentrics -> vertices  (grid_sample backward + A6)
-          const float fx0 = (float)s.tap.x0, fy0 = (float)s.tap.y0;
-          const float ex = fx0 + 1.f - s.tap.ix, wx = s.tap.ix - fx0, ey = fy0 + 1.f - s.tap.iy, wy = s.tap.iy - fy0;
-          const float d00 = s.c00.x * gcx + s.c00.y * gcy + s.c00.z * gcz, d01 = s.c01.x * gcx + s.c01.y * gcy + s.c01.z * gcz;
-          const float d10 = s.c10.x * gcx + s.c10.y * gcy + s.c10.z * gcz, d11 = s.c11.x * gcx + s.c11.y * gcy + s.c11.z * gcz;
+          const float fx0 = (float)tx.tap.x0, fy0 = (float)tx.tap.y0;
+          const float ex = fx0 + 1.f - tx.tap.ix, wx = tx.tap.ix - fx0, ey = fy0 + 1.f - tx.tap.iy, wy = tx.tap.iy - fy0;
+          const float d00 = tx.c00.x * gcx + tx.c00.y * gcy + tx.c00.z * gcz, d01 = tx.c01.x * gcx + tx.c01.y * gcy + tx.c01.z * gcz;
+          const float d10 = tx.c10.x * gcx + tx.c10.y * gcy + tx.c10.z * gcz, d11 = tx.c11.x * gcx + tx.c11.y * gcy + tx.c11.z * gcz;
           const float gix = (d01 - d00) * ey + (d11 - d10) * wy;
           const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
-          const float gu = gix * s.tap.mx, gv = giy * s.tap.my;
+          const float gu = gix * tx.tap.mx, gv = giy * tx.tap.my;
           f3 gbu = {gu * s.uv01.x + gv * s.uv01.y, gu * s.uv01.z + gv * s.uv01.w, gu * s.u2 + gv * s.v2};
           const size_t gs = slot_base + slot;
           f3 gbc = gbu;
@@ -864,51 +899,54 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
     }
     if (P.g_maps4) warp_tex_scatter(P.g_maps4, tkey, t01, t10, t11, tv, lane);
     if (!DETACH) {
-      warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
+      if (__ballot_sync(0xffffffffu, key >= 0)) warp_agg_add<9>(P.g_tri + slot_base * 9, 9, key, gv9, lane);
       if (__ballot_sync(0xffffffffu, ckey >= 0)) warp_agg_add<9>(P.g_conv + slot_base * 9, 9, ckey, gc9, lane);
     }
   }
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
+  const bool want_alpha = ALPHA && P.g_faces_alpha != nullptr;
+  const bool want_dist = P.sigma > 0.f && P.g_tri != nullptr;
+  if (!want_alpha && !want_dist) return;
   for (int k = n_warp - 1; k >= 0; --k) {
-    int key = -1;
-    float gv7[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // (x, y) of the three vertices, then the face opacity
+    int akey = -1, vkey = -1;
+    float aval = 0.f;
+    float gv4[4] = {0.f, 0.f, 0.f, 0.f};        // (x, y) of the two vertices of the closest edge
     if (k < n) {
-      const float a = s_alpha[k * DBW_BWD_NT + tid], cdot = s_cdot[k * DBW_BWD_NT + tid], e = s_e[k * DBW_BWD_NT + tid];
-      const float occ_k = s_occ[k * DBW_BWD_NT + tid];
-      const float g_alpha = occ_k * (cdot - Tacc);
-      Tacc = a * cdot + (1.f - a) * Tacc;
+      const float4 q = s_q[k * DBW_BWD_NT];      // (alpha, cdot, e, occ)
+      const float g_alpha = q.w * (q.y - Tacc);
+      Tacc = q.x * q.y + (1.f - q.x) * Tacc;
       if (g_alpha != 0.f) {
-        const int slot = ids[(size_t)k * plane];
-        const size_t gs = slot_base + slot;
-        const TriGeom t = unpack_tri(__ldg(&P.rec[gs * 4]), __ldg(&P.rec[gs * 4 + 1]), __ldg(&P.rec[gs * 4 + 2]), __ldg(&P.rec[gs * 4 + 3]));
-        float fa = 1.f;
-        if (ALPHA) {
-          fa = __ldg(&P.faces_alpha[(size_t)view * P.alpha_stride + t.face]);
-          if (P.g_faces_alpha) { key = slot; gv7[6] = g_alpha * e; }
-        }
-        if (P.sigma > 0.f && P.g_tri) {
-          Bary b;
-          if (SAVED) b.inside = P.frag[(((size_t)view * P.K + k) * plane + pix) * 8 + 2] < 0.f;   // sign of the saved distance
-          else b = eval_bary(p, t, P.persp, P.clipb);
-          float g_sd = 0.f;           // gradient w.r.t. the SIGNED squared distance
-          if (P.clip_inside) { if (!b.inside) g_sd = g_alpha * fa * (-e / P.sigma); }   // clamp(d, 0): flat inside the face
-          else g_sd = g_alpha * fa * (-e * (1.f - e) / P.sigma);
-          const float g_dist = b.inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
+        const int bits = s_bits[k * DBW_BWD_NT], slot = bits & DBW_FRAG_SLOT_MASK;
+        const int face = slot >= P.F ? slot - P.F : slot;
+        if (want_alpha) { akey = alpha_index(P, view, face); aval = g_alpha * q.z; }
+        if (want_dist) {
+          // gradient w.r.t. the SIGNED squared distance: alpha = e(d) * fa, so fa * e = alpha
+          const float sd = frag[(size_t)k * plane].w;
+          const bool inside = sd < 0.f;
+          float g_sd = 0.f;
+          if (P.clip_inside) { if (!inside) g_sd = g_alpha * (-q.x / P.sigma); }          // clamp(d, 0): flat inside the face
+          else g_sd = g_alpha * (-q.x * (1.f - q.z) / P.sigma);
+          const float g_dist = inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
           if (g_dist != 0.f) {
-            f2 g0 = {0.f, 0.f}, g1 = {0.f, 0.f}, g2 = {0.f, 0.f};
-            tri_dist_backward(p, t, g_dist, g0, g1, g2);
-            key = slot;
-            gv7[0] = g0.x; gv7[1] = g0.y; gv7[2] = g1.x; gv7[3] = g1.y; gv7[4] = g2.x; gv7[5] = g2.y;
+            const int edge = (bits >> DBW_FRAG_EDGE_SHIFT) & 3;
+            const size_t gs = slot_base + slot;
+            const float4 r0 = __ldg(&P.rec[gs * 4]), r3 = __ldg(&P.rec[gs * 4 + 3]);
+            const float2 r1 = __ldg(reinterpret_cast<const float2*>(&P.rec[gs * 4 + 1]));
+            const f2 v0 = {r0.x, r0.y}, v1 = {r0.z, r0.w}, v2 = {r1.x, r1.y};
+            const f2 ea = edge == 2 ? v1 : v0, eb = edge == 0 ? v1 : v2;
+            const float il = edge == 0 ? r3.y : (edge == 1 ? r3.z : r3.w);
+            f2 g_a = {0.f, 0.f}, g_b = {0.f, 0.f};
+            seg_backward(p, ea, eb, il, g_dist, g_a, g_b);
+            vkey = slot * 4 + edge;
+            gv4[0] = g_a.x; gv4[1] = g_a.y; gv4[2] = g_b.x; gv4[3] = g_b.y;
           }
         }
       }
     }
-    // one aggregation per layer for both gradients (the opacity rides in the spare lane group of the 8-wide reduction)
-    if (__ballot_sync(0xffffffffu, key >= 0))
-      warp_agg_add_xya(P.g_tri ? P.g_tri + slot_base * 9 : nullptr,
-                       (ALPHA && P.g_faces_alpha) ? P.g_faces_alpha + (size_t)view * P.alpha_stride : nullptr, P.F, key, gv7, lane);
+    if (want_alpha && __ballot_sync(0xffffffffu, akey >= 0)) warp_agg_add1(P.g_faces_alpha, akey, aval, lane);
+    if (want_dist && __ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_edge(P.g_tri + slot_base * 9, vkey, gv4, lane);
   }
 }
 
@@ -1072,20 +1110,29 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   RasterParams P;
   memset(&P, 0, sizeof(P));
   P.B = s.n_views; P.H = s.height; P.W = s.width; P.K = s.faces_per_pixel; P.V = s.n_verts; P.F = s.n_faces; P.M = s.n_maps;
-  P.alpha_stride = s.alpha_view_stride;
-  P.sigma = s.sigma; P.blur = s.blur_radius; P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
+  P.alpha_stride = s.alpha_view_stride; P.inv_alpha_group = 1.f / (float)(s.alpha_group > 0 ? s.alpha_group : 1);
+  P.n_static_faces = s.n_static_faces;
+  P.sigma = s.sigma; P.blur = s.blur_radius; P.sqrt_blur = sqrtf(s.blur_radius); P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
-  P.maps4 = w.maps4; P.faces_alpha = faces_alpha; P.frag = s.save_fragment_state ? w.frag : nullptr;
+  P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
+  P.frag = s.save_fragment_state ? w.frag : nullptr; P.nfrag = s.save_fragment_state ? w.nfrag : nullptr;
   return P;
 }
 
-template <int K>
-static void launch_forward(const RasterParams& P, cudaStream_t st) {
-  constexpr int NT = K <= 4 ? DBW_FWD_NT_SMALLK : DBW_FWD_NT;
+// dynamic shared memory of the raster kernels: K list entries (forward) / K saved scalars (backward) of 20 B per thread
+static size_t frag_smem_bytes(int K, int NT) { return (size_t)K * NT * (sizeof(float4) + sizeof(float)); }
+
+template <int NT>
+static cudaError_t launch_forward(const RasterParams& P, cudaStream_t st) {
   const dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16), P.B);
-  if (P.ep_target) raster_forward_kernel<K, NT, true><<<grid, NT, 0, st>>>(P);
-  else raster_forward_kernel<K, NT, false><<<grid, NT, 0, st>>>(P);
+  const size_t smem = frag_smem_bytes(P.K, NT);
+  auto go = [&](auto kern) -> cudaError_t {
+    if (smem > 40 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+    kern<<<grid, NT, smem, st>>>(P);
+    return cudaSuccess;
+  };
+  return P.ep_target ? go(raster_forward_kernel<NT, true>) : go(raster_forward_kernel<NT, false>);
 }
 
 extern "C" int dbw_render_forward(const DbwRenderSettings* s, const float* verts, const int32_t* faces, const float* faces_uvs,
@@ -1128,7 +1175,7 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
                                size_t workspace_bytes, const float* face_shade, float* out_dists, const DbwLossEpilogue* ep,
                                void* stream) {
   if (validate(s)) return -1;
-  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba || !topk_ids || !workspace)
+  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !out_rgba || !workspace)
     return fail("dbw_render_forward: null pointer argument");
   if (!s->verts_are_ndc && (!R || !T)) return fail("dbw_render_forward: R and T are required unless verts_are_ndc");
   Workspace w = carve(*s, workspace);
@@ -1165,14 +1212,11 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
     P.ep_partials = ep->loss_partials; P.ep_inv_count = ep->inv_count; P.ep_part_mask = ep->n_partials - 1;
   }
   const int K = s->faces_per_pixel;
-  ScopedTimer timer(0, K, st);
-  if (K <= 1) launch_forward<1>(P, st);
-  else if (K <= 4) launch_forward<4>(P, st);
-  else if (K <= 10) launch_forward<10>(P, st);
-  else if (K <= 16) launch_forward<16>(P, st);
-  else if (K <= 25) launch_forward<25>(P, st);
-  else if (K <= 32) launch_forward<32>(P, st);
-  else launch_forward<64>(P, st);
+  {
+    ScopedTimer timer(0, K, st);
+    const cudaError_t e = K <= 4 ? launch_forward<DBW_FWD_NT_SMALLK>(P, st) : launch_forward<DBW_FWD_NT>(P, st);
+    if (e != cudaSuccess) return fail("raster_forward_kernel attribute", e);
+  }
   LAUNCH_CK("raster_forward_kernel");
   return 0;
 }
@@ -1194,8 +1238,10 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
                                           float* g_faces_alpha, float* g_maps, void* bwd_scratch, size_t bwd_scratch_bytes,
                                           void* stream) {
   if (validate(s)) return -1;
-  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !topk_ids || !workspace || !grad_rgba || !bwd_scratch)
+  (void)topk_ids;          // kept in the signature for ABI continuity: the backward streams the workspace's fragment records
+  if (!verts || !faces || !faces_uvs || !face_map || !maps || !map_table || !workspace || !grad_rgba || !bwd_scratch)
     return fail("dbw_render_backward: null pointer argument");
+  if (!s->save_fragment_state) return fail("dbw_render_backward: the forward must run with save_fragment_state = 1");
   Workspace w = carve(*s, (void*)workspace);
   BwdScratch g = carve_bwd(*s, bwd_scratch);
   if (workspace_bytes < w.total || bwd_scratch_bytes < g.total) return fail("dbw_render_backward: workspace too small");
@@ -1205,21 +1251,20 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
   CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
-  P.topk = (int*)topk_ids; P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = g.g_tri; P.g_conv = g.g_conv;
+  P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = need_geom ? g.g_tri : nullptr; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16), B);
-  const size_t smem = 4 * (size_t)s->faces_per_pixel * DBW_BWD_NT * sizeof(float);
+  const size_t smem = frag_smem_bytes(s->faces_per_pixel, DBW_BWD_NT);
   {
     auto launch = [&](auto kern) -> cudaError_t {
-      if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+      if (smem > 40 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
       ScopedTimer timer(1, s->faces_per_pixel, st);
       kern<<<grid, DBW_BWD_NT, smem, st>>>(P);
       return cudaSuccess;
     };
-    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr, sv = det && s->save_fragment_state;
-    cudaError_t e = sv  ? (al ? launch(raster_backward_kernel<true, true, true>) : launch(raster_backward_kernel<true, false, true>))
-                  : det ? (al ? launch(raster_backward_kernel<true, true, false>) : launch(raster_backward_kernel<true, false, false>))
-                        : (al ? launch(raster_backward_kernel<false, true, false>) : launch(raster_backward_kernel<false, false, false>));
+    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr;
+    cudaError_t e = det ? (al ? launch(raster_backward_kernel<true, true>) : launch(raster_backward_kernel<true, false>))
+                        : (al ? launch(raster_backward_kernel<false, true>) : launch(raster_backward_kernel<false, false>));
     if (e != cudaSuccess) return fail("raster_backward_kernel attribute", e);
   }
   LAUNCH_CK("raster_backward_kernel");

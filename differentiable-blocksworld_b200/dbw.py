@@ -117,6 +117,7 @@ class DifferentiableBlocksWorld(nn.Module):
         self.n_total_views = None         # data-parallel context (parallel.py): views of the whole step
         self.noise_generator = None       # RNG shared by all ranks for opacity noise / overlap samples
         self.opacity_noise_buffer = None  # pre-drawn randn (N,) used instead of drawing inside forward (graph.py)
+        self.overlap_samples_buffer = None  # pre-drawn U(0,1) (N,1000,3) for the overlap term, likewise
         self._static = None
         self._env_stream = None
         self._reg_state_stale = False
@@ -192,6 +193,9 @@ class DifferentiableBlocksWorld(nn.Module):
         return deepcopy(self._init_kwargs)
 
     def set_perceptual_loss(self, fn):
+        """fn(imgs, rec) -> scalar: an nn.Module (registered, follows .to() / state_dict) or any callable"""
+        if isinstance(getattr(self, 'perceptual_loss', None), nn.Module) and not isinstance(fn, nn.Module):
+            del self.perceptual_loss
         self.perceptual_loss = fn
 
     def set_cur_epoch(self, epoch):
@@ -251,7 +255,7 @@ class DifferentiableBlocksWorld(nn.Module):
             if not hard_filter:
                 alpha = torch.cat([torch.ones(self.env_n_faces, device=R.device), self._alpha.repeat_interleave(self.BNF)])
             return renderer(scene.extend(B), R=R, T=T, faces_alpha=alpha), None
-        if self.static_topology and self.fused_scene and R.is_cuda:
+        if self._fused_scene_ok(R):
             return self._render_decoupled_fused(R, T, hard_filter, renderer)
         env = join_meshes_as_scene([self.build_bkg(world_coord=True), self.build_ground(world_coord=True)])
         env_rgba = self.renderer_env(env.extend(B), R=R, T=T)
@@ -265,11 +269,18 @@ class DifferentiableBlocksWorld(nn.Module):
         alpha = None if hard_filter else self._alpha.repeat_interleave(self.BNF)
         return env_rgba, renderer(blocks.extend(B), R=R, T=T, faces_alpha=alpha)
 
+    def _fused_scene_ok(self, ref):
+        """the fused scene kernels apply: static topology on the GPU, and a box decimation the texture-prep kernel has
+        (factor 8, the value of every shipped config; others go through the eager F.avg_pool2d path of _maps)"""
+        decim_live = self.training and self.is_live('decimate_txt')
+        return (self.static_topology and self.fused_scene and ref.is_cuda and (not decim_live or self.decim_factor in (1, 8)))
+
     @staticmethod
-    def _raster(r, verts, faces, fvu, fmap, maps, table, R, T, alpha, texels4):
+    def _raster(r, verts, faces, fvu, fmap, maps, table, R, T, alpha, texels4, alpha_group=1, n_static_faces=0):
         return render_scene(verts, faces, fvu, fmap, maps, table, R, T, r.cameras.intrinsics(), r.img_size, r.sigma,
                             r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color, alpha,
-                            r.perspective_correct, blur_radius=r.blur_radius, maps_are_texels4=texels4)
+                            r.perspective_correct, blur_radius=r.blur_radius, maps_are_texels4=texels4,
+                            alpha_group=alpha_group, n_static_faces=n_static_faces)
 
     @staticmethod
     def _composite(env_rgba, fg_rgba):
@@ -350,7 +361,7 @@ class DifferentiableBlocksWorld(nn.Module):
         atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
         rows, cols = atlas.shape[1], atlas.shape[2]
         table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
-        alpha = None if hard_filter else self._alpha[:, None].expand(-1, self.BNF).reshape(-1)
+        alpha = None if hard_filter else self._alpha          # one opacity per block: alpha_group = BNF faces share an entry
         self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
         return (env_verts, env_atlas, env_table), (blk_verts, atlas.reshape(-1, 4), table, fmap, alpha)
 
@@ -366,8 +377,9 @@ class DifferentiableBlocksWorld(nn.Module):
             stream.wait_stream(main)
         with torch.cuda.stream(stream):
             env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
-                                    R, T, None, texels4=True)
-        fg_rgba = self._raster(renderer, blk_verts, st['faces_b'], st['fvu_b'], fmap, atlas, table, R, T, alpha, texels4=True)
+                                    R, T, None, texels4=True, n_static_faces=self.bkg_n_faces)
+        fg_rgba = self._raster(renderer, blk_verts, st['faces_b'], st['fvu_b'], fmap, atlas, table, R, T, alpha, texels4=True,
+                               alpha_group=self.BNF)
         if stream is not main:
             main.wait_stream(stream)
             env_rgba.record_stream(main)
@@ -375,7 +387,7 @@ class DifferentiableBlocksWorld(nn.Module):
 
     def _fused_loss_ok(self, imgs):
         """the loss epilogue of the rasterizer applies: decoupled static scene on the GPU, plain MSE, nothing else reads `rec`"""
-        return (self.fused_loss and self.decouple_rendering and self.static_topology and self.fused_scene and imgs.is_cuda
+        return (self.fused_loss and self.decouple_rendering and self._fused_scene_ok(imgs)
                 and isinstance(self.criterion, nn.MSELoss) and 'rgb' in self.loss_weights
                 and not ('perceptual' in self.loss_weights and self.perceptual_loss is not None))
 
@@ -387,8 +399,9 @@ class DifferentiableBlocksWorld(nn.Module):
         (env_verts, env_atlas, env_table), (blk_verts, atlas, table, fmap, alpha) = self._scene_tensors(hard_filter)
         key = (id(renderer), id(st['faces_b']), tuple(env_table), tuple(table))
         if self._passes is None or self._passes[0] != key:
-            self._passes = (key, ScenePass(st['faces_e'], st['fvu_e'], st['fmap_e'], env_table, self.renderer_env),
-                            ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer))
+            self._passes = (key, ScenePass(st['faces_e'], st['fvu_e'], st['fmap_e'], env_table, self.renderer_env,
+                                           n_static_faces=self.bkg_n_faces),
+                            ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer, alpha_group=self.BNF))
         return scene_mse(env_verts, env_atlas, blk_verts, atlas, alpha, inp['R'], inp['T'], inp['imgs'], self._passes[1],
                          self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']))
 
@@ -565,7 +578,7 @@ class DifferentiableBlocksWorld(nn.Module):
         if 'overlap' in w:
             S, R, T = self._blocks_SRT
             terms['overlap'] = w['overlap'] * L.overlap(S, R, T, *self._blocks_eps, self._alpha_full, self.ratio_block_scene,
-                                                        coarse, generator=self.noise_generator)
+                                                        coarse, generator=self.noise_generator, unit_samples=self.overlap_samples_buffer)
         vals = list(terms.values())
         total = vals[0] if vals else torch.zeros((), device=imgs.device)
         for v in vals[1:]:
@@ -592,34 +605,117 @@ class DifferentiableBlocksWorld(nn.Module):
 
     @torch.no_grad()
     def quantitative_eval(self, loader, device, hard_inference=True):
-        """PSNR of hard renders over a loader (the SSIM / LPIPS columns of dbw.py:464-493 need networks out of scope)"""
+        """the columns of final_scores.tsv (dbw.py:464-493): n_blocks, L_tot, L_rec, PSNR, SSIM, LPIPS, alpha_k -- hard 4x
+        supersampled renders of the opaque blocks over a loader.  LPIPS is NaN when no perceptual network is installed."""
         self.eval()
         opacities = self.get_opacities()
         scene = self.build_scene(filter_transparent=True)
-        total, count = 0.0, 0
+        perceptual = getattr(self, 'perceptual_loss', None)
+        sums, count = dict(L_tot=0.0, L_rec=0.0, PSNR=0.0, SSIM=0.0, LPIPS=0.0), 0
         for inp, labels in loader:
             inp = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inp.items()}
             self._install_cameras(inp)
-            n = len(inp['imgs'])
+            imgs, n = inp['imgs'], len(inp['imgs'])
             rec = (self.renderer(scene.extend(n), inp['R'], inp['T'], viz_purpose=True)[:, :3] if hard_inference
                    else self.predict(inp, labels, filter_transparent=True))
-            total += float(-10.0 * torch.log10(F.mse_loss(inp['imgs'], rec))) * n
+            losses = self.compute_losses(imgs, rec)
+            sums['L_tot'] += float(losses['total']) * n
+            sums['L_rec'] += float(sum(losses[k] for k in ('rgb', 'perceptual') if k in losses)) * n
+            sums['PSNR'] += float(-10.0 * torch.log10(F.mse_loss(imgs, rec))) * n
+            sums['SSIM'] += float(L.ssim(imgs, rec).mean()) * n
+            sums['LPIPS'] += (float(perceptual(imgs, rec)) if perceptual is not None else float('nan')) * n
             count += n
-        return OrderedDict([('n_blocks', int((opacities > 0.5).sum())), ('PSNR', total / max(count, 1))]
+        return OrderedDict([('n_blocks', int((opacities > 0.5).sum()))] + [(k, v / max(count, 1)) for k, v in sums.items()]
                            + [(f'alpha{k}', a.item()) for k, a in enumerate(opacities)])
+
+    @torch.no_grad()
+    def qualitative_eval(self, loader, device, path=None, NV=240, n_inputs=10):
+        """the still images and meshes of dbw.py:495-554: texture maps, the scene as OBJ (with and without background), and
+        per input view the hard reconstruction, its block-coloured edge overlays and the lit synthetic-colour render.
+        The reference's mp4 trajectories (NV frames through imageio / ffmpeg) and the ground-truth point-cloud PLY are
+        export paths outside the render hot path and are not written."""
+        from pathlib import Path
+        path = Path(path) if path is not None else Path('.')
+        path.mkdir(parents=True, exist_ok=True)
+        self.eval()
+        (path / 'textures').mkdir(exist_ok=True)
+        _save_png(torch.sigmoid(self.texture_bkg).permute(0, 3, 1, 2)[0], path / 'textures' / 'bkg.png')
+        _save_png(torch.sigmoid(self.texture_ground).permute(0, 3, 1, 2)[0], path / 'textures' / 'ground.png')
+        for k, img in enumerate(torch.sigmoid(self.textures).permute(0, 3, 1, 2)):
+            _save_png(img, path / 'textures' / f'block_{str(k).zfill(2)}.png')
+        meshes = self.build_scene(filter_transparent=True)
+        _save_obj(meshes, path / 'mesh_full.obj')
+        _save_obj(self.build_scene(filter_transparent=True, w_bkg=False, reduce_ground=True), path / 'mesh.obj')
+        syn_blocks = self.build_blocks(filter_transparent=True, synthetic_colors=True, as_scene=True)
+        if len(syn_blocks) == 0:
+            return None
+        colors = self.get_scene_face_colors(filter_transparent=True, w_env=False)
+        count, n_zeros = 0, int(np.log10(max(n_inputs - 1, 1))) + 1
+        for inp, labels in loader:
+            if count >= n_inputs:
+                break
+            inp = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inp.items()}
+            self._install_cameras(inp)
+            for k in range(min(len(inp['imgs']), n_inputs - count)):
+                tag = str(count).zfill(n_zeros)
+                img, R, T = inp['imgs'][k:k + 1], inp['R'][k:k + 1], inp['T'][k:k + 1]
+                _save_png(img[0], path / f'{tag}_inp.png')
+                rec = self.renderer(meshes, R, T, viz_purpose=True)[:, :3]
+                _save_png(rec[0], path / f'{tag}_rec.png')
+                _save_png(self.renderer.draw_edges(rec, syn_blocks, R, T, colors)[0], path / f'{tag}_rec_col.png')
+                _save_png(self.renderer.draw_edges(img, syn_blocks, R, T, colors)[0], path / f'{tag}_rec_col_inp.png')
+                syn = self.renderer_light(syn_blocks, R, T, viz_purpose=True)[:, :3]
+                _save_png(syn[0], path / f'{tag}_rec_syn_nobkg.png')
+                _save_png(self.renderer_light.draw_edges(syn, syn_blocks, R, T, linewidth=0.7, colors=(0.3, 0.3, 0.3))[0],
+                          path / f'{tag}_rec_syn_nobkg_edged.png')
+                count += 1
+        return count
+
+
+def _save_png(chw, path):
+    from PIL import Image
+    arr = (chw.detach().float().clamp(0, 1) * 255).permute(1, 2, 0).cpu().numpy().astype(np.uint8)
+    Image.fromarray(arr).convert('RGB').save(path)
+
+
+def _save_obj(meshes, path):
+    """geometry-only Wavefront OBJ of the first mesh (the reference's textured export goes through PyTorch3D's save_obj)"""
+    verts, faces = meshes.get_mesh_verts_faces(0)
+    with open(path, 'w') as fh:
+        for v in verts.detach().cpu().tolist():
+            fh.write('v {:.6f} {:.6f} {:.6f}\n'.format(*v))
+        for f in (faces.detach().cpu() + 1).tolist():
+            fh.write('f {} {} {}\n'.format(*f))
+
+
+class PerceptualTerm(nn.Module):
+    """`LPIPSLoss` of the reference (src/model/loss.py:32-40): a FROZEN LPIPS network as a registered submodule (moved by
+    .to(), present in the state_dict as `perceptual_loss.*`), called as net(imgs, rec, normalize=True).mean().  The network
+    itself is a VGG16 conv stack (cuDNN / tensor cores): outside the render hot path."""
+
+    def __init__(self, net):
+        super().__init__()
+        self.loss = net
+        for p in self.loss.parameters():
+            p.requires_grad_(False)
+
+    def forward(self, imgs, rec):
+        return self.loss(imgs, rec, normalize=True).mean()
 
 
 def _make_perceptual(name):
-    try:
-        import lpips  # noqa: F401  (not in this image)
-    except ImportError:
-        print(f'[dbw_b200] perceptual loss "{name}" needs the `lpips` package and VGG weights, which are not available '
-              f'here; the term is reported as 0 until set_perceptual_loss() installs a callable')
-        return None
+    """the perceptual term's network, or None (with a LOUD warning: every shipped config weighs it 0.1) when `lpips` and its
+    VGG weights are not available -- set_perceptual_loss() installs any callable / module instead"""
     if name != 'lpips':
         raise NotImplementedError(name)
-    net = lpips.LPIPS(net='vgg')
-    return lambda imgs, rec: net(imgs, rec, normalize=True).mean()
+    try:
+        import lpips
+        return PerceptualTerm(lpips.LPIPS(net='vgg', verbose=False))
+    except (ImportError, NotImplementedError, OSError) as exc:
+        import warnings
+        warnings.warn(f'[dbw_b200] perceptual_weight > 0 but the LPIPS network is unavailable ({exc}): the perceptual term is '
+                      f'DROPPED from the objective (reported as 0) until set_perceptual_loss() installs one', RuntimeWarning)
+        return None
 
 
 def create_model(cfg, img_size, **kwargs):

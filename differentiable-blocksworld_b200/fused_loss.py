@@ -25,17 +25,18 @@ N_PARTIALS = 1024
 class ScenePass:
     """static description of one render pass: topology, UVs, map layout and the renderer's shading options"""
 
-    def __init__(self, faces, faces_uvs, face_map, map_table_host, renderer):
+    def __init__(self, faces, faces_uvs, face_map, map_table_host, renderer, alpha_group=1, n_static_faces=0):
         self.faces = faces.to(torch.int32).contiguous()
         self.faces_uvs = faces_uvs.contiguous().float()
         self.face_map = face_map.to(torch.int32).contiguous()
         self.map_table_host, self.r = map_table_host, renderer
+        self.alpha_group, self.n_static_faces = alpha_group, n_static_faces
 
     def settings(self, verts, maps, B, faces_alpha):
         r = self.r
         return scene_settings(verts, self.faces, maps, self.map_table_host, B, r.cameras.intrinsics(), r.img_size, r.sigma,
                               r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color, faces_alpha,
-                              r.perspective_correct, False, r.blur_radius, True)
+                              r.perspective_correct, False, r.blur_radius, True, self.alpha_group, self.n_static_faces)
 
 
 def _workspace(cfg, dev):
@@ -59,15 +60,12 @@ class _SceneMSEFn(torch.autograd.Function):
         (cfg_e, table_e), (cfg_b, table_b) = cfgs
         ws_e, bwd_e = _workspace(cfg_e, dev)
         ws_b, bwd_b = _workspace(cfg_b, dev)
-        Ke, Kb = cfg_e.faces_per_pixel, cfg_b.faces_per_pixel
         env_rgba = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)
-        ids_e = torch.empty(B, Ke, H, W, dtype=torch.int32, device=dev)
         _lib.check(L.dbw_render_forward_ex(ctypes.byref(cfg_e), _c(env_verts), _c(env_pass.faces), _c(env_pass.faces_uvs),
                                            _c(env_pass.face_map), _c(env_maps), _c(table_e), _c(R), _c(T), None, _c(env_rgba),
-                                           _c(ids_e), _c(ws_e), ws_e.numel(), None, None, _stream()), 'dbw_render_forward_ex')
+                                           None, _c(ws_e), ws_e.numel(), None, None, _stream()), 'dbw_render_forward_ex')
         g_fg = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)       # d loss / d blocks RGBA (unscaled)
         g_env = torch.empty(B, 4, H, W, dtype=torch.float32, device=dev)      # d loss / d env RGBA (unscaled)
-        ids_b = torch.empty(B, Kb, H, W, dtype=torch.int32, device=dev)
         partials = torch.empty(N_PARTIALS, dtype=torch.float32, device=dev)
         rec = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_rec else None
         ep = DbwLossEpilogue()
@@ -75,11 +73,10 @@ class _SceneMSEFn(torch.autograd.Function):
         ep.rec = rec.data_ptr() if rec is not None else None
         ep.loss_partials, ep.n_partials, ep.inv_count = partials.data_ptr(), N_PARTIALS, float(inv_count)
         _lib.check(L.dbw_render_forward_loss(ctypes.byref(cfg_b), _c(blk_verts), _c(blk_pass.faces), _c(blk_pass.faces_uvs),
-                                             _c(fmap_b), _c(blk_maps), _c(table_b), _c(R), _c(T), _c(fa), _c(g_fg), _c(ids_b),
+                                             _c(fmap_b), _c(blk_maps), _c(table_b), _c(R), _c(T), _c(fa), _c(g_fg), None,
                                              _c(ws_b), ws_b.numel(), ctypes.byref(ep), _stream()), 'dbw_render_forward_loss')
         loss = partials.sum()
-        ctx.save_for_backward(env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ids_e, ids_b,
-                              ws_e, ws_b, g_fg, g_env)
+        ctx.save_for_backward(env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ws_e, ws_b, g_fg, g_env)
         ctx.meta = (env_pass, blk_pass, cfg_e, cfg_b, bwd_e, bwd_b)
         if want_rec:
             ctx.mark_non_differentiable(rec)
@@ -88,15 +85,14 @@ class _SceneMSEFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _g_rec=None):
-        (env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ids_e, ids_b, ws_e, ws_b, g_fg,
-         g_env) = ctx.saved_tensors
+        env_verts, env_maps, blk_verts, blk_maps, fa, R, T, fmap_b, table_e, table_b, ws_e, ws_b, g_fg, g_env = ctx.saved_tensors
         env_pass, blk_pass, cfg_e, cfg_b, bwd_e, bwd_b = ctx.meta
         L = _lib.lib()
         dev = blk_verts.device
         gl = g_loss.detach().contiguous().float()
         need = ctx.needs_input_grad
 
-        def run(cfg, p, fmap, verts, maps, table, alpha, ids, ws, grad, bwd_bytes, need_v, need_m, need_a):
+        def run(cfg, p, fmap, verts, maps, table, alpha, ws, grad, bwd_bytes, need_v, need_m, need_a):
             need_a = need_a and alpha is not None
             g_verts = g_alpha = None
             if need_v and need_a:          # one zero-fill for both small gradients
@@ -111,14 +107,14 @@ class _SceneMSEFn(torch.autograd.Function):
                 return None, None, None
             scratch = torch.empty(bwd_bytes, dtype=torch.uint8, device=dev)
             _lib.check(L.dbw_render_backward_scaled(ctypes.byref(cfg), _c(verts), _c(p.faces), _c(p.faces_uvs), _c(fmap), _c(maps),
-                                                    _c(table), _c(R), _c(T), _c(alpha), _c(ids), _c(ws), ws.numel(), _c(grad),
+                                                    _c(table), _c(R), _c(T), _c(alpha), None, _c(ws), ws.numel(), _c(grad),
                                                     _c(gl), _c(g_verts), _c(g_alpha), _c(g_maps), _c(scratch), scratch.numel(),
                                                     _stream()), 'dbw_render_backward_scaled')
             return g_verts, g_maps, g_alpha
 
-        gv_b, gm_b, ga_b = run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ids_b, ws_b, g_fg, bwd_b,
+        gv_b, gm_b, ga_b = run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ws_b, g_fg, bwd_b,
                                need[2], need[3], need[4])
-        gv_e, gm_e, _ = run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ids_e, ws_e, g_env, bwd_e,
+        gv_e, gm_e, _ = run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ws_e, g_env, bwd_e,
                             need[0], need[1], False)
         return gv_e, gm_e, gv_b, gm_b, ga_b, None, None, None, None, None, None, None, None, None
 

@@ -8,7 +8,7 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3, capture_all_reduce=False):
+    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3, capture_all_reduce=False, generator=None):
         self.vp, self.model = view_parallel, view_parallel.model
         # optionally capture the gradient all-reduce INTO the graph.  Off by default: with this image's NCCL the captured
         # collective hung on 2 GPUs (measured, round 1), so the all-reduce is issued right after the replay instead.
@@ -17,9 +17,17 @@ class GraphedStep:
         dev = example_inp['imgs'].device
         self.static_inp = {k: v.clone() for k, v in example_inp.items()}
         self.model.n_total_views = n_total_views
-        self.model.opacity_noise_buffer = torch.zeros_like(self.model.alpha_logit)
-        self.gen = torch.Generator(device=dev)
-        self.gen.manual_seed(self.vp.seed)
+        # random inputs of a step are pre-drawn into buffers OWNED BY THIS STEP (a graph captures addresses): the opacity
+        # noise (dbw.py:300-301) and the overlap term's sample points (dbw.py:393).  `generator` is shared by the steps of a
+        # PipelinedGraphedStep so that consecutive steps draw consecutive numbers; every rank seeds it identically.
+        self.noise_buf = torch.zeros_like(self.model.alpha_logit)
+        from .losses import OVERLAP_N_POINTS
+        self.overlap_buf = (torch.zeros(self.model.n_blocks, OVERLAP_N_POINTS, 3, device=dev)
+                            if 'overlap' in self.model.loss_weights else None)
+        self.gen = generator
+        if self.gen is None:
+            self.gen = torch.Generator(device=dev)
+            self.gen.manual_seed(self.vp.seed)
         self.model._install_cameras(self.static_inp)          # the one-off host read of the intrinsics happens here
         self._capture(warmup=warmup)
 
@@ -28,8 +36,13 @@ class GraphedStep:
         m = self.model
         return (m.training, m.is_live('coarse_learning'), m.is_live('decimate_txt'), m.is_live('kill_blocks'))
 
+    def _bind_buffers(self):
+        self.model.opacity_noise_buffer, self.model.overlap_samples_buffer = self.noise_buf, self.overlap_buf
+        self.model.noise_generator = None          # nothing draws inside the captured region
+
     def _capture(self, warmup=1):
         self.phase = self._phase()
+        self._bind_buffers()
         # the parameters (and their AccumulateGrad nodes) were created on the default stream, the capture runs on a side
         # stream: intended, and ordered by the wait_stream calls below -- silence autograd's stream-mismatch warning
         _warn_off = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
@@ -60,7 +73,10 @@ class GraphedStep:
                     self.static_inp[k].copy_(v, non_blocking=non_blocking)
         if self._phase() != self.phase:          # a schedule milestone was crossed (coarse -> fine, decimation off): re-capture
             self._capture()
-        self.model.opacity_noise_buffer.normal_(generator=self.gen)     # identical on every rank (same seed, same count)
+        self._bind_buffers()                       # eager code in between (evaluation, another GraphedStep) may have re-pointed them
+        self.noise_buf.normal_(generator=self.gen)                      # identical on every rank (same seed, same count)
+        if self.overlap_buf is not None:
+            self.overlap_buf.uniform_(generator=self.gen)
         self.graph.replay()
         if not self.capture_all_reduce:
             self.vp.bucket.all_reduce(self.vp.group)
@@ -73,7 +89,10 @@ class PipelinedGraphedStep:
     the losses of the step that consumed `host_inp`."""
 
     def __init__(self, view_parallel, example_inp, n_total_views, capture_all_reduce=False):
-        self.steps = [GraphedStep(view_parallel, example_inp, n_total_views, capture_all_reduce=capture_all_reduce) for _ in range(2)]
+        gen = torch.Generator(device=example_inp['imgs'].device)
+        gen.manual_seed(view_parallel.seed)
+        self.steps = [GraphedStep(view_parallel, example_inp, n_total_views, capture_all_reduce=capture_all_reduce, generator=gen)
+                      for _ in range(2)]
         self.copy_stream = torch.cuda.Stream()
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]      # inputs of buffer b have landed
         self.free = [torch.cuda.Event(), torch.cuda.Event()]       # buffer b has been consumed by its replay

@@ -58,7 +58,8 @@ class _RenderFn(torch.autograd.Function):
     """autograd seam over dbw_render_forward / dbw_render_backward (include/dbw_render.h)."""
 
     @staticmethod
-    def forward(ctx, verts, maps, faces_alpha, R, T, faces, faces_uvs, face_map, map_table, cfg, face_shade=None, want_dists=False):
+    def forward(ctx, verts, maps, faces_alpha, R, T, faces, faces_uvs, face_map, map_table, cfg, face_shade=None, want_dists=False,
+                want_ids=False):
         if not verts.is_cuda:
             raise DbwError('the B200 renderer needs CUDA tensors (there is no CPU fallback)')
         s = cfg
@@ -71,26 +72,32 @@ class _RenderFn(torch.autograd.Function):
         _lib.check(L.dbw_workspace_bytes(ctypes.byref(s), ctypes.byref(fwd), ctypes.byref(bwd)), 'dbw_workspace_bytes')
         ws = torch.empty(fwd.value, dtype=torch.uint8, device=verts.device)
         out = torch.empty(B, 4, H, W, dtype=torch.float32, device=verts.device)
-        ids = torch.empty(B, K, H, W, dtype=torch.int32, device=verts.device)
+        # the per-pixel face ids / distances are diagnostic outputs (render_edges, tests): the backward streams the fragment
+        # records the forward keeps in its workspace (settings.save_fragment_state)
+        ids = torch.empty(B, K, H, W, dtype=torch.int32, device=verts.device) if (want_ids or want_dists) else None
         dists = torch.empty(B, K, H, W, dtype=torch.float32, device=verts.device) if want_dists else None
         shade = face_shade.detach().contiguous().float() if face_shade is not None else None
         _lib.check(L.dbw_render_forward_ex(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
                                            _c(map_table), _c(R), _c(T), _c(fa), _c(out), _c(ids), _c(ws), fwd.value,
                                            _c(shade), _c(dists), _stream()), 'dbw_render_forward_ex')
-        ctx.save_for_backward(verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws)
+        ctx.save_for_backward(verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ws)
         ctx.cfg, ctx.bwd_bytes, ctx.lit = s, bwd.value, shade is not None
-        ctx.mark_non_differentiable(ids)
         if want_dists:
-            ctx.mark_non_differentiable(dists)
+            ctx.mark_non_differentiable(ids, dists)
             return out, ids, dists
-        return out, ids
+        if want_ids:
+            ctx.mark_non_differentiable(ids)
+            return out, ids
+        return out
 
     @staticmethod
-    def backward(ctx, g_out, _g_ids, _g_dists=None):
+    def backward(ctx, g_out, _g_ids=None, _g_dists=None):
         if ctx.lit:
             raise NotImplementedError('flat-shaded (lit) renders are a visualisation path: no backward')
-        verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ids, ws = ctx.saved_tensors
+        verts, maps, fa, R, T, faces, faces_uvs, face_map, map_table, ws = ctx.saved_tensors
         s = ctx.cfg
+        if not s.save_fragment_state:
+            raise DbwError('this render was made with gradients disabled (no fragment records were kept)')
         L = _lib.lib()
         g_out = g_out.contiguous().float()
         need_v, need_m, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and fa is not None
@@ -105,10 +112,10 @@ class _RenderFn(torch.autograd.Function):
         g_maps = torch.zeros_like(maps) if need_m else None
         scratch = torch.empty(ctx.bwd_bytes, dtype=torch.uint8, device=verts.device)
         _lib.check(L.dbw_render_backward(ctypes.byref(s), _c(verts), _c(faces), _c(faces_uvs), _c(face_map), _c(maps),
-                                         _c(map_table), _c(R), _c(T), _c(fa), _c(ids), _c(ws), ws.numel(), _c(g_out),
+                                         _c(map_table), _c(R), _c(T), _c(fa), None, _c(ws), ws.numel(), _c(g_out),
                                          _c(g_verts), _c(g_fa), _c(g_maps), _c(scratch), scratch.numel(), _stream()),
                    'dbw_render_backward')
-        return g_verts, g_maps, g_fa, None, None, None, None, None, None, None, None, None
+        return g_verts, g_maps, g_fa, None, None, None, None, None, None, None, None, None, None
 
 
 _TABLE_CACHE = {}
@@ -125,7 +132,7 @@ def _device_map_table(table_host, dev):
 
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
                   perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
-                  n_map_floats=0, maps_are_texels4=False, save_fragment_state=False):
+                  n_map_floats=0, maps_are_texels4=False, save_fragment_state=False, alpha_group=1, n_static_faces=0):
     s = DbwRenderSettings()
     s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
     s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
@@ -139,37 +146,41 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     s.n_map_floats = int(n_map_floats)
     s.maps_are_texels4 = int(maps_are_texels4)
     s.save_fragment_state = int(save_fragment_state)
+    s.alpha_group, s.n_static_faces = int(alpha_group), int(n_static_faces)
     return s
 
 
 def scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip=None,
                    detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None, perspective_correct=True,
-                   verts_are_ndc=False, blur_radius=None, maps_are_texels4=False):
-    """(DbwRenderSettings, device map table) of one render pass over raw scene tensors"""
+                   verts_are_ndc=False, blur_radius=None, maps_are_texels4=False, alpha_group=1, n_static_faces=0):
+    """(DbwRenderSettings, device map table) of one render pass over raw scene tensors.
+    alpha_group: faces per opacity entry (faces_alpha then has F / alpha_group [or B * that] entries);
+    n_static_faces: leading faces whose vertices are constants (no vertex gradient wanted)."""
     H, W = image_size
     V, Fn = verts.shape[-2], faces.shape[0]
     map_table = _device_map_table(map_table_host, verts.device)
     alpha_stride = 0
     if faces_alpha is not None:
-        if faces_alpha.numel() == B * Fn and B > 1:
-            alpha_stride = Fn
-        elif faces_alpha.numel() != Fn:
-            raise DbwError(f'faces_alpha must have F={Fn} or B*F={B * Fn} entries, got {faces_alpha.numel()}')
+        n_alpha = Fn // alpha_group
+        if faces_alpha.numel() == B * n_alpha and B > 1:
+            alpha_stride = n_alpha
+        elif faces_alpha.numel() != n_alpha:
+            raise DbwError(f'faces_alpha must have {n_alpha} or B*{n_alpha} entries, got {faces_alpha.numel()}')
     if blur_radius is None:
         blur_radius = np.log(1. / 1e-4 - 1.) * sigma            # renderer.py:51
     cfg = make_settings(B, H, W, faces_per_pixel, V, Fn, len(map_table_host), alpha_stride, intr, sigma, blur_radius,
                         z_clip, background, clip_inside, perspective_correct, True, detach_bary, verts_are_ndc,
                         n_map_floats=(maps.numel() // 4 * 3) if maps_are_texels4 else maps.numel(),
                         maps_are_texels4=maps_are_texels4,
-                        # a detach_bary backward can stream saved fragment colours / UVs instead of re-deriving them
-                        save_fragment_state=bool(detach_bary) and torch.is_grad_enabled())
+                        # what a backward streams: one 16 B record per kept fragment, written only when one may follow
+                        save_fragment_state=torch.is_grad_enabled(), alpha_group=alpha_group, n_static_faces=n_static_faces)
     return cfg, map_table
 
 
 def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
                  z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
                  perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False,
-                 face_shade=None, return_dists=False):
+                 face_shade=None, return_dists=False, alpha_group=1, n_static_faces=0):
     """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
     verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
     map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
@@ -178,16 +189,14 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     B = R.shape[0] if R is not None else verts.shape[0]
     cfg, map_table = scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip,
                                     detach_bary, clip_inside, background, faces_alpha, perspective_correct, verts_are_ndc,
-                                    blur_radius, maps_are_texels4)
+                                    blur_radius, maps_are_texels4, alpha_group, n_static_faces)
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)
     res = _RenderFn.apply(verts, maps, faces_alpha, R, T, faces.to(torch.int32).contiguous(),
                           faces_uvs.contiguous().float(), face_map.to(torch.int32).contiguous(), map_table, cfg,
-                          face_shade, return_dists)
-    if return_dists:
-        return res                       # (rgba, slot ids, signed squared distances)
-    return (res[0], res[1]) if return_ids else res[0]
+                          face_shade, return_dists, return_ids)
+    return res                           # rgba | (rgba, slot ids) | (rgba, slot ids, signed squared distances)
 
 
 class Renderer(nn.Module):

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 5
+#define DBW_ABI_VERSION 6
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -56,9 +56,15 @@ typedef struct DbwRenderSettings {
   int32_t n_map_floats;       /* total floats in `maps` (= 3 * sum_m H_m*W_m): sizes the library's float4 texel scratch    */
   int32_t maps_are_texels4;   /* 1: `maps` (and `g_maps`) are already RGB+pad float4 texel atlases (dbw_texture_prep_*);
                                  DbwMapDesc.offset keeps its meaning (3 * first texel index)                              */
-  int32_t save_fragment_state;/* 1: the forward also keeps (u, v, signed dist, r, g, b) of every kept fragment in its workspace
-                                 (32 B per fragment actually present) so that a detach_bary backward re-derives no
-                                 geometry for colours / opacities; costs B*K*H*W*32 bytes of workspace ADDRESS space        */
+  int32_t save_fragment_state;/* 1: the forward also keeps one 16 B record {triangle slot | closest edge, u, v, signed squared
+                                 distance} per kept fragment (+ a per-pixel count byte) in its workspace; dbw_render_backward*
+                                 streams these instead of re-deriving geometry and REQUIRES them.  Costs
+                                 B*H*W*(16 K + 1) bytes of workspace ADDRESS space (only fragments that exist are touched)  */
+  int32_t alpha_group;        /* faces sharing one opacity entry (0/1: one per face).  faces_alpha / g_faces_alpha then have
+                                 n_faces / alpha_group entries per view: a DBW block is 80 faces with ONE opacity
+                                 (src/model/dbw.py:219 repeat_interleave's it per face; that is alpha_group = 1)            */
+  int32_t n_static_faces;     /* faces [0, n_static_faces) have constant vertices (the background sphere of the environment,
+                                 src/model/dbw.py:267-280): the backward skips their vertex gradient                        */
 } DbwRenderSettings;
 
 /* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */
@@ -84,9 +90,11 @@ int dbw_workspace_bytes(const DbwRenderSettings* settings, size_t* fwd_bytes, si
  *                no gradient) -- how a static-topology caller drops low-opacity blocks (src/model/dbw.py:316-328)
  *   maps, map_table  packed maps + (M) DbwMapDesc (device)
  *   R (B,3,3), T (B,3)  row-vector convention X_view = X_world @ R + T (src/dataset/dtu.py:75-124)
- *   faces_alpha  NULL, or per-face opacity (src/model/dbw.py:219, renderer.py:258-260), see alpha_view_stride
+ *   faces_alpha  NULL, or per-face opacity (src/model/dbw.py:219, renderer.py:258-260), see alpha_view_stride / alpha_group
  *   out_rgba     (B,4,H,W)  RGB + coverage, NCHW (renderer.py:268)
- *   topk_ids     (B,K,H,W) int32: z-sorted face slots kept per pixel (-1 = empty); needed by backward
+ *   topk_ids     (B,K,H,W) int32 or NULL: z-sorted face slots kept per pixel (-1 = empty) = fragments.pix_to_face modulo
+ *                the slot convention; a diagnostic / visualisation output (render_edges), NOT what the backward reads --
+ *                that is the workspace's fragment records (settings->save_fragment_state)
  */
 int dbw_render_forward(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
                        const float* faces_uvs, const int32_t* face_map, const float* maps,
@@ -112,6 +120,8 @@ int dbw_render_forward_ex(const DbwRenderSettings* settings, const float* verts,
  *   g_verts        (V,3)  [or (B,V,3) when verts_are_ndc]
  *   g_faces_alpha  same shape as faces_alpha (may be NULL when faces_alpha is NULL)
  *   g_maps         same packing as maps (may be NULL: no texture gradient)
+ * Requires the forward to have run with save_fragment_state = 1 on the same workspace; `topk_ids` is ignored (may be
+ * NULL; kept in the signature since ABI 1).
  */
 int dbw_render_backward(const DbwRenderSettings* settings, const float* verts, const int32_t* faces,
                         const float* faces_uvs, const int32_t* face_map, const float* maps,

@@ -26,7 +26,7 @@ static inline float4 __ldg(const float4* p) { return *p; }
 
 #include "../../differentiable-blocksworld_b200/csrc/dbw_math.cuh"
 #include "../../differentiable-blocksworld_b200/csrc/dbw_clip.cuh"
-#include "../../differentiable-blocksworld_b200/csrc/dbw_topk.cuh"
+#include "../../differentiable-blocksworld_b200/csrc/dbw_fraglist.cuh"
 #include "../../differentiable-blocksworld_b200/csrc/dbw_scene_math.cuh"
 
 // record of one triangle as face_setup's write_slot packs it (dbw_render.cu, write_slot): reciprocal of the eps-shifted area
@@ -133,25 +133,31 @@ void hm_clip(const float* fv, int n, float z_clip, int persp, int* ntri, float* 
 
 }  // extern "C"
 
-template <int K>
-static void run_topk(int n, const float* pz, const int* slot, const float* sd, const int* neighbor, int* out_slot, float* out_sd) {
-  unsigned long long key[K];
-  float dk[K];
-  for (int k = 0; k < K; ++k) { key[k] = ~0ull; dk[k] = 0.f; }
-  for (int i = 0; i < n; ++i) topk_offer<K>(key, dk, pz[i], slot[i], sd[i], fabsf(sd[i]), neighbor[i]);
-  for (int k = 0; k < K; ++k) { out_slot[k] = key[k] != ~0ull ? (int)(unsigned)key[k] : -1; out_sd[k] = dk[k]; }
-}
-
 extern "C" {
-// a stream of n candidates of one pixel offered to the register top-K of raster_forward_kernel<K>; K in {1, 4, 10, 25}
+// a stream of n candidates of one pixel offered to the sorted shared-memory fragment list of raster_forward_kernel
+// (fraglist_offer, dbw_fraglist.cuh), laid out as on the device: this pixel's column inside a [K][stride] array
 int hm_topk(int K, int n, const float* pz, const int* slot, const float* sd, const int* neighbor, int* out_slot, float* out_sd) {
-  switch (K) {
-    case 1: run_topk<1>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
-    case 4: run_topk<4>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
-    case 10: run_topk<10>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
-    case 25: run_topk<25>(n, pz, slot, sd, neighbor, out_slot, out_sd); return 0;
+  const int stride = 7, col = 3;                 // any column of a wider array: neighbours must stay untouched
+  float4* A = new float4[(size_t)K * stride];
+  float* V = new float[(size_t)K * stride];
+  for (int i = 0; i < K * stride; ++i) { A[i] = make_float4(-7.f, -7.f, -7.f, -7.f); V[i] = -7.f; }
+  int cnt = 0;
+  for (int i = 0; i < n; ++i)
+    cnt = fraglist_offer(A + col, V + col, stride, cnt, K, pz[i], slot[i], i % 3, sd[i], fabsf(sd[i]), neighbor[i], 0.25f * i, 0.5f * i);
+  int bad = 0;
+  for (int k = 0; k < K; ++k) {
+    const float4 e = A[k * stride + col];
+    out_slot[k] = k < cnt ? (__float_as_int(e.y) & DBW_FRAG_SLOT_MASK) : -1;
+    out_sd[k] = k < cnt ? e.z : 0.f;
+    if (k < cnt) {                               // the payload travels with its key: edge id, u, v of the candidate that made it
+      int src = -1;
+      for (int i = 0; i < n; ++i) if (slot[i] == out_slot[k]) src = i;
+      if (src < 0 || ((__float_as_int(e.y) >> DBW_FRAG_EDGE_SHIFT) & 3) != src % 3 || e.w != 0.25f * src || V[k * stride + col] != 0.5f * src || e.x != pz[src]) bad = 1;
+    }
   }
-  return -1;
+  for (int i = 0; i < K * stride; ++i) if (i % stride != col && (A[i].x != -7.f || V[i] != -7.f)) bad = 2;
+  delete[] A; delete[] V;
+  return bad;
 }
 }  // extern "C"
 

@@ -81,10 +81,24 @@ def test_cfg2_blocks_pass_coarse_400x400(cfg2, boxy):
 
 
 def test_cfg2_blocks_pass_fine_400x400(cfg2):
+    """fine phase (sigma = 5e-6): the opacity exp(-d / sigma) of a halo pixel amplifies the fp32 rounding of the squared
+    distance d (coordinates ~0.5 NDC, ulp 6e-8; d ~ 4.6e-5 at the halo's rim) by 1 / sigma -- an fp32 evaluation of the
+    REFERENCE arithmetic deviates from fp64 by more than 1e-4 at a few pixels too.  The fp32 oracle is the tolerance model
+    (SURVEY 8c): the CUDA path may not be worse than twice what the fp32 oracle itself shows against fp64."""
     tpl, (R, T, K) = cfg2
     p = _params(10, 256, boxy=True)
     blocks, _ = tpl.build_blocks(p)
-    amb = _grad_parity(blocks, R[:2], T[:2], K, (400, 400), 5e-6, 10, 0.001, True, None, True, seed=2)
+    ref64, fr64 = D.render(blocks, R[:2], T[:2], K, (400, 400), sigma=5e-6, faces_per_pixel=10, z_clip=0.001, return_fragments=True)
+    blocks32 = {k: ([m.detach().float() for m in v] if k == 'maps' else (v.detach().float() if v.is_floating_point() else v))
+                for k, v in blocks.items()}
+    ref32, fr32 = D.render(blocks32, R[:2].float(), T[:2].float(), K.float(), (400, 400), sigma=5e-6, faces_per_pixel=10, z_clip=0.001,
+                           return_fragments=True)
+    same = (fr32.pix_to_face == fr64.pix_to_face).all(-1)[:, None]
+    err32 = ((ref32.double() - ref64.detach()).abs() * same)
+    frac32, max32 = (err32 > 1e-4).double().mean().item(), err32.max().item()
+    print(f'cfg2 blocks fine: fp32 ORACLE vs fp64 oracle on equal decisions: {frac32 * 100:.4f}% of values above 1e-4, max {max32:.2e}')
+    amb = _grad_parity(blocks, R[:2], T[:2], K, (400, 400), 5e-6, 10, 0.001, True, None, True, seed=2,
+                       img_bad_frac=max(2 * frac32, 1e-5), img_max_err=max(2 * max32, 1e-4))
     print(f'cfg2 blocks fine: ambiguous pixels {amb * 100:.4f}%')
 
 

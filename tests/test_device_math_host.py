@@ -185,9 +185,10 @@ def _oracle_queue(K, cands):
 
 
 @pytest.mark.parametrize('K', [1, 4, 10, 25])
-def test_register_top_k_matches_the_oracle_queue(hm, K):
-    """topk_offer (dbw_topk.cuh): ordering by (depth, slot) incl. exact depth ties, overflow beyond K, and the mutual
-    exclusion of the two halves of a z-clipped quad, against the oracle's queue on random candidate streams"""
+def test_fragment_list_matches_the_oracle_queue(hm, K):
+    """fraglist_offer (dbw_fraglist.cuh, the per-pixel sorted list in shared memory): ordering by (depth, slot) incl. exact
+    depth ties, overflow beyond K, the mutual exclusion of the two halves of a z-clipped quad, and that every entry's
+    payload (closest edge, u, v) travels with its key -- against the oracle's queue on random candidate streams"""
     g = np.random.default_rng(K)
     for trial in range(300):
         n = int(g.integers(0, 3 * K + 4))
