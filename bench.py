@@ -2,14 +2,18 @@
 """bench.py -- render+backward views/sec of the DBW render hot path (BASELINE.json metric).
 
 A "step" = one optimisation step's render work on one batch of B synthetic views: build the scene from the leaf
-parameters, render the environment pass (K=1, sigma=0) and the blocks pass (K=10, sigma=1e-4, per-face opacities),
+parameters, render the environment pass (K=1, sigma=0) and the blocks pass (K, sigma=1e-4, per-block opacities),
 composite + MSE against the target images, and back-propagate to every leaf parameter
 (S, R_6d, T, sq_eps, alpha_logit, textures, texture_bkg, texture_ground, R_6d_ground, T_ground).  SURVEY.md 8d.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (torchrun launches N ranks for N > 1)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload dtu|bmvs|stress]     our arm (torchrun launches N ranks)
   python bench.py --impl reference ...                            the reference's algorithm on the host cores (oracle port)
+
+Workloads = BASELINE.json configs: dtu = configs[1]/[2] (the metric's configuration and the default), bmvs = configs[3],
+stress = configs[4].  N > 1 is STRONG scaling: the step's views are split over the ranks at (view, 16-row band) granularity.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -21,18 +25,33 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-WORKLOAD = {'name': 'dtu_scan24_shape', 'n_blocks': 10, 'n_views': 49, 'height': 400, 'width': 400,
-            'faces_per_pixel': 10, 'txt_size': 256}
-SEED = 227391          # configs/dtu/default.yml:42
-
-MODEL_CFG = {
-    'mesh': {'n_blocks': WORKLOAD['n_blocks'], 'S_world': 0.5, 'R_world': [115, 0, 0], 'txt_size': WORKLOAD['txt_size']},
-    'renderer': {'faces_per_pixel': WORKLOAD['faces_per_pixel'], 'cameras': {'name': 'perspective'}, 'detach_bary': True,
-                 'z_clip': 0.001},
-    'rend_optim': {'coarse_learning': 1500, 'decimate_txt': 750, 'decimate_factor': 8, 'kill_blocks': True,
-                   'decouple_rendering': True, 'opacity_noise': True},
-    'loss': {'rgb_weight': 1},
+WORKLOADS = {
+    'dtu': dict(baseline='configs[1] (1 GPU) / configs[2] (8 GPUs)', n_blocks=10, n_views=49, height=400, width=400,
+                faces_per_pixel=10, txt_size=256, txt_bkg_upscale=1,
+                what='DTU scan24 shape: 10 superquadric blocks (800 faces) + env (448 faces), 49 views 400x400, K=10, 256^2 textures'),
+    'bmvs': dict(baseline='configs[3]', n_blocks=10, n_views=64, height=576, width=768, faces_per_pixel=10, txt_size=256,
+                 txt_bkg_upscale=1, what='BlendedMVS shape: 10 blocks + env, 64 views 576x768, K=10, 256^2 textures'),
+    'stress': dict(baseline='configs[4]', n_blocks=50, n_views=256, height=800, width=800, faces_per_pixel=25, txt_size=128,
+                   txt_bkg_upscale=2, what='stress shape (configs/bmvs/gundam_50.yml): 50 blocks (4000 faces) + env, 256 views '
+                                           '800x800, K=25, 128^2 block textures, 256^2 env textures'),
 }
+SEED = 227391          # configs/dtu/default.yml:42
+PASS_BYTES = 30e9      # views of a step are processed in passes of at most this much workspace (gradients accumulate)
+
+
+def model_cfg(w):
+    return {
+        'mesh': {'n_blocks': w['n_blocks'], 'S_world': 0.5, 'R_world': [115, 0, 0], 'txt_size': w['txt_size'],
+                 'txt_bkg_upscale': w['txt_bkg_upscale']},
+        'renderer': {'faces_per_pixel': w['faces_per_pixel'], 'cameras': {'name': 'perspective'}, 'detach_bary': True, 'z_clip': 0.001},
+        'rend_optim': {'coarse_learning': 1500, 'decimate_txt': 750, 'decimate_factor': 8, 'kill_blocks': True,
+                       'decouple_rendering': True, 'opacity_noise': True},
+        'loss': {'rgb_weight': 1},
+    }
+
+
+def metric_name(w):
+    return f'render+backward views/sec ({w["height"]}x{w["width"]}, {w["n_blocks"]} blocks)'
 
 
 def peaks():
@@ -43,15 +62,27 @@ def peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this very
-# workload at N=1 (profiles/ncu_full_r1f_summary.txt); None for other shard sizes
-NCU_TRAFFIC_BYTES = {'raster_forward[env K=1]': 108.9e6, 'raster_forward[blocks K=10]': 1402.5e6,
-                     'raster_backward[blocks K=10]': 1001.7e6, 'raster_backward[env K=1]': 162.3e6}
+def kernel_fingerprint():
+    """sha256 over the kernel sources: ties a committed ncu capture (profiles/ncu_traffic.json) to the build that is benched"""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'differentiable-blocksworld_b200', 'csrc')
+    for fn in sorted(os.listdir(d)):
+        if fn.endswith(('.cu', '.cuh')):
+            h.update(open(os.path.join(d, fn), 'rb').read())
+    return h.hexdigest()[:16]
 
 
-def algorithmic_bytes_per_view(K, H, W):
-    """RGBA out + grad RGBA in + int32 top-K ids written forward and read backward = H*W*(32 + 8K)."""
-    return H * W * (32 + 8 * K)
+def ncu_traffic(kernel_label, workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_label` from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by scripts/summarize_profile.py) -- only if it was taken on THIS build of the kernels,
+    this workload and one GPU; else None"""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if world != 1 or not os.path.exists(path):
+        return None, 'no capture'
+    d = json.load(open(path))
+    if d.get('kernel_fingerprint') != kernel_fingerprint() or d.get('workload') != workload:
+        return None, f'profiles/ncu_traffic.json is from another build ({d.get("kernel_fingerprint")}) or workload: not used'
+    return d['bytes_per_launch'].get(kernel_label), f'{d.get("source", "profiles/ncu_traffic.json")} (same kernel sources: {d["kernel_fingerprint"]})'
 
 
 class ClockSampler:
@@ -93,17 +124,37 @@ class ClockSampler:
                 'samples': len(rows), 'power_w_max': max(pw) if pw else None}
 
 
-def synthetic_inputs(B, H, W, device=None, pin=False):
+def synthetic_inputs(w):
     from dbw_b200.synthetic import ring_cameras
+    B, H, W = w['n_views'], w['height'], w['width']
     R, T, K = ring_cameras(B)
     g = torch.Generator().manual_seed(SEED)
     imgs = torch.rand(B, 3, H, W, generator=g)
-    inp = {'imgs': imgs, 'R': R, 'T': T, 'K': K[None].expand(B, -1, -1).contiguous()}
-    if pin:
-        inp = {k: v.pin_memory() for k, v in inp.items()}
-    if device is not None:
-        inp = {k: v.to(device) for k, v in inp.items()}
-    return inp
+    return {'imgs': imgs, 'R': R, 'T': T, 'K': K[None].expand(B, -1, -1).contiguous()}
+
+
+def make_passes(local, rows, w):
+    """split this rank's views into passes of equal shape: [{imgs, R, T, K, rows}] (host, pinned).  Padding entries of the
+    last pass repeat view 0 with an EMPTY row range, so that one captured graph serves every pass."""
+    B_local, H, W, K = len(local['imgs']), w['height'], w['width'], w['faces_per_pixel']
+    per_view = H * W * (16 * K + 17 + 16 * 6 + 12)          # fragment records + count (both passes), RGBA-sized images, target
+    cap = max(1, int(PASS_BYTES // per_view))
+    n_pass = -(-B_local // cap)
+    size = -(-B_local // n_pass)
+    if rows is None:
+        rows = torch.tensor([[0, H]] * B_local, dtype=torch.int32)
+    passes = []
+    for p in range(n_pass):
+        idx = list(range(p * size, min((p + 1) * size, B_local)))
+        pad = size - len(idx)
+        sel = torch.tensor(idx + [0] * pad)
+        chunk = {k: v[sel].contiguous() for k, v in local.items()}
+        r = rows[sel].clone()
+        if pad:
+            r[len(idx):] = 0
+        chunk['rows'] = r.contiguous()
+        passes.append({k: v.pin_memory() for k, v in chunk.items()})
+    return passes
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -115,51 +166,97 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    import dbw_b200
+    import dbw_b200  # noqa: F401
     from dbw_b200 import _lib
     from dbw_b200.dbw import DifferentiableBlocksWorld
-    from dbw_b200.parallel import ViewParallel, shard_views
+    from dbw_b200.parallel import ViewParallel
     from dbw_b200.graph import GraphedStep, PipelinedGraphedStep
     from copy import deepcopy
 
-    B, H, W, K = WORKLOAD['n_views'], WORKLOAD['height'], WORKLOAD['width'], WORKLOAD['faces_per_pixel']
+    w = WORKLOADS[args.workload]
+    B, H, W, K = w['n_views'], w['height'], w['width'], w['faces_per_pixel']
     torch.manual_seed(SEED)
-    model = DifferentiableBlocksWorld((H, W), **deepcopy(MODEL_CFG)).to(dev)
+    model = DifferentiableBlocksWorld((H, W), **deepcopy(model_cfg(w))).to(dev)
     model.train()
-    vp = ViewParallel(model, seed=SEED)
-    host = synthetic_inputs(B, H, W, pin=True)
-    sl = shard_views(B, world, rank)
-    host_local = {k: v[sl].contiguous().pin_memory() for k, v in host.items()}
-    B_local = sl.stop - sl.start
-    dev_local = {k: v.to(dev) for k, v in host_local.items()}
+    vp = ViewParallel(model, seed=SEED, row_bands=True, collective=args.collective)
+    host_local, _ = vp.shard(synthetic_inputs(w))
+    rows = host_local.pop('rows', None)
+    passes = make_passes(host_local, rows, w)
+    n_pass, views_per_pass = len(passes), len(passes[0]['imgs'])
+    local_px = int(sum(int((p['rows'][:, 1] - p['rows'][:, 0]).sum()) for p in passes)) * W
+    dev_passes = [{k: v.to(dev) for k, v in p.items()} for p in passes]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    acc = torch.zeros_like(vp.bucket.flat) if n_pass > 1 else None
 
-    def step_eager():
-        return vp.forward_backward(dev_local, None, already_sharded=True, n_total_views=B)
+    def step_eager(collective=True):
+        for i, p in enumerate(dev_passes):
+            vp.forward_backward(p, None, already_sharded=True, n_total_views=B, all_reduce=False)
+            if acc is not None:
+                acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
+        if acc is not None:
+            vp.bucket.flat.copy_(acc)
+        if collective:
+            vp.bucket.all_reduce(vp.group)
 
-    car = args.allreduce_in_graph
-    graphed = None if args.no_graph else GraphedStep(vp, dev_local, B, capture_all_reduce=car)
-    piped = None if args.no_graph else PipelinedGraphedStep(vp, dev_local, B, capture_all_reduce=car)
+    graphed = piped = None
+    if not args.no_graph:
+        piped = PipelinedGraphedStep(vp, dev_passes[0], B)
+        graphed = piped.steps[0]
 
-    def step_resident():
-        return graphed.run() if graphed is not None else step_eager()
+    def step_resident(collective=True):
+        if graphed is None:
+            return step_eager(collective)
+        for i, p in enumerate(dev_passes):
+            graphed.run(p if n_pass > 1 else None, all_reduce=False)
+            if acc is not None:
+                acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
+        if acc is not None:
+            vp.bucket.flat.copy_(acc)
+        if collective:
+            vp.bucket.all_reduce(vp.group)
 
     def step_e2e():
-        if piped is not None:
-            # H2D of this step's inputs (pinned) into the graph's static buffers; the NEXT step's inputs are prefetched on
-            # a copy stream while this step computes (every step's copy is inside the timed region)
-            losses = piped.run(host_local, host_local)
+        """the public API with HOST buffers: every pass's inputs are copied H2D from pinned memory (the next pass's while
+        this one computes: double-buffered), and the step's loss is read back"""
+        loss = 0.0
+        if piped is None:
+            for i, p in enumerate(passes):
+                inp = {k: v.to(dev, non_blocking=True) for k, v in p.items()}
+                losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B, all_reduce=False)
+                if acc is not None:
+                    acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
+                loss = loss + losses['rgb']
         else:
-            inp = {k: v.to(dev, non_blocking=True) for k, v in host_local.items()}
-            losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B)
-        return float(losses['rgb'].item())                                        # D2H read of the step's result
+            for i, p in enumerate(passes):
+                losses = piped.run(p, passes[(i + 1) % n_pass], all_reduce=False)
+                if acc is not None:
+                    acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
+                loss = loss + losses['rgb']
+        if acc is not None:
+            vp.bucket.flat.copy_(acc)
+        vp.bucket.all_reduce(vp.group)
+        return float(loss.item())                                                 # D2H read of the step's result
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    def timed(fn, steps):
+        evs = []
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_resident()
     barrier()
 
@@ -171,19 +268,10 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    evs = []
-    barrier()
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step_resident()
-        b.record()
-        evs.append((a, b))
-    barrier()
-    launches = launches_per_step * args.steps
-    ms_local = sum(a.elapsed_time(b) for a, b in evs)
+    ms_local = timed(step_resident, args.steps)
     clocks = sampler.summary() if sampler else None
+    # the same steps without the gradient collective: what the all-reduce adds to a step when it is exposed
+    ms_nocoll_local = timed(lambda: step_resident(False), args.steps) if world > 1 else ms_local
 
     # ---- per-kernel durations (roofline): the same steps run eagerly with CUDA events around the raster kernels on their
     # launch stream (events cannot be read back from inside a replayed graph; kernel durations do not depend on how
@@ -192,7 +280,7 @@ def run_ours(args):
     _lib.lib().dbw_timing_enable(1)
     for _ in range(args.steps):
         flush.zero_()
-        step_eager()
+        step_eager(False)
     barrier()
     _lib.lib().dbw_timing_enable(0)
     kt = {(kind, kk): _lib.kernel_time_ms(kind, kk) for kind in (0, 1) for kk in (1, K)}
@@ -201,78 +289,83 @@ def run_ours(args):
     # ---- end-to-end timing through the public API with host buffers
     for _ in range(2):
         step_e2e()
-    barrier()
-    evs2 = []
-    for _ in range(args.steps):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step_e2e()
-        b.record()
-        evs2.append((a, b))
-    barrier()
-    ms_e2e_local = sum(a.elapsed_time(b) for a, b in evs2)
+    ms_e2e_local = timed(step_e2e, args.steps)
 
-    t = torch.tensor([ms_local, ms_e2e_local], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_local, ms_e2e_local, ms_nocoll_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e_total = t.tolist()
+    ms_total, ms_e2e_total, ms_nocoll_total = t.tolist()
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
         value = B * args.steps / (ms_total / 1e3)
         e2e_value = B * args.steps / (ms_e2e_total / 1e3)
         peak, peak_src = peaks()
-        # dominant kernel = the raster kernel with the largest summed duration over the timed region
         names = {(0, 1): 'raster_forward[env K=1]', (0, K): f'raster_forward[blocks K={K}]',
                  (1, 1): 'raster_backward[env K=1]', (1, K): f'raster_backward[blocks K={K}]'}
-        dom = max(kt, key=lambda k: kt[k][0])
-        dom_ms = kt[dom][0] / max(kt[dom][1], 1)
-        kk = dom[1]
-        # per launch: each direction moves half of H*W*(32+8K) per view (16 B RGBA + 4K B ids), B_local views per launch
-        alg_bytes = B_local * H * W * (16 + 4 * kk)
-        achieved = alg_bytes / (dom_ms / 1e3) / 1e9
-        h2d = sum(v.numel() * v.element_size() for v in host_local.values())
+        per_step = {names[k]: kt[k][0] / args.steps for k in kt}
+
+        def roofline(key):
+            """each direction of a pass moves H*W*(16 + 4K) algorithmic bytes per view (RGBA + K ids); this rank's
+            launches of one step cover local_px pixels"""
+            ms = kt[key][0] / args.steps                       # all launches of this kernel in one step (one per pass)
+            alg = local_px * (16 + 4 * key[1])
+            traffic, src = ncu_traffic(names[key], args.workload, world)
+            return {'bound': 'hbm', 'kernel': names[key], 'achieved': alg / (ms / 1e3) / 1e9, 'peak': peak, 'unit': 'GB/s',
+                    'frac': alg / (ms / 1e3) / 1e9 / peak, 'traffic': traffic, 'traffic_source': src, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_step': alg, 'kernel_ms_per_step': ms, 'launches_per_step': kt[key][1] / args.steps}
+
+        dom = max(kt, key=lambda k: kt[k][0])                  # the raster kernel with the largest summed duration
+        raster_ms = sum(per_step.values())
+        h2d = sum(v.numel() * v.element_size() for p in passes for v in p.values())
         line = {
-            'metric': 'render+backward views/sec (400x400, 10 blocks)', 'value': value, 'unit': 'views/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step,
+            'metric': metric_name(w), 'value': value, 'unit': 'views/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': warm, 'ms_per_step': ms_per_step,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'DTU scan24 shape: 10 superquadric blocks (800 faces) + env (448 faces), 49 views 400x400, '
-                                   'K=10, 256^2 textures, coarse phase (sigma=1e-4, per-face opacities); views sharded over ranks '
-                                   '(7,6,6,..), one NCCL all-reduce of the flat gradient bucket',
-                       'views_per_step': B, 'l2': 'flushed (256 MB memset) between steps, outside the per-step event pairs',
+            'config': {'workload': f'{args.workload}: {w["what"]}; BASELINE {w["baseline"]}; coarse phase (sigma=1e-4, per-block '
+                                   f'opacities + noise, 8x decimated textures); the step\'s {B} views are split over the ranks at '
+                                   f'(view, 16-row band) granularity, gradients reduced by one all-reduce ({vp.collective_name})',
+                       'views_per_step': B, 'views_per_pass_per_rank': views_per_pass, 'passes_per_step': n_pass,
+                       'l2': 'flushed (256 MB memset) between steps, outside the per-step event pairs',
                        'loss': 'rgb (MSE) only; LPIPS excluded (SURVEY 8d)', 'seed': SEED,
-                       'submission': 'eager' if graphed is None else 'whole step captured once in a CUDA graph and replayed',
-                       'e2e_pipeline': 'none' if piped is None else 'inputs of step i+1 copied H2D on a side stream during step i (double-buffered)'},
+                       'submission': 'eager' if graphed is None else 'each pass captured once in a CUDA graph and replayed',
+                       'e2e_pipeline': 'none' if piped is None else 'inputs of the next pass copied H2D on a side stream during this pass (double-buffered)'},
             'e2e': {'value': e2e_value, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
-            'gpu_launches': launches,
+            'gpu_launches': launches_per_step * args.steps,
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': NCU_TRAFFIC_BYTES.get(names[dom]) if world == 1 else None,
-                         'traffic_source': 'profiles/ncu_full_r1f_summary.txt (bytes per launch at N=1)', 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': alg_bytes, 'avg_launch_ms': dom_ms,
-                         'kernels_ms_per_step': {names[k]: kt[k][0] / args.steps for k in kt}},
+            'roofline': dict(roofline(dom), kernels_ms_per_step=per_step),
+            'roofline_backward': roofline((1, K)),
+            'breakdown_ms_per_step': {'step': ms_per_step, 'raster_kernels_rank0': raster_ms,
+                                      'other_kernels_and_launch_gaps': ms_nocoll_total / args.steps - raster_ms,
+                                      'exposed_collective': (ms_total - ms_nocoll_total) / args.steps},
+            'note': 'PyTorch3D-CUDA (the north star\'s comparator) is not installable here: unmeasured',
         }
         if world == 1 and not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline(n_views=16)
+            line['cpu_baseline'] = cpu_baseline(args.workload)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle port)
-def oracle_step(n_views, threads=None):
-    """One render+backward pass of the reference's algorithm (oracle port) over n_views views of the workload."""
+def sample_views(n_views, n):
+    """n view indices spread evenly over the ring: the CPU legs render a subset of the very views the GPU arm renders"""
+    return [int(round(i * n_views / n)) % n_views for i in range(n)]
+
+
+def oracle_step(workload, views):
+    """One render+backward pass of the reference's algorithm (oracle port) over the given views of the workload."""
     from oracle import dbw_path as D
-    H, W, K = WORKLOAD['height'], WORKLOAD['width'], WORKLOAD['faces_per_pixel']
-    tpl = D.SceneTemplate(n_blocks=WORKLOAD['n_blocks'], txt_size=WORKLOAD['txt_size'])
-    p = {k: v.requires_grad_(True) for k, v in D.init_params(WORKLOAD['n_blocks'], WORKLOAD['txt_size'], seed=SEED).items()}
-    R, T, Km = D.ring_cameras(WORKLOAD['n_views'])
+    w = WORKLOADS[workload]
+    H, W, K = w['height'], w['width'], w['faces_per_pixel']
+    tpl = D.SceneTemplate(n_blocks=w['n_blocks'], txt_size=w['txt_size'], txt_bkg_upscale=w['txt_bkg_upscale'])
+    p = {k: v.requires_grad_(True) for k, v in D.init_params(w['n_blocks'], w['txt_size'], w['txt_bkg_upscale'], seed=SEED).items()}
+    R, T, Km = D.ring_cameras(w['n_views'])
     g = torch.Generator().manual_seed(SEED)
-    imgs = torch.rand(n_views, 3, H, W, generator=g)
+    imgs = torch.rand(len(views), 3, H, W, generator=g)
     keep = torch.sigmoid(p['alpha_logit'].detach()) > 0.01
     t0 = time.perf_counter()
-    rec = D.predict(tpl, p, R[:n_views], T[:n_views], Km, (H, W), sigma=1e-4, faces_per_pixel=K, z_clip=0.001, keep=keep, decimate=8)
+    rec = D.predict(tpl, p, R[views], T[views], Km, (H, W), sigma=1e-4, faces_per_pixel=K, z_clip=0.001, keep=keep, decimate=8)
     loss = D.mse_loss(imgs, rec)
     loss.backward()
     return time.perf_counter() - t0
@@ -284,37 +377,43 @@ def cpu_threads():
     return min(os.cpu_count(), 32)
 
 
-def cpu_baseline(n_views=16):
+def cpu_baseline(workload, n_views=None):
+    w = WORKLOADS[workload]
+    n_views = n_views or max(1, int(16 * 160000 / (w['height'] * w['width'])))
+    views = sample_views(w['n_views'], n_views)
     torch.set_num_threads(cpu_threads())
-    oracle_step(1)                                   # warm-up (page in the library, thread pools)
-    dt = oracle_step(n_views)
-    return {'value': n_views / dt, 'unit': 'views/s', 'cores': cpu_threads(), 'kind': 'port',
-            'sample': f'{n_views} of the 49 views (400x400, 10 blocks, K=10), forward+backward once, '
-                      f'OpenMP rasterizer + torch ops on {cpu_threads()} of {os.cpu_count()} host threads; {dt:.1f} s'}
+    oracle_step(workload, views[:1])                  # warm-up (page in the library, thread pools)
+    dt = oracle_step(workload, views)
+    return {'value': n_views / dt, 'unit': 'views/s', 'cores': cpu_threads(), 'kind': 'port', 'views_sampled': views,
+            'sample': f'{n_views} of the {w["n_views"]} views ({w["height"]}x{w["width"]}, {w["n_blocks"]} blocks, K={w["faces_per_pixel"]}), '
+                      f'forward+backward once, OpenMP rasterizer + torch ops on {cpu_threads()} of {os.cpu_count()} host threads; {dt:.1f} s'}
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
+    w = WORKLOADS[args.workload]
     torch.set_num_threads(cpu_threads())
     n = 2
+    views = sample_views(w['n_views'], n)
     for _ in range(min(args.warmup, 1)):
-        oracle_step(1)
+        oracle_step(args.workload, views[:1])
     tot = 0.0
     for _ in range(args.steps):
-        tot += oracle_step(n)
+        tot += oracle_step(args.workload, views)
     value = n * args.steps / tot
-    sample = f'{n} of the 49 views per step (400x400, 10 blocks, K=10), forward+backward'
+    sample = f'{n} of the {w["n_views"]} views per step ({w["height"]}x{w["width"]}, {w["n_blocks"]} blocks, K={w["faces_per_pixel"]}), forward+backward'
     print(json.dumps({
-        'impl': 'reference', 'metric': 'render+backward views/sec (400x400, 10 blocks)', 'value': value, 'unit': 'views/s',
+        'impl': 'reference', 'metric': metric_name(w), 'value': value, 'unit': 'views/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1), 'ms_per_step': tot / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DTU scan24 shape (same as our arm); bounded sample: ' + sample, 'seed': SEED},
-        'cpu_baseline': {'value': value, 'unit': 'views/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample},
+        'config': {'workload': f'{args.workload}: {w["what"]} (same scene, cameras and seed as our arm); bounded sample: ' + sample,
+                   'views_per_step': w['n_views'], 'views_sampled': views, 'seed': SEED},
+        'cpu_baseline': {'value': value, 'unit': 'views/s', 'cores': cpu_threads(), 'kind': 'port', 'sample': sample, 'views_sampled': views},
         'e2e': {'value': value, 'unit': 'views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'note': 'PyTorch3D (the reference dependency that owns this arithmetic) is not installable here; this arm times the '
-                'CPU restatement of its algorithm (oracle/, "port") on the host cores',
+        'note': 'PyTorch3D (the reference dependency that owns this arithmetic) is not installable here, so PyTorch3D-CUDA and '
+                'PyTorch3D-CPU are both UNMEASURED; this arm times the CPU restatement of its algorithm (oracle/, "port") on the host cores',
     }))
 
 
@@ -324,10 +423,14 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='dtu', choices=sorted(WORKLOADS))
+    ap.add_argument('--collective', default='auto', choices=['auto', 'nccl', 'p2p'],
+                    help='gradient all-reduce: hand-written NVLink peer-memory kernel (p2p), NCCL, or p2p when it initialises (auto)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='submit the step eagerly instead of replaying a CUDA graph')
-    ap.add_argument('--allreduce-in-graph', action='store_true', help='capture the NCCL all-reduce into the CUDA graph (experimental)')
     args = ap.parse_args()
+    if args.workload != 'dtu' and args.steps == 100:
+        args.steps = 10              # the larger workloads take 10-100x longer per step: keep the default run within minutes
     if args.impl == 'reference':
         if args.steps > 5:
             args.steps = 5          # each step is a bounded CPU sample; keep the whole run within minutes

@@ -21,7 +21,7 @@ class DbwRenderSettings(ctypes.Structure):
         ('clip_inside', ctypes.c_int32), ('perspective_correct', ctypes.c_int32),
         ('clip_barycentric', ctypes.c_int32), ('detach_bary', ctypes.c_int32), ('verts_are_ndc', ctypes.c_int32),
         ('n_map_floats', ctypes.c_int32), ('maps_are_texels4', ctypes.c_int32), ('save_fragment_state', ctypes.c_int32),
-        ('alpha_group', ctypes.c_int32), ('n_static_faces', ctypes.c_int32),
+        ('alpha_group', ctypes.c_int32), ('n_static_faces', ctypes.c_int32), ('view_rows', ctypes.c_void_p),
     ]
 
 
@@ -48,7 +48,8 @@ EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_work
            'dbw_render_forward_loss', 'dbw_render_backward_scaled',
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
-           'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward']
+           'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward',
+           'dbw_comm_create', 'dbw_comm_ipc_handle', 'dbw_comm_connect', 'dbw_comm_all_reduce', 'dbw_comm_error', 'dbw_comm_destroy']
 
 _lib = None
 
@@ -83,6 +84,12 @@ def lib():
         L.dbw_scene_geometry_backward.argtypes = [ctypes.POINTER(DbwSceneGeometry)] + [vp] * 8
         L.dbw_texture_prep_forward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp]
         L.dbw_texture_prep_backward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp, vp]
+        L.dbw_comm_create.argtypes = [ctypes.c_int32, ctypes.c_int32, sz, ctypes.POINTER(vp)]
+        L.dbw_comm_ipc_handle.argtypes = [vp, vp]
+        L.dbw_comm_connect.argtypes = [vp, vp]
+        L.dbw_comm_all_reduce.argtypes = [vp, vp, sz, vp]
+        L.dbw_comm_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+        L.dbw_comm_destroy.argtypes = [vp]
         L.dbw_timing_enable.restype = None
         L.dbw_timing_reset.restype = None
         L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]

@@ -1,0 +1,235 @@
+// dbw_comm.cu -- the step's ONE gradient exchange as a hand-written all-reduce over NVLink 5 / NVSwitch
+// peer memory: a plain kernel (no NCCL, no host synchronisation), so that it is captured INSIDE the step's CUDA graph --
+// round 1 had to issue an ncclAllReduce after the graph replay (capturing it hung) and paid ~0.13 ms per step for it.
+//
+// One process per GPU.  Every rank owns an arena (cudaMalloc, exported with cudaIpcGetMemHandle, opened by its peers):
+//     control:  flagsA[world], flagsB[world] (written BY the peers), epoch, grid-barrier counters
+//     data[2]   the rank's addends of this / the previous all-reduce          (parity = epoch & 1)
+//     red[2]    the slice of the sum this rank reduced (two-shot path)
+// all_reduce(buf, n):
+//     stage buf -> data[parity];  barrier A (every rank's addends are visible)
+//     one-shot (payload <= ONE_SHOT_BYTES): every rank sums all peers' data in rank order                -> buf
+//     two-shot: rank r sums slice r of all peers' data -> red[parity] and buf;  barrier B;  the other slices are read
+//               from their owners' red                                                                   -> buf
+// Every rank adds in the same order (0..world-1), so the result is bit-identical on all ranks.  The parity double buffering
+// replaces the trailing barrier: a rank can overwrite data[p] / red[p] of epoch e only in epoch e+2, which it reaches after
+// barrier A of e+1, i.e. after every peer has launched e+1 and therefore finished reading epoch e (stream order).
+// Barriers are epoch-stamped flags stored into the PEERS' arenas with st.release.sys and polled locally with
+// ld.acquire.sys; a poll that exceeds ~2 s sets the arena's error word instead of hanging the GPU.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dbw_render.h"
+
+int dbw_fail_(const char* what, cudaError_t e);
+void dbw_count_launch_(void);
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return dbw_fail_(#call, _e); } while (0)
+
+#define COMM_MAX_WORLD 16
+#define COMM_BLOCKS 48
+#define COMM_THREADS 512
+#define ONE_SHOT_BYTES (512 * 1024)
+#define CTRL_BYTES 4096
+
+struct CommDev {
+  int world, rank;
+  unsigned* ctrl[COMM_MAX_WORLD];        // each rank's control block: [0,world) flagsA, [64, 64+world) flagsB
+  float* data[COMM_MAX_WORLD][2];
+  float* red[COMM_MAX_WORLD][2];
+  size_t cap_floats;
+};
+// local control words (indices into ctrl[rank]): 128 epoch, 129 grid-barrier arrivals, 130 barrier base, 131 error
+#define CW_FLAGS_A 0
+#define CW_FLAGS_B 64
+#define CW_EPOCH 128
+#define CW_ARRIVE 129
+#define CW_BASE 130
+#define CW_ERROR 131
+
+struct Comm {
+  CommDev d;
+  void* arena;
+  void* peer_base[COMM_MAX_WORLD];
+  size_t arena_bytes;
+  bool connected;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ float4 ld_peer(const float4* p) {          // peer memory is never served from a stale L1 line
+  float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
+}
+
+#define SPIN_LIMIT (4000000000ll)        // ~2 s of SM clocks
+
+// barrier over the blocks of THIS kernel (all co-resident: COMM_BLOCKS <= SMs)
+__device__ __forceinline__ void grid_barrier(unsigned* ctl, unsigned target) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(&ctl[CW_ARRIVE], 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(&ctl[CW_ARRIVE]) < target) if (clock64() - t0 > SPIN_LIMIT) { ctl[CW_ERROR] = 1u; break; }
+  }
+  __syncthreads();
+}
+
+// barrier over the ranks: block 0 stamps `epoch` into flag word `which + rank` of every peer and waits for every peer's stamp
+__device__ __forceinline__ void rank_barrier(const CommDev& c, unsigned* ctl, int which, unsigned epoch) {
+  if (blockIdx.x == 0 && threadIdx.x < c.world) {
+    const int p = threadIdx.x;
+    st_release_sys(c.ctrl[p] + which + c.rank, epoch);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(ctl + which + p) < epoch) if (clock64() - t0 > SPIN_LIMIT) { ctl[CW_ERROR] = 2u; break; }
+  }
+}
+
+__global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev c, float* __restrict__ buf, size_t n4) {
+  unsigned* ctl = c.ctrl[c.rank];
+  const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];     // stable until block 0 advances them after barrier A
+  const int par = epoch & 1u, G = gridDim.x;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)G * blockDim.x;
+  float4* buf4 = reinterpret_cast<float4*>(buf);
+  // ---- stage this rank's addends where the peers can read them
+  float4* mine = reinterpret_cast<float4*>(c.data[c.rank][par]);
+  for (size_t i = tid; i < n4; i += nthr) mine[i] = buf4[i];
+  grid_barrier(ctl, base + 1u * G);
+  rank_barrier(c, ctl, CW_FLAGS_A, epoch);                            // A: every rank's data[par] is complete and visible
+  grid_barrier(ctl, base + 2u * G);
+  const bool one_shot = n4 * sizeof(float4) <= ONE_SHOT_BYTES;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + (one_shot ? 2u : 4u) * G; }
+  if (one_shot) {
+    for (size_t i = tid; i < n4; i += nthr) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int p = 0; p < c.world; ++p) {
+        const float4 v = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      buf4[i] = acc;
+    }
+    return;
+  }
+  // ---- two-shot: reduce my slice, publish it, gather the others
+  const size_t slice = (n4 + c.world - 1) / c.world;
+  const size_t lo = (size_t)c.rank * slice, hi = lo + slice < n4 ? lo + slice : n4;
+  float4* myred = reinterpret_cast<float4*>(c.red[c.rank][par]);
+  for (size_t i = lo + tid; i < hi; i += nthr) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < c.world; ++p) {
+      const float4 v = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    myred[i - lo] = acc; buf4[i] = acc;
+  }
+  grid_barrier(ctl, base + 3u * G);
+  rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every rank's reduced slice is complete and visible
+  grid_barrier(ctl, base + 4u * G);
+  for (int q = 1; q < c.world; ++q) {
+    const int p = (c.rank + q) % c.world;                             // start at different owners: spread the NVSwitch load
+    const size_t plo = (size_t)p * slice, phi = plo + slice < n4 ? plo + slice : n4;
+    const float4* src = reinterpret_cast<const float4*>(c.red[p][par]);
+    for (size_t i = plo + tid; i < phi; i += nthr) buf4[i] = ld_peer(src + (i - plo));
+  }
+}
+
+static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_data, size_t* off_red, size_t* slice_floats) {
+  const size_t cap = (cap_floats + 3) / 4 * 4;
+  const size_t slice = ((cap / 4 + world - 1) / world) * 4;
+  *off_data = CTRL_BYTES; *off_red = CTRL_BYTES + 2 * cap * sizeof(float); *slice_floats = slice;
+  return *off_red + 2 * slice * sizeof(float);
+}
+
+extern "C" int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out) {
+  if (!comm_out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_floats == 0)
+    return dbw_fail_("dbw_comm_create: bad arguments (1 <= world <= 16, 0 <= rank < world, max_floats > 0)", cudaSuccess);
+  Comm* c = new Comm();
+  memset(c, 0, sizeof(Comm));
+  c->d.world = world; c->d.rank = rank; c->d.cap_floats = (max_floats + 3) / 4 * 4;
+  size_t od, orr, sl;
+  c->arena_bytes = arena_layout(max_floats, world, &od, &orr, &sl);
+  cudaError_t e = cudaMalloc(&c->arena, c->arena_bytes);
+  if (e != cudaSuccess) { delete c; return dbw_fail_("dbw_comm_create: cudaMalloc", e); }
+  e = cudaMemset(c->arena, 0, c->arena_bytes);
+  if (e != cudaSuccess) { cudaFree(c->arena); delete c; return dbw_fail_("dbw_comm_create: cudaMemset", e); }
+  CK(cudaDeviceSynchronize());
+  *comm_out = c;
+  return 0;
+}
+
+extern "C" int dbw_comm_ipc_handle(void* comm, void* out_handle64) {
+  Comm* c = (Comm*)comm;
+  if (!c || !out_handle64) return dbw_fail_("dbw_comm_ipc_handle: null argument", cudaSuccess);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->arena));
+  memcpy(out_handle64, &h, 64);
+  return 0;
+}
+
+extern "C" int dbw_comm_connect(void* comm, const void* all_handles) {
+  Comm* c = (Comm*)comm;
+  if (!c || !all_handles) return dbw_fail_("dbw_comm_connect: null argument", cudaSuccess);
+  size_t od, orr, sl;
+  arena_layout(c->d.cap_floats, c->d.world, &od, &orr, &sl);
+  for (int p = 0; p < c->d.world; ++p) {
+    void* base = c->arena;
+    if (p != c->d.rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)all_handles + (size_t)p * 64, 64);
+      CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    c->peer_base[p] = base;
+    char* b = (char*)base;
+    c->d.ctrl[p] = (unsigned*)b;
+    for (int q = 0; q < 2; ++q) {
+      c->d.data[p][q] = (float*)(b + od) + (size_t)q * c->d.cap_floats;
+      c->d.red[p][q] = (float*)(b + orr) + (size_t)q * sl;
+    }
+  }
+  c->connected = true;
+  return 0;
+}
+
+extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void* stream) {
+  Comm* c = (Comm*)comm;
+  if (!c || !buf) return dbw_fail_("dbw_comm_all_reduce: null argument", cudaSuccess);
+  if (!c->connected) return dbw_fail_("dbw_comm_all_reduce: dbw_comm_connect has not run", cudaSuccess);
+  if (n_floats % 4 || n_floats > c->d.cap_floats) return dbw_fail_("dbw_comm_all_reduce: n_floats must be a multiple of 4 and <= the capacity", cudaSuccess);
+  if (((uintptr_t)buf) % 16) return dbw_fail_("dbw_comm_all_reduce: buf must be 16-byte aligned", cudaSuccess);
+  if (c->d.world == 1 || n_floats == 0) return 0;
+  all_reduce_kernel<<<COMM_BLOCKS, COMM_THREADS, 0, (cudaStream_t)stream>>>(c->d, buf, n_floats / 4);
+  dbw_count_launch_();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return dbw_fail_("all_reduce_kernel", e);
+  return 0;
+}
+
+// 0: fine; 1 / 2: a grid / rank barrier timed out (a peer did not arrive within ~2 s) -- results are then garbage
+extern "C" int dbw_comm_error(void* comm, int32_t* out) {
+  Comm* c = (Comm*)comm;
+  if (!c || !out) return dbw_fail_("dbw_comm_error: null argument", cudaSuccess);
+  unsigned v = 0;
+  CK(cudaMemcpy(&v, (unsigned*)c->arena + CW_ERROR, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  *out = (int32_t)v;
+  return 0;
+}
+
+extern "C" int dbw_comm_destroy(void* comm) {
+  Comm* c = (Comm*)comm;
+  if (!c) return 0;
+  cudaDeviceSynchronize();
+  if (c->connected)
+    for (int p = 0; p < c->d.world; ++p) if (p != c->d.rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
+  cudaFree(c->arena);
+  delete c;
+  return 0;
+}

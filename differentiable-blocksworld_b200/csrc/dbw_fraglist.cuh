@@ -6,7 +6,7 @@
 // insertion is one 128-bit + one 32-bit shared load/store pair per shifted entry, the register cost is the entry count.
 // Each entry carries everything shading needs -- no geometry is re-derived for the kept fragments:
 //     A[k] = (pz, bits, signed squared distance, u)      V[k] = v
-//     bits = triangle slot (24 bits) | closest edge (2 bits: 0 = v0v1, 1 = v0v2, 2 = v1v2) << 24
+//     bits = triangle slot (24 bits) | closest edge (2 bits: 0 = v0v1, 1 = v0v2, 2 = v1v2) << 24 | outside (sd >= 0) << 26
 // Order = the tuple order of PyTorch3D's CPU rasterizer queue (depth, then face index); the two
 // halves of a z-clipped quad exclude each other (Appendix A3).  Plain C++ apart from the __device__ markers:
 // tests/host_math compiles it for the CPU and checks it against the oracle's queue.
@@ -15,6 +15,7 @@
 
 #define DBW_FRAG_SLOT_MASK 0x00ffffff
 #define DBW_FRAG_EDGE_SHIFT 24
+#define DBW_FRAG_OUTSIDE_BIT (1 << 26)
 
 // (pz, slot) < key of entry e ?   depths are >= 0, so their bit patterns order like the values
 __device__ __forceinline__ bool frag_key_less(unsigned pz_bits, int slot, float4 e) {
@@ -49,7 +50,7 @@ __device__ __forceinline__ int fraglist_offer(float4* A, float* V, int stride, i
     A[i * stride] = e; V[i * stride] = V[(i - 1) * stride];
     --i;
   }
-  A[i * stride] = make_float4(pz, __int_as_float(slot | (edge << DBW_FRAG_EDGE_SHIFT)), sd, u);
+  A[i * stride] = make_float4(pz, __int_as_float(slot | (edge << DBW_FRAG_EDGE_SHIFT) | (sd < 0.f ? 0 : DBW_FRAG_OUTSIDE_BIT)), sd, u);
   V[i * stride] = v;
   return n + 1;
 }

@@ -312,6 +312,7 @@ struct RasterParams {
   int alpha_stride;
   float inv_alpha_group;     // 1 / (faces sharing one opacity entry): alpha index = floor((face + 0.5) * inv_alpha_group)
   int n_static_faces;        // faces [0, n_static_faces) have constant vertices: the backward skips their vertex gradient
+  const int* view_rows;      // (B,2) [row_begin, row_end) rendered of each view, or NULL = all rows (row-band sharding)
   float sigma, blur, sqrt_blur, bg0, bg1, bg2;
   int clip_inside, persp, clipb, detach_bary;
   const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags; const int* view_bbox;
@@ -434,7 +435,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   // a warp covers an 8x4 pixel patch; 2x4 warps cover the 16x16 tile
   const int xi = tx0 + (warp & 1) * 8 + (lane & 7);
   const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
-  const bool live = xi < P.W && yi < P.H;
+  int row_lo = 0, row_hi = P.H;
+  if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
+  if (ty0 >= row_hi || ty0 + TILE_H <= row_lo) return;       // this view's rows of the tile belong to another rank
+  const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
   // NDC coordinates of the tile's 16 pixel columns and 16 rows (+X is left, +Y is up): 32 exact evaluations per CTA,
   // shared through shared memory, instead of two per thread
   __shared__ float s_ndc[TILE_W + TILE_H];
@@ -800,7 +804,10 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
   const int view = blockIdx.z;
   const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
   const int yi = blockIdx.y * (DBW_BWD_NT / 16) + (warp >> 1) * 4 + (lane >> 3);
-  const bool live = xi < P.W && yi < P.H;
+  int row_lo = 0, row_hi = P.H;
+  if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
+  if ((int)(blockIdx.y * (DBW_BWD_NT / 16)) >= row_hi || (int)((blockIdx.y + 1) * (DBW_BWD_NT / 16)) <= row_lo) return;
+  const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
   const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = live ? (size_t)yi * P.W + xi : 0;
@@ -923,8 +930,7 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
         if (want_alpha) { akey = alpha_index(P, view, face); aval = g_alpha * q.z; }
         if (want_dist) {
           // gradient w.r.t. the SIGNED squared distance: alpha = e(d) * fa, so fa * e = alpha
-          const float sd = frag[(size_t)k * plane].w;
-          const bool inside = sd < 0.f;
+          const bool inside = !(bits & DBW_FRAG_OUTSIDE_BIT);
           float g_sd = 0.f;
           if (P.clip_inside) { if (!inside) g_sd = g_alpha * (-q.x / P.sigma); }          // clamp(d, 0): flat inside the face
           else g_sd = g_alpha * (-q.x * (1.f - q.z) / P.sigma);
@@ -1111,7 +1117,7 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   memset(&P, 0, sizeof(P));
   P.B = s.n_views; P.H = s.height; P.W = s.width; P.K = s.faces_per_pixel; P.V = s.n_verts; P.F = s.n_faces; P.M = s.n_maps;
   P.alpha_stride = s.alpha_view_stride; P.inv_alpha_group = 1.f / (float)(s.alpha_group > 0 ? s.alpha_group : 1);
-  P.n_static_faces = s.n_static_faces;
+  P.n_static_faces = s.n_static_faces; P.view_rows = s.view_rows;
   P.sigma = s.sigma; P.blur = s.blur_radius; P.sqrt_blur = sqrtf(s.blur_radius); P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;

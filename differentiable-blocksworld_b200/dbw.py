@@ -223,6 +223,9 @@ class DifferentiableBlocksWorld(nn.Module):
     # ------------------------------------------------------------------ one step
     def forward(self, inp, labels=None):
         imgs = inp['imgs']
+        if inp.get('rows') is not None and not self._fused_loss_ok(imgs):
+            raise NotImplementedError("inp['rows'] (row-band sharding, parallel.py) needs the fused-loss path: decoupled rendering, "
+                                      'MSE, no perceptual term')
         if self._fused_loss_ok(imgs):
             return self.compute_losses(imgs, None, rgb_loss=self._scene_mse_fused(inp))
         env_rgba, fg_rgba = self._render_layers(inp)
@@ -403,7 +406,7 @@ class DifferentiableBlocksWorld(nn.Module):
                                            n_static_faces=self.bkg_n_faces),
                             ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer, alpha_group=self.BNF))
         return scene_mse(env_verts, env_atlas, blk_verts, atlas, alpha, inp['R'], inp['T'], inp['imgs'], self._passes[1],
-                         self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']))
+                         self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']), view_rows=inp.get('rows'))
 
     def _blocks_static(self, hard_filter):
         """eager (PyTorch ops) construction of the blocks scene with fixed shapes -- the reference's arithmetic

@@ -32,11 +32,11 @@ class ScenePass:
         self.map_table_host, self.r = map_table_host, renderer
         self.alpha_group, self.n_static_faces = alpha_group, n_static_faces
 
-    def settings(self, verts, maps, B, faces_alpha):
+    def settings(self, verts, maps, B, faces_alpha, view_rows=None):
         r = self.r
         return scene_settings(verts, self.faces, maps, self.map_table_host, B, r.cameras.intrinsics(), r.img_size, r.sigma,
                               r.faces_per_pixel, r.z_clip, r.detach_bary, r.clip_inside, r.background_color, faces_alpha,
-                              r.perspective_correct, False, r.blur_radius, True, self.alpha_group, self.n_static_faces)
+                              r.perspective_correct, False, r.blur_radius, True, self.alpha_group, self.n_static_faces, view_rows)
 
 
 def _workspace(cfg, dev):
@@ -120,13 +120,13 @@ class _SceneMSEFn(torch.autograd.Function):
 
 
 def scene_mse(env_verts, env_atlas, blk_verts, blk_atlas, blk_alpha, R, T, imgs, env_pass, blk_pass, blk_face_map,
-              n_total_views=None, return_rec=False):
+              n_total_views=None, return_rec=False, view_rows=None):
     """MSE between `imgs` (B,3,H,W) and the blocks composited over the environment, both rendered from raw scene tensors
     (float4 texel atlases from scene_ops.texture_atlas).  `n_total_views`: size of the GLOBAL batch the mean runs over
-    (view-sharded data parallelism).  Returns the loss, or (loss, rec) with a non-differentiable `rec`."""
+    (view-sharded data parallelism); `view_rows` (B,2) int32: the [row_begin, row_end) of each view this rank owns.  Returns the loss, or (loss, rec) with a non-differentiable `rec`."""
     B, _, H, W = imgs.shape
     inv = 1.0 / (float(n_total_views or B) * 3 * H * W)
     # settings are made out here: inside Function.forward grad mode is off and the passes would not save fragment state
-    cfgs = (env_pass.settings(env_verts, env_atlas, B, None), blk_pass.settings(blk_verts, blk_atlas, B, blk_alpha))
+    cfgs = (env_pass.settings(env_verts, env_atlas, B, None, view_rows), blk_pass.settings(blk_verts, blk_atlas, B, blk_alpha, view_rows))
     return _SceneMSEFn.apply(env_verts, env_atlas, blk_verts, blk_atlas, blk_alpha, R, T, imgs, env_pass, blk_pass,
                              blk_face_map, cfgs, inv, bool(return_rec))

@@ -8,10 +8,12 @@ import torch
 
 
 class GraphedStep:
-    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3, capture_all_reduce=False, generator=None):
+    def __init__(self, view_parallel, example_inp, n_total_views, warmup=3, capture_all_reduce=None, generator=None):
         self.vp, self.model = view_parallel, view_parallel.model
-        # optionally capture the gradient all-reduce INTO the graph.  Off by default: with this image's NCCL the captured
-        # collective hung on 2 GPUs (measured, round 1), so the all-reduce is issued right after the replay instead.
+        # The gradient all-reduce is captured INTO the graph when it is the peer-memory kernel (a plain launch).  An
+        # ncclAllReduce is issued right after the replay instead: captured, it hung on 2 GPUs with this image's NCCL (round 1).
+        if capture_all_reduce is None:
+            capture_all_reduce = view_parallel.graph_capturable_collective
         self.capture_all_reduce = capture_all_reduce and view_parallel.world_size > 1
         self.n_total = n_total_views
         dev = example_inp['imgs'].device
@@ -65,8 +67,9 @@ class GraphedStep:
             self.vp.bucket.all_reduce(self.vp.group)
         return losses
 
-    def run(self, inp=None, non_blocking=True):
-        """inp: optional dict of (host or device) tensors for this step, copied into the static buffers."""
+    def run(self, inp=None, non_blocking=True, all_reduce=True):
+        """inp: optional dict of (host or device) tensors for this step, copied into the static buffers.
+        all_reduce=False skips the collective when it is issued after the replay (a captured one always runs)."""
         if inp is not None:
             for k, v in inp.items():
                 if k in self.static_inp:
@@ -78,7 +81,7 @@ class GraphedStep:
         if self.overlap_buf is not None:
             self.overlap_buf.uniform_(generator=self.gen)
         self.graph.replay()
-        if not self.capture_all_reduce:
+        if not self.capture_all_reduce and all_reduce:
             self.vp.bucket.all_reduce(self.vp.group)
         return self.losses
 
@@ -88,7 +91,7 @@ class PipelinedGraphedStep:
     host->device on a side stream (what a prefetching DataLoader does for src/trainer.py:141).  `run(host_inp)` returns
     the losses of the step that consumed `host_inp`."""
 
-    def __init__(self, view_parallel, example_inp, n_total_views, capture_all_reduce=False):
+    def __init__(self, view_parallel, example_inp, n_total_views, capture_all_reduce=None):
         gen = torch.Generator(device=example_inp['imgs'].device)
         gen.manual_seed(view_parallel.seed)
         self.steps = [GraphedStep(view_parallel, example_inp, n_total_views, capture_all_reduce=capture_all_reduce, generator=gen)
@@ -107,7 +110,7 @@ class PipelinedGraphedStep:
                     self.steps[b].static_inp[k].copy_(v, non_blocking=True)
             self.ready[b].record(self.copy_stream)
 
-    def run(self, host_inp, next_host_inp=None):
+    def run(self, host_inp, next_host_inp=None, all_reduce=True):
         """consume `host_inp` (staged now unless it was prefetched as the previous call's `next_host_inp`) and
         prefetch `next_host_inp` for the following call."""
         b = self.i % 2
@@ -122,7 +125,7 @@ class PipelinedGraphedStep:
         else:
             self.primed = False
         cur.wait_event(self.ready[b])
-        losses = self.steps[b].run()
+        losses = self.steps[b].run(all_reduce=all_reduce)
         self.free[b].record(cur)
         self.i += 1
         return losses

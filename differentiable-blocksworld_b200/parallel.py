@@ -11,8 +11,12 @@ NVLink 5 / NVSwitch then gives every rank the full gradient.  Correctness condit
     divided by the world size before the SUM;
   * the opacity noise (dbw.py:300-301) and the overlap sample points (dbw.py:393) come from a generator that every
     rank seeds identically at every step."""
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_views(n_views, world_size, rank):
@@ -22,6 +26,61 @@ def shard_views(n_views, world_size, rank):
     return slice(start, start + base + (1 if rank < extra else 0))
 
 
+ROW_BAND = 16          # rows per shardable band: the tallest raster tile (16 x 16, the K <= 4 forward), so tiles stay whole
+
+
+def shard_row_bands(n_views, height, world_size, rank, band=ROW_BAND):
+    """Balanced sharding at (view, row band) granularity: the n_views * ceil(height / band) bands of a step, in (view, row)
+    order, are cut into world_size contiguous runs whose lengths differ by at most one band (49 views of 400 rows over 8
+    ranks: 153 or 154 bands of 16 rows each, i.e. 6.12 views per rank instead of 7 for the largest whole-view shard).
+    Returns this rank's pieces as [(view, row_begin, row_end)], one per view it touches."""
+    per_view = -(-height // band)
+    total = n_views * per_view
+    base, extra = divmod(total, world_size)
+    start = rank * base + min(rank, extra)
+    stop = start + base + (1 if rank < extra else 0)
+    pieces = []
+    for v in range(start // per_view, -(-stop // per_view) if stop > start else start // per_view):
+        b0, b1 = max(start, v * per_view) - v * per_view, min(stop, (v + 1) * per_view) - v * per_view
+        if b1 > b0:
+            pieces.append((v, b0 * band, min(b1 * band, height)))
+    return pieces
+
+
+class PeerAllReduce:
+    """The hand-written NVLink all-reduce of csrc/dbw_comm.cu (include/dbw_render.h dbw_comm_*): every rank exports its
+    arena with a CUDA IPC handle, the handles are all-gathered once through torch.distributed, and from then on an
+    all-reduce is ONE kernel launch on the current stream -- capturable inside the step's CUDA graph, no NCCL involved."""
+
+    def __init__(self, max_floats, device, group=None):
+        L = _lib.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.handle = ctypes.c_void_p()
+        _lib.check(L.dbw_comm_create(self.world, self.rank, max_floats, ctypes.byref(self.handle)), 'dbw_comm_create')
+        mine = (ctypes.c_ubyte * 64)()
+        _lib.check(L.dbw_comm_ipc_handle(self.handle, mine), 'dbw_comm_ipc_handle')
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        gathered = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(gathered, t, group=group)
+        blob = bytes(torch.cat(gathered).cpu().tolist())
+        _lib.check(L.dbw_comm_connect(self.handle, blob), 'dbw_comm_connect')
+        dist.barrier(group)
+
+    def all_reduce(self, flat):
+        _lib.check(_lib.lib().dbw_comm_all_reduce(self.handle, ctypes.c_void_p(flat.data_ptr()), flat.numel(),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'dbw_comm_all_reduce')
+
+    def error(self):
+        out = ctypes.c_int32(0)
+        _lib.check(_lib.lib().dbw_comm_error(self.handle, ctypes.byref(out)), 'dbw_comm_error')
+        return out.value
+
+    def close(self):
+        if self.handle:
+            _lib.lib().dbw_comm_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+
 class GradBucket:
     """All parameter gradients as views into one flat buffer -> a single all-reduce per step."""
 
@@ -29,7 +88,9 @@ class GradBucket:
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
-        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        self.n = n
+        self.flat = torch.zeros((n + 3) // 4 * 4, dtype=ref.dtype, device=ref.device)     # padded: 128-bit all-reduce lanes
+        self.peer = None               # PeerAllReduce once ViewParallel has set it up
         self._zeros = {}
         off, self.views = 0, []
         for p in self.params:
@@ -57,13 +118,16 @@ class GradBucket:
                 g = self._zeros[id(p)]
             pieces.append(g.reshape(-1))
         with torch.no_grad():
-            torch.cat(pieces, out=self.flat)
+            torch.cat(pieces, out=self.flat[:self.n])
         for p, v in zip(self.params, self.views):
             p.grad = v
 
     def all_reduce(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if self.peer is not None:
+                self.peer.all_reduce(self.flat)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
 
     @property
     def nbytes(self):
@@ -74,21 +138,45 @@ class ViewParallel:
     """Wraps a model whose `forward(inp, labels)` returns a dict of losses incl. 'total' (the DBW contract,
     src/trainer.py:141-143) and which exposes `n_total_views` and `noise_generator` attributes."""
 
-    VIEW_KEYS = ('imgs', 'R', 'T')
+    VIEW_KEYS = ('imgs', 'R', 'T', 'K')
 
-    def __init__(self, model, group=None, seed=227391):
+    def __init__(self, model, group=None, seed=227391, row_bands=False, collective='nccl'):
+        """collective: 'nccl' (torch.distributed all_reduce; also what gloo groups use), 'p2p' (the NVLink peer-memory kernel
+        of csrc/dbw_comm.cu, CUDA-graph capturable) or 'auto' (p2p if it initialises on this node, else nccl)"""
         self.model, self.group, self.seed = model, group, seed
+        self.row_bands = row_bands          # shard at (view, row band) granularity (needs the model's fused-loss path)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket = GradBucket(model.parameters())
         self._step = 0
+        self.collective_name = 'none (1 rank)' if self.world_size == 1 else 'ncclAllReduce'
+        if self.world_size > 1 and collective in ('p2p', 'auto') and self.bucket.flat.is_cuda:
+            try:
+                self.bucket.peer = PeerAllReduce(self.bucket.flat.numel(), self.bucket.flat.device, group)
+                self.collective_name = 'hand-written NVLink peer-memory kernel (dbw_comm_all_reduce), inside the CUDA graph'
+            except Exception as exc:          # e.g. no peer access between the GPUs of this node
+                if collective == 'p2p':
+                    raise
+                print(f'[dbw_b200] peer-memory all-reduce unavailable ({exc}); using NCCL')
+
+    @property
+    def graph_capturable_collective(self):
+        return self.bucket.peer is not None
 
     def shard(self, inp):
+        """this rank's part of a batch: whole views, or -- with row_bands -- the views it touches plus `rows` (B_local, 2):
+        the [row_begin, row_end) of each that it renders (the model hands them to the kernels, dbw_render.h view_rows)"""
         B = len(inp['imgs'])
-        sl = shard_views(B, self.world_size, self.rank)
         out = dict(inp)
+        if self.row_bands and self.world_size > 1:
+            pieces = shard_row_bands(B, inp['imgs'].shape[-2], self.world_size, self.rank)
+            idx = [v for v, _, _ in pieces]
+            sl = slice(idx[0], idx[-1] + 1) if idx else slice(0, 0)
+            out['rows'] = torch.tensor([[a, b] for _, a, b in pieces], dtype=torch.int32).reshape(-1, 2)
+        else:
+            sl = shard_views(B, self.world_size, self.rank)
         for k in self.VIEW_KEYS:
-            if k in inp:
+            if k in inp and torch.is_tensor(inp[k]) and inp[k].shape[:1] == (B,):
                 out[k] = inp[k][sl]
         return out, B
 
@@ -99,7 +187,7 @@ class ViewParallel:
             self.model.noise_generator = g
         g.manual_seed(self.seed + self._step)      # identical on every rank, fresh every step
 
-    def forward_backward(self, inp, labels=None, already_sharded=False, n_total_views=None):
+    def forward_backward(self, inp, labels=None, already_sharded=False, n_total_views=None, all_reduce=True):
         """zero grads -> local forward -> backward -> ONE all-reduce.  Returns the (local) loss dict."""
         if not already_sharded:
             inp, n_total_views = self.shard(inp)
@@ -108,7 +196,8 @@ class ViewParallel:
         self._step += 1
         losses = self.model(inp, labels)
         self.bucket.backward(self.weighted_total(losses, len(inp['imgs']), n_total_views))
-        self.bucket.all_reduce(self.group)
+        if all_reduce:
+            self.bucket.all_reduce(self.group)
         return losses
 
     def weighted_total(self, losses, n_local_views, n_total_views):

@@ -132,7 +132,8 @@ def _device_map_table(table_host, dev):
 
 def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, z_clip, background, clip_inside=True,
                   perspective_correct=True, clip_barycentric=True, detach_bary=False, verts_are_ndc=False, eps=EPS,
-                  n_map_floats=0, maps_are_texels4=False, save_fragment_state=False, alpha_group=1, n_static_faces=0):
+                  n_map_floats=0, maps_are_texels4=False, save_fragment_state=False, alpha_group=1, n_static_faces=0,
+                  view_rows=None):
     s = DbwRenderSettings()
     s.n_views, s.height, s.width, s.faces_per_pixel = B, H, W, K
     s.n_verts, s.n_faces, s.n_maps, s.alpha_view_stride = V, Fn, M, alpha_stride
@@ -147,12 +148,17 @@ def make_settings(B, H, W, K, V, Fn, M, alpha_stride, intr, sigma, blur_radius, 
     s.maps_are_texels4 = int(maps_are_texels4)
     s.save_fragment_state = int(save_fragment_state)
     s.alpha_group, s.n_static_faces = int(alpha_group), int(n_static_faces)
+    if view_rows is not None:
+        if view_rows.dtype != torch.int32 or not view_rows.is_cuda or tuple(view_rows.shape) != (B, 2) or not view_rows.is_contiguous():
+            raise DbwError('view_rows must be a contiguous CUDA int32 tensor of shape (B, 2)')
+        s.view_rows = view_rows.data_ptr()
+        s._view_rows_owner = view_rows            # keeps the device buffer alive as long as the settings
     return s
 
 
 def scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip=None,
                    detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None, perspective_correct=True,
-                   verts_are_ndc=False, blur_radius=None, maps_are_texels4=False, alpha_group=1, n_static_faces=0):
+                   verts_are_ndc=False, blur_radius=None, maps_are_texels4=False, alpha_group=1, n_static_faces=0, view_rows=None):
     """(DbwRenderSettings, device map table) of one render pass over raw scene tensors.
     alpha_group: faces per opacity entry (faces_alpha then has F / alpha_group [or B * that] entries);
     n_static_faces: leading faces whose vertices are constants (no vertex gradient wanted)."""
@@ -173,14 +179,15 @@ def scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigm
                         n_map_floats=(maps.numel() // 4 * 3) if maps_are_texels4 else maps.numel(),
                         maps_are_texels4=maps_are_texels4,
                         # what a backward streams: one 16 B record per kept fragment, written only when one may follow
-                        save_fragment_state=torch.is_grad_enabled(), alpha_group=alpha_group, n_static_faces=n_static_faces)
+                        save_fragment_state=torch.is_grad_enabled(), alpha_group=alpha_group, n_static_faces=n_static_faces,
+                        view_rows=view_rows)
     return cfg, map_table
 
 
 def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, intr, image_size, sigma, faces_per_pixel,
                  z_clip=None, detach_bary=False, clip_inside=True, background=(0., 0., 0.), faces_alpha=None,
                  perspective_correct=True, verts_are_ndc=False, blur_radius=None, return_ids=False, maps_are_texels4=False,
-                 face_shade=None, return_dists=False, alpha_group=1, n_static_faces=0):
+                 face_shade=None, return_dists=False, alpha_group=1, n_static_faces=0, view_rows=None):
     """Functional form over raw tensors (used by Renderer.forward and by the parity tests).
     verts (V,3) [or (B,V,3) NDC], faces (F,3) int32, faces_uvs (F,3,2), face_map (F) int32, maps flat float buffer,
     map_table_host [(offset,H,W)], R (B,3,3), T (B,3), faces_alpha None | (F,) | (B*F,).
@@ -189,7 +196,7 @@ def render_scene(verts, faces, faces_uvs, face_map, maps, map_table_host, R, T, 
     B = R.shape[0] if R is not None else verts.shape[0]
     cfg, map_table = scene_settings(verts, faces, maps, map_table_host, B, intr, image_size, sigma, faces_per_pixel, z_clip,
                                     detach_bary, clip_inside, background, faces_alpha, perspective_correct, verts_are_ndc,
-                                    blur_radius, maps_are_texels4, alpha_group, n_static_faces)
+                                    blur_radius, maps_are_texels4, alpha_group, n_static_faces, view_rows)
     if R is None:
         R = torch.eye(3, device=dev)[None].expand(B, -1, -1)
         T = torch.zeros(B, 3, device=dev)

@@ -65,6 +65,10 @@ typedef struct DbwRenderSettings {
                                  (src/model/dbw.py:219 repeat_interleave's it per face; that is alpha_group = 1)            */
   int32_t n_static_faces;     /* faces [0, n_static_faces) have constant vertices (the background sphere of the environment,
                                  src/model/dbw.py:267-280): the backward skips their vertex gradient                        */
+  const int32_t* view_rows;   /* DEVICE (B,2) int32 or NULL: [row_begin, row_end) of each view that this call renders / differentiates.
+                                 Rows outside are left untouched in every output (and contribute nothing to a fused loss):
+                                 a data-parallel step shards at (view, row band) granularity, so 49 views split evenly
+                                 over 8 ranks                                                                   */
 } DbwRenderSettings;
 
 /* Texture table entry: map m lives at maps[offset .. offset + height*width*3), row-major (H, W, 3). */
@@ -233,6 +237,24 @@ uint64_t dbw_launch_count(void);
 void dbw_timing_enable(int on);
 int dbw_timing_read(int kind, int K, double* total_ms, int* count);
 void dbw_timing_reset(void);
+
+/*
+ * The step's one gradient exchange (views shard with no data-path collective; ONE all-reduce(SUM) of the flat
+ * parameter-gradient bucket) as a hand-written all-reduce over NVLink peer memory -- a plain kernel launch on `stream`,
+ * hence capturable inside the step's CUDA graph.  One process per GPU of one node:
+ *   dbw_comm_create      allocates this rank's arena (2 x max_floats + control; cudaMalloc)
+ *   dbw_comm_ipc_handle  64-byte cudaIpcMemHandle of the arena, to be all-gathered by the caller (torch.distributed)
+ *   dbw_comm_connect     opens the peers' arenas: all_handles = world x 64 bytes in rank order
+ *   dbw_comm_all_reduce  in-place SUM of buf[0..n_floats) over the ranks (n_floats % 4 == 0, buf 16-byte aligned); every rank
+ *                        adds in rank order: bit-identical results everywhere.  One-shot below 512 KB, two-shot above
+ *   dbw_comm_error       0, or which barrier timed out (a peer did not arrive within ~2 s: results are garbage, no hang)
+ */
+int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out);
+int dbw_comm_ipc_handle(void* comm, void* out_handle64);
+int dbw_comm_connect(void* comm, const void* all_handles);
+int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void* stream);
+int dbw_comm_error(void* comm, int32_t* out);
+int dbw_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_settings_struct_layout_and_workspace_query():
     from dbw_b200 import _lib
     from dbw_b200.renderer import make_settings
-    assert ctypes.sizeof(_lib.DbwRenderSettings) == _lib.lib().dbw_sizeof_settings() == 29 * 4
+    assert ctypes.sizeof(_lib.DbwRenderSettings) == _lib.lib().dbw_sizeof_settings() == 29 * 4 + 4 + 8       # 29 int32/float fields, padding, one pointer
     assert ctypes.sizeof(_lib.DbwMapDesc) == 16
     s = make_settings(49, 400, 400, 10, 420, 800, 10, 0, (4.8, 4.8, 0., 0.), 1e-4, 9.21e-4, 0.001, (0, 0, 0),
                       n_map_floats=10 * 256 * 279 * 3)

@@ -183,6 +183,79 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+class _ToyRows(torch.nn.Module):
+    """per-pixel 'render' loss over (B,H,W) images that honours inp['rows'] the way the kernels do (dbw_render.h view_rows)"""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.linspace(0.1, 0.9, 5))
+        self.textures = torch.nn.Parameter(torch.ones(3))
+        self.n_total_views, self.noise_generator = None, None
+
+    def forward(self, inp, labels=None):
+        imgs = inp['imgs']
+        B, H, W = imgs.shape
+        pred = imgs * self.w[None, None] + self.textures.sum() * inp['R'].sum((1, 2))[:, None, None]
+        err = (pred - 0.5) ** 2
+        if inp.get('rows') is not None:
+            y = torch.arange(H)[None, :, None]
+            err = err * ((y >= inp['rows'][:, 0, None, None]) & (y < inp['rows'][:, 1, None, None]))
+        rgb = err.sum() / (self.n_total_views * H * W)
+        reg = self.textures.pow(2).sum()
+        return {'rgb': rgb, 'tv': reg, 'total': rgb + reg}
+
+
+def _worker_rows(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from dbw_b200.parallel import ViewParallel
+    torch.manual_seed(0)
+    vp = ViewParallel(_ToyRows(), seed=123, row_bands=True)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(5, 48, 5, generator=g), 'R': torch.rand(5, 3, 3, generator=g), 'T': torch.rand(5, 3, generator=g)}
+    local, n_total = vp.shard(inp)
+    out[f'rows{rank}'] = local['rows'].clone()
+    vp.forward_backward(inp)
+    out[rank] = vp.bucket.flat.clone()
+    dist.destroy_process_group()
+
+
+def test_row_band_view_parallel_gradients_equal_single_process_gloo():
+    """world_size-2 gloo run with (view, row band) sharding: the ranks split a view in the middle; the summed gradient is the
+    single-process gradient of the same step"""
+    from dbw_b200.parallel import ViewParallel
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_worker_rows, args=(2, port, out), nprocs=2, join=True)
+    assert out['rows0'].tolist() == [[0, 48], [0, 48], [0, 32]] and out['rows1'].tolist() == [[32, 48], [0, 48], [0, 48]]
+    torch.manual_seed(0)
+    vp = ViewParallel(_ToyRows(), seed=123)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(5, 48, 5, generator=g), 'R': torch.rand(5, 3, 3, generator=g), 'T': torch.rand(5, 3, generator=g)}
+    vp.forward_backward(inp)
+    assert torch.allclose(out[0], out[1]) and torch.allclose(out[0], vp.bucket.flat, rtol=1e-5, atol=1e-7)
+
+
+def test_row_band_sharding_is_a_balanced_partition():
+    """parallel.shard_row_bands: every (view, row) exactly once, contiguous pieces, loads within one 16-row band"""
+    from dbw_b200.parallel import shard_row_bands, ROW_BAND
+    for n_views, H, world in [(49, 400, 8), (49, 400, 2), (64, 576, 8), (256, 800, 8), (3, 50, 4), (1, 16, 4), (5, 400, 1)]:
+        seen = torch.zeros(n_views, H, dtype=torch.int32)
+        loads = []
+        for r in range(world):
+            pieces = shard_row_bands(n_views, H, world, r)
+            assert [v for v, _, _ in pieces] == sorted(set(v for v, _, _ in pieces))       # one piece per touched view, in order
+            for v, a, b in pieces:
+                assert 0 <= a < b <= H and a % ROW_BAND == 0
+                seen[v, a:b] += 1
+            loads.append(sum(b - a for _, a, b in pieces))
+        assert (seen == 1).all(), (n_views, H, world)
+        assert max(loads) - min(loads) <= ROW_BAND, loads
+    # 49 views over 8 ranks: 6.12 views' worth of rows each instead of 7 whole views on the busiest rank
+    assert max(sum(b - a for _, a, b in shard_row_bands(49, 400, 8, r)) for r in range(8)) == 2464
+
+
 def test_view_parallel_gradients_equal_single_process_gloo():
     """world_size-2 gloo run: sharded views + ONE all-reduce == the single-process gradient of the same step."""
     from dbw_b200.parallel import ViewParallel
@@ -213,8 +286,9 @@ def test_grad_bucket_backward_gathers_like_accumulation():
     bucket = GradBucket([a, b, unused])
     bucket.backward(loss_fn())
     got = bucket.flat.clone()
+    assert bucket.n == 21 and bucket.flat.numel() == 24             # padded to whole 128-bit lanes for the all-reduce kernel
     ga, gb = torch.autograd.grad(loss_fn(), [a, b])
-    ref = torch.cat([ga.reshape(-1), gb.reshape(-1), torch.zeros(4)])
+    ref = torch.cat([ga.reshape(-1), gb.reshape(-1), torch.zeros(4 + 3)])
     assert torch.allclose(got, ref, rtol=1e-6, atol=1e-7)
     for p in (a, b, unused):
         assert p.grad is not None and p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr()
