@@ -11,8 +11,8 @@
 //   verts_ndc  (B,V,3)            projected vertices (x_ndc, y_ndc, z_view)
 //   bbox       (B,2F) float4      blur-expanded NDC bbox of each face slot (xmin,xmax,ymin,ymax); xmin=+inf: empty
 //   rec        (B,2F,4) float4    v0xy v1xy | v2xy z0 z1 | z2 face neighbor flags | 1/area, 1/|e01|^2, 1/|e02|^2, 1/|e12|^2
-//   rec2       (B,2F,2) float4    u0 v0 u1 v1 | u2 v2 map_texel_offset (H<<16|W)   (static per face, replicated per view so
-//                                 that shading needs ONE dependent load level after the face id)
+//   rec2       (B,2F,2) float4    u0 v0 u1 v1 | u2 v2 map_id -   (static per face, replicated per view: one load level after the
+//                                 face id); the map table itself (first texel, H, W of each map) is staged in shared memory
 //   maps4      (sum H*W) float4   the caller's (H,W,3) maps re-packed as RGB+pad texels: one 128-bit load per bilinear tap
 //   conv       (B,2F,9)           barycentric conversion (clipped -> original face), only for clipped slots
 //   slots [0,F) hold each face's (first) triangle, slots [F,2F) the second triangle of a z-clipped quad.
@@ -85,7 +85,7 @@ extern "C" void dbw_timing_reset(void) {
 
 struct Workspace {
   float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4;
-  float4* frag; unsigned char* nfrag; size_t total;
+  float4* frag; float4* frag_rgb; unsigned char* nfrag; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
   Workspace w; char* p = (char*)base; size_t off = 0;
@@ -100,6 +100,7 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   const size_t npx = B * (size_t)s.height * s.width;
   w.frag = (float4*)(p + off);     off += s.save_fragment_state ? align_up(npx * (size_t)s.faces_per_pixel * sizeof(float4)) : 0;
+  w.frag_rgb = (float4*)(p + off); off += s.save_fragment_state ? align_up(npx * (size_t)s.faces_per_pixel * sizeof(float4)) : 0;
   w.nfrag = (unsigned char*)(p + off); off += s.save_fragment_state ? align_up(npx) : 0;
   w.total = off; return w;
 }
@@ -130,7 +131,8 @@ static int validate(const DbwRenderSettings* s) {
   if (s->n_faces % ag) return fail("n_faces must be a multiple of alpha_group");
   if (s->alpha_view_stride != 0 && s->alpha_view_stride != s->n_faces / ag) return fail("alpha_view_stride must be 0 or n_faces / alpha_group");
   if (s->n_static_faces < 0 || s->n_static_faces > s->n_faces) return fail("n_static_faces out of range [0, n_faces]");
-  if (2 * (long long)s->n_faces > DBW_FRAG_SLOT_MASK) return fail("too many faces: triangle slots are stored in 24 bits");
+  if (2 * (long long)s->n_faces > DBW_FRAG_SLOT_MASK) return fail("too many faces: triangle slots are stored in 20 bits");
+  if (s->n_maps > DBW_FRAG_MAX_MAPS) return fail("too many texture maps: a fragment's map is stored in 9 bits");
   if (s->sigma < 0.f || s->blur_radius < 0.f) return fail("sigma and blur_radius must be >= 0");
   if (s->n_map_floats <= 0 || s->n_map_floats % 3 != 0) return fail("n_map_floats must be a positive multiple of 3");
   return 0;
@@ -271,7 +273,8 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   if (mid < 0) r.ntri = 0;                                 // face disabled by the caller (e.g. a killed block): never rasterized
   const DbwMapDesc md = map_table[mid < 0 ? 0 : mid];
   const float4 uv01 = make_float4(fu[0], fu[1], fu[2], fu[3]);
-  const float4 uv2m = make_float4(fu[4], fu[5], __int_as_float(md.offset / 3), __int_as_float((md.height << 16) | md.width));
+  (void)md;
+  const float4 uv2m = make_float4(fu[4], fu[5], __int_as_float(mid < 0 ? 0 : mid), 0.f);
   write_slot(bbox, rec, rec2, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur, uv01, uv2m);
   write_slot(bbox, rec, rec2, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur, uv01, uv2m);
   if (r.ntri == 2) atomicOr(&view_flags[b], 1);
@@ -311,6 +314,7 @@ struct RasterParams {
   int B, H, W, K, V, F, M;
   int alpha_stride;
   float inv_alpha_group;     // 1 / (faces sharing one opacity entry): alpha index = floor((face + 0.5) * inv_alpha_group)
+  int n_alpha;               // opacity entries per view = F / alpha_group
   int n_static_faces;        // faces [0, n_static_faces) have constant vertices: the backward skips their vertex gradient
   const int* view_rows;      // (B,2) [row_begin, row_end) rendered of each view, or NULL = all rows (row-band sharding)
   float sigma, blur, sqrt_blur, bg0, bg1, bg2;
@@ -319,7 +323,9 @@ struct RasterParams {
   const float4* maps4;
   const float* faces_alpha;
   float* out_rgba; int* topk;        // topk may be NULL
+  const DbwMapDesc* map_table;   // (M) device: offset (3 * first texel), height, width of each map
   float4* frag;              // (B,K,H,W) saved fragment records {bits, u, v, signed dist} or NULL
+  float4* frag_rgb;          // (B,K,H,W) their colours {r, g, b, -}: the backward's d/d(opacity) needs colour . gradient
   unsigned char* nfrag;      // (B,H,W) number of records written per pixel
   const float* face_shade;   // (B,F,3) per-view per-face colour multiplier (flat shading) or NULL
   float* out_dists;          // (B,K,H,W) signed squared distances of the kept fragments (-1 = empty) or NULL
@@ -363,9 +369,17 @@ __device__ __forceinline__ int alpha_index(const RasterParams& P, int view, int 
 
 // bilinear colour of a fragment from its UV (shared by forward shading and the detach_bary backward)
 struct Texel4 { TexTap tap; f3 c00, c01, c10, c11, color; };
-__device__ __forceinline__ void fetch_color(const RasterParams& P, float u, float v, float4 q1, Texel4& s) {
-  const int hw = __float_as_int(q1.w);
-  s.tap = tex_tap(u, v, __float_as_int(q1.z), hw >> 16, hw & 0xffff);
+// the map table in shared memory: (first texel, H, W, -) per map, staged once per CTA -- a fragment's tap addresses then
+// depend on no global load
+__device__ __forceinline__ void stage_map_table(const RasterParams& P, int4* s_desc, int tid, int nthreads) {
+  for (int m = tid; m < P.M; m += nthreads) {
+    const DbwMapDesc d = P.map_table[m];
+    s_desc[m] = make_int4(d.offset / 3, d.height, d.width, 0);
+  }
+}
+__device__ __forceinline__ void tap_only(float u, float v, int4 d, Texel4& s) { s.tap = tex_tap(u, v, d.x, d.y, d.z); }
+__device__ __forceinline__ void fetch_color(const RasterParams& P, float u, float v, int4 d, Texel4& s) {
+  s.tap = tex_tap(u, v, d.x, d.y, d.z);
   s.c00 = ld_texel(P.maps4, s.tap.i00); s.c01 = ld_texel(P.maps4, s.tap.i01);
   s.c10 = ld_texel(P.maps4, s.tap.i10); s.c11 = ld_texel(P.maps4, s.tap.i11);
   s.color.x = s.c00.x * s.tap.w00 + s.c01.x * s.tap.w01 + s.c10.x * s.tap.w10 + s.c11.x * s.tap.w11;
@@ -377,14 +391,15 @@ __device__ __forceinline__ void fetch_color(const RasterParams& P, float u, floa
 struct Shade {
   TriGeom t; Bary b; f3 bu;       // bu: barycentrics w.r.t. the ORIGINAL face (after un-clipping)
   float4 uv01; float u2, v2;      // per-face-vertex UVs
-  float u, v; float4 q1;
+  float u, v; int map_id;
 };
 
 __device__ __forceinline__ void shade_geometry(const RasterParams& P, int view, int slot, f2 p, Shade& s) {
   const size_t gs = (size_t)view * 2 * P.F + slot;
   const float4 r0 = __ldg(&P.rec[gs * 4]), r1 = __ldg(&P.rec[gs * 4 + 1]), r2 = __ldg(&P.rec[gs * 4 + 2]), r3 = __ldg(&P.rec[gs * 4 + 3]);
   const float4 q0 = __ldg(&P.rec2[gs * 2]);
-  s.q1 = __ldg(&P.rec2[gs * 2 + 1]);
+  const float4 q1 = __ldg(&P.rec2[gs * 2 + 1]);
+  s.map_id = __float_as_int(q1.z);
   s.t = unpack_tri(r0, r1, r2, r3);
   s.b = eval_bary(p, s.t, P.persp, P.clipb);
   s.bu = s.b.bc;
@@ -394,23 +409,24 @@ __device__ __forceinline__ void shade_geometry(const RasterParams& P, int view, 
     s.bu.y = s.b.bc.x * cv[1] + s.b.bc.y * cv[4] + s.b.bc.z * cv[7];
     s.bu.z = s.b.bc.x * cv[2] + s.b.bc.y * cv[5] + s.b.bc.z * cv[8];
   }
-  s.uv01 = q0; s.u2 = s.q1.x; s.v2 = s.q1.y;
-  s.u = s.bu.x * q0.x + s.bu.y * q0.z + s.bu.z * s.q1.x;
-  s.v = s.bu.x * q0.y + s.bu.y * q0.w + s.bu.z * s.q1.y;
+  s.uv01 = q0; s.u2 = q1.x; s.v2 = q1.y;
+  s.u = s.bu.x * q0.x + s.bu.y * q0.z + s.bu.z * q1.x;
+  s.v = s.bu.x * q0.y + s.bu.y * q0.w + s.bu.z * q1.y;
 }
 
 // Resident CTAs per SM each raster kernel is compiled for (register cap = 65536 / (threads * CTAs)).
 #ifndef DBW_FWD_SMALLK_MINB
-#define DBW_FWD_SMALLK_MINB 5     // CTAs of DBW_FWD_NT_SMALLK threads
+#define DBW_FWD_SMALLK_MINB 5     // CTAs of DBW_FWD_NT_SMALLK threads (51 registers; 4 was slower on B200)
 #endif
 #ifndef DBW_FWD_MINB
-#define DBW_FWD_MINB 8            // CTAs of DBW_FWD_NT threads
+#define DBW_FWD_MINB 7            // CTAs of DBW_FWD_NT threads: shared memory (25.6 KB of lists at K = 10 + 5 KB tile list) allows 7;
+                                  // measured on B200: 7 CTAs x 72 registers beats 6 x 80 by 7 %
 #endif
 #ifndef DBW_BWD_DETACH_MINB
-#define DBW_BWD_DETACH_MINB 8     // backward without the barycentric path, CTAs of DBW_BWD_NT threads (64 registers)
+#define DBW_BWD_DETACH_MINB 7     // backward without the barycentric path, CTAs of DBW_BWD_NT threads (72 registers)
 #endif
 #ifndef DBW_BWD_BARY_MINB
-#define DBW_BWD_BARY_MINB 5       // backward with the barycentric path: more live state (96 registers)
+#define DBW_BWD_BARY_MINB 4       // backward with the barycentric path: more live state (128 registers)
 #endif
 
 // One kernel for every K: the per-pixel list of the K nearest fragments lives in (dynamic) shared memory (dbw_fraglist.cuh).
@@ -418,14 +434,17 @@ __device__ __forceinline__ void shade_geometry(const RasterParams& P, int view, 
 template <int NT, bool EP>
 __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_MINB) raster_forward_kernel(const RasterParams P) {
   // faces a tile lists at once (more: chunked path)
-  constexpr int CAP = NT <= 128 ? 128 : 256;
-  static_assert(CAP >= NT, "a scan batch adds up to NT entries");
+#ifndef DBW_LIST_CAP
+#define DBW_LIST_CAP 64      // tile lists average 17 faces (max 64) at cfg 2: 5 KB instead of 10.5 KB buys a 7th resident CTA
+#endif
+  constexpr int CAP = NT <= 128 ? DBW_LIST_CAP : 256;
+  static_assert(CAP >= NT || CAP == 64, "a scan batch adds up to NT entries");
   __shared__ float4 s_bbox[CAP];
   __shared__ float4 s_rec[CAP * 4];
   __shared__ int s_slot[CAP];
   __shared__ int s_count;
   __shared__ __align__(8) uint64_t s_bar;      // mbarrier of the TMA record gather
-  extern __shared__ float4 s_dyn[];            // fragment lists: K*NT float4 (pz, bits, sd, u), then K*NT float (v)
+  extern __shared__ float4 s_dyn[];            // fragment lists: K*NT float4 (pz, bits, sd, u), K*NT float (v); then the map table
   uint32_t bar_phase = 0;
 
   constexpr int TILE_H = NT / 16;
@@ -445,20 +464,26 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   if (tid < TILE_W) s_ndc[tid] = pix_to_ndc(P.W - 1 - min(tx0 + tid, P.W - 1), P.W, P.H);
   else if (tid < TILE_W + TILE_H) s_ndc[tid] = pix_to_ndc(P.H - 1 - min(ty0 + tid - TILE_W, P.H - 1), P.H, P.W);
   if (tid == 0) { s_count = 0; mbar_init(&s_bar, 1); }
+  // the map table goes to shared memory too: this thread's entry is loaded now and stored just before the barrier that follows
+  // the bin scan, so that nobody waits for it
+  int4* const s_desc = reinterpret_cast<int4*>(reinterpret_cast<float*>(s_dyn + (size_t)P.K * NT) + (size_t)P.K * NT);
+  DbwMapDesc my_desc = {0, 0, 0, 0};
+  if (tid < P.M) my_desc = P.map_table[tid];
+  const int4 vbox = __ldg(reinterpret_cast<const int4*>(P.view_bbox) + view);      // in flight across the barrier
+  const int vflags = __ldg(P.view_flags + view);
   __syncthreads();
   const f2 p = {s_ndc[xi - tx0], s_ndc[TILE_W + yi - ty0]};
   const int tx1 = min(tx0 + TILE_W, P.W) - 1, ty1 = min(ty0 + TILE_H, P.H) - 1;
   const float t_xmin = s_ndc[tx1 - tx0], t_xmax = s_ndc[0], t_ymin = s_ndc[TILE_W + ty1 - ty0], t_ymax = s_ndc[TILE_W];
   // tiles outside the union of the view's face boxes have nothing to rasterize: no scan
-  const int* vb = P.view_bbox + view * 4;
-  const bool tile_empty = ord2f(vb[0]) > t_xmax || ord2f(vb[1]) < t_xmin || ord2f(vb[2]) > t_ymax || ord2f(vb[3]) < t_ymin;
+  const bool tile_empty = ord2f(vbox.x) > t_xmax || ord2f(vbox.y) < t_xmin || ord2f(vbox.z) > t_ymax || ord2f(vbox.w) < t_ymin;
 
   const int K = P.K;
   float4* const lA = s_dyn + tid;                                            // this thread's list column
   float* const lV = reinterpret_cast<float*>(s_dyn + (size_t)K * NT) + tid;
   int n = 0;
 
-  const int nslots = tile_empty ? 0 : ((P.view_flags[view] & 1) ? 2 * P.F : P.F);
+  const int nslots = tile_empty ? 0 : ((vflags & 1) ? 2 * P.F : P.F);
   const size_t slot_base = (size_t)view * 2 * P.F;
   const float4* bbox = P.bbox + slot_base;
   const float4* rec = P.rec + slot_base * 4;
@@ -499,11 +524,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
           bu.y = b.bc.x * cv[1] + b.bc.y * cv[4] + b.bc.z * cv[7];
           bu.z = b.bc.x * cv[2] + b.bc.y * cv[5] + b.bc.z * cv[8];
         }
-        const float4 q0 = __ldg(&P.rec2[gs * 2]);
-        const float2 q1 = __ldg(reinterpret_cast<const float2*>(&P.rec2[gs * 2 + 1]));
+        const float4 q0 = __ldg(&P.rec2[gs * 2]), q1 = __ldg(&P.rec2[gs * 2 + 1]);
         const float u = bu.x * q0.x + bu.y * q0.z + bu.z * q1.x;
         const float v = bu.x * q0.y + bu.y * q0.w + bu.z * q1.y;
-        n = fraglist_offer(lA, lV, NT, n, K, b.pz, slot, edge, b.inside ? -dist : dist, dist, t.neighbor, u, v);
+        n = fraglist_offer(lA, lV, NT, n, K, b.pz, slot, edge, b.inside ? -dist : dist, dist, t.neighbor, u, v, __float_as_int(q1.z));
       }
     }
     // no barrier here: on the fast path nothing rewrites the list, and warps that finish early start shading (and hide
@@ -523,16 +547,34 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
     const float2 r1 = __ldg(reinterpret_cast<const float2*>(&rec[(size_t)s * 4 + 1]));
     return tri_overlaps_rect({r0.x, r0.y}, {r0.z, r0.w}, {r1.x, r1.y}, rx0, rx1, ry0, ry1);
   };
-  for (int base = 0; base < nslots; base += NT) {
-    float4 bb = make_float4(0, 0, 0, 0);
-    const bool hit = scan_hit(base + tid, bb);
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    int wbase = 0;
-    if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-    if (hit && pos < CAP) { s_slot[pos] = base + tid; s_bbox[pos] = bb; }
+  // four batches per trip, their box loads issued together: the scan is a chain of L2 latencies otherwise
+  for (int base = 0; base < nslots; base += 4 * NT) {
+    float4 bb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sl = base + q * NT + tid;
+      bb[q] = sl < nslots ? __ldg(&bbox[sl]) : make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int sl = base + q * NT + tid;
+      bool hit = !(bb[q].x > t_xmax || bb[q].y < t_xmin || bb[q].z > t_ymax || bb[q].w < t_ymin);
+      if (hit) {
+        const float4 r0 = __ldg(&rec[(size_t)sl * 4]);
+        const float2 r1 = __ldg(reinterpret_cast<const float2*>(&rec[(size_t)sl * 4 + 1]));
+        hit = tri_overlaps_rect({r0.x, r0.y}, {r0.z, r0.w}, {r1.x, r1.y}, rx0, rx1, ry0, ry1);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m == 0u) continue;
+      int wbase = 0;
+      if (lane == 0) wbase = atomicAdd(&s_count, __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      const int pos = wbase + __popc(m & ((1u << lane) - 1u));
+      if (hit && pos < CAP) { s_slot[pos] = sl; s_bbox[pos] = bb[q]; }
+    }
   }
+  if (tid < P.M) s_desc[tid] = make_int4(my_desc.offset / 3, my_desc.height, my_desc.width, 0);
+  for (int m = tid + NT; m < P.M; m += NT) { const DbwMapDesc d = P.map_table[m]; s_desc[m] = make_int4(d.offset / 3, d.height, d.width, 0); }
   __syncthreads();
   const int total = s_count;
   if (total <= CAP) {
@@ -542,9 +584,10 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
     __syncthreads();
     if (tid == 0) s_count = 0;
     __syncthreads();
-    for (int base = 0; base < nslots; base += NT) {
+    constexpr int BS = NT < CAP ? NT : CAP;          // slots scanned per batch: a batch never overflows an empty list
+    for (int base = 0; base < nslots; base += BS) {
       float4 bb = make_float4(0, 0, 0, 0);
-      const bool hit = scan_hit(base + tid, bb);
+      const bool hit = tid < BS && scan_hit(base + tid, bb);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       int wbase = 0;
       if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
@@ -555,8 +598,8 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
       }
       __syncthreads();
       const int cnt = s_count;
-      const bool last = base + NT >= nslots;
-      if (cnt > CAP - NT || last) {
+      const bool last = base + BS >= nslots;
+      if (cnt > CAP - BS || last) {
         raster_list(cnt);
         __syncthreads();              // every warp is done with the list before it is reset and refilled
         if (tid == 0) s_count = 0;
@@ -572,6 +615,14 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = (size_t)yi * P.W + xi;
   int n_saved = 0;
+  float ep_e[3] = {0.f, 0.f, 0.f}, ep_t[3] = {0.f, 0.f, 0.f};
+  if (EP) {                     // the epilogue's environment / target pixels: in flight while the fragments are shaded
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ep_e[c] = __ldg(P.ep_env + (size_t)view * 4 * plane + (size_t)c * plane + pix);
+      ep_t[c] = __ldg(P.ep_target + (size_t)view * 3 * plane + (size_t)c * plane + pix);
+    }
+  }
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
     const float4 e = lA[k * NT];
@@ -581,18 +632,20 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
     if (P.out_dists) P.out_dists[((size_t)view * K + k) * plane + pix] = d0;
     if (occ == 0.f) continue;     // behind a fully opaque fragment (fine phase: alpha = 1 inside a face): contributes exactly 0
     const float v = lV[k * NT];
-    if (P.frag) {                 // what the backward streams instead of re-deriving geometry: one 16 B record per fragment
-      P.frag[((size_t)view * K + k) * plane + pix] = make_float4(e.y, e.w, v, d0);
-      n_saved = k + 1;
-    }
     const int face = slot >= P.F ? slot - P.F : slot;
     Texel4 tx;
-    fetch_color(P, e.w, v, __ldg(&P.rec2[(slot_base + slot) * 2 + 1]), tx);
+    fetch_color(P, e.w, v, s_desc[(unsigned)bits >> DBW_FRAG_MAP_SHIFT], tx);
     float a = frag_alpha(d0, P.sigma, P.clip_inside);
     if (P.faces_alpha) a *= __ldg(&P.faces_alpha[alpha_index(P, view, face)]);
     if (P.face_shade) {          // flat shading: colour = texel * (ambient + diffuse * relu(n . l)) per (view, face)
       const float* m = P.face_shade + ((size_t)view * P.F + face) * 3;
       tx.color.x *= __ldg(m); tx.color.y *= __ldg(m + 1); tx.color.z *= __ldg(m + 2);
+    }
+    if (P.frag) {                 // what the backward streams instead of re-deriving geometry and texels: two 16 B records
+      const size_t fi = ((size_t)view * K + k) * plane + pix;
+      P.frag[fi] = make_float4(e.y, e.w, v, d0);
+      P.frag_rgb[fi] = make_float4(tx.color.x, tx.color.y, tx.color.z, 0.f);
+      n_saved = k + 1;
     }
     const float w = occ * a;
     r += w * tx.color.x; g += w * tx.color.y; bl += w * tx.color.z;
@@ -611,12 +664,6 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   } else {
     // fused epilogue (same arithmetic as composite_mse_kernel): composite over the environment render, squared error
     // against the target, and the gradients of the MSE w.r.t. both layers -- out_rgba receives d loss / d (this render)
-    float ep_e[3], ep_t[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      ep_e[c] = __ldg(P.ep_env + (size_t)view * 4 * plane + (size_t)c * plane + pix);
-      ep_t[c] = __ldg(P.ep_target + (size_t)view * 3 * plane + (size_t)c * plane + pix);
-    }
     float* ge = P.ep_g_env + (size_t)view * 4 * plane + pix;
     float gm = 0.f;
 #pragma unroll
@@ -680,8 +727,45 @@ __device__ __forceinline__ float warp_sum_spread(float (&x)[NP], int lane) {
 template <int N> struct Pow2Ceil { static constexpr int v = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
 template <int NP> struct SpreadShift { static constexpr int v = NP == 1 ? 5 : NP == 2 ? 4 : NP == 4 ? 3 : NP == 8 ? 2 : NP == 16 ? 1 : 0; };
 
+// Group sums through the integer reduction unit (REDUX, sm_80+): the members of a group (`grp`, all executing this) scale
+// their N values by a common power of two derived from the group's largest magnitude, round to int32 (|x| < 2^25, so 32
+// addends cannot overflow), add them with one REDUX.SUM per value and scale back.  Quantisation: 2^-25 of the group's largest
+// magnitude per addend -- the size of fp32 summation rounding -- and the sum itself is exact and order-independent.
+// One instruction per value instead of a shuffle butterfly.  Returns the sums to every member.
+template <int N>
+__device__ __forceinline__ void group_sum_redux(unsigned grp, const float (&v)[N], float (&out)[N]) {
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) mx = fmaxf(mx, fabsf(v[i]));
+  const unsigned gmax = __reduce_max_sync(grp, __float_as_uint(mx));        // non-negative floats order like their bit patterns
+  int ex = (int)(gmax >> 23) - 127;
+  ex = ex < -100 ? -100 : ex;
+  const float scale = __int_as_float((127 + 24 - ex) << 23), inv = __int_as_float((127 - 24 + ex) << 23);
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = (float)__reduce_add_sync(grp, __float2int_rn(v[i] * scale)) * inv;
+}
+
 template <int N>
 __device__ __forceinline__ void warp_agg_add(float* __restrict__ dst, int stride, int key, const float (&v)[N], int lane) {
+#ifdef DBW_AGG_REDUX
+  unsigned todo_r = __ballot_sync(0xffffffffu, key >= 0);
+  while (todo_r) {
+    const int leader = __ffs(todo_r) - 1;
+    const int lk = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = (key == lk);
+    const unsigned grp = __ballot_sync(0xffffffffu, mine);
+    if (mine) {
+      float r[N];
+      group_sum_redux<N>(grp, v, r);
+      if (lane == leader) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (r[i] != 0.f) atomicAdd(dst + (size_t)lk * stride + i, r[i]);
+      }
+    }
+    todo_r &= ~grp;
+  }
+  return;
+#endif
   constexpr int NP = Pow2Ceil<N>::v, SH = SpreadShift<NP>::v;
   unsigned todo = __ballot_sync(0xffffffffu, key >= 0);
   while (todo) {
@@ -772,6 +856,20 @@ __device__ __forceinline__ void warp_agg_add_edge(float* __restrict__ g_tri, int
     // vertex pair of the edge: 0 = (v0, v1), 1 = (v0, v2), 2 = (v1, v2); vertex j's (x, y) live at floats 3j, 3j+1
     const int ia = edge == 2 ? 3 : 0, ib = edge == 0 ? 3 : 6;
     float* d = g_tri + (size_t)(lk >> 2) * 9;
+#ifdef DBW_AGG_REDUX
+    if (mine) {
+      float r[4];
+      group_sum_redux<4>(grp, v, r);
+      if (lane == leader) {
+        if (r[0] != 0.f) atomicAdd(d + ia, r[0]);
+        if (r[1] != 0.f) atomicAdd(d + ia + 1, r[1]);
+        if (r[2] != 0.f) atomicAdd(d + ib, r[2]);
+        if (r[3] != 0.f) atomicAdd(d + ib + 1, r[3]);
+      }
+    }
+    todo &= ~grp;
+    continue;
+#endif
     if (__popc(grp) <= DBW_AGG_MIN) {
       if (mine) {
         if (v[0] != 0.f) atomicAdd(d + ia, v[0]);
@@ -797,9 +895,12 @@ __device__ __forceinline__ void warp_agg_add_edge(float* __restrict__ g_tri, int
 // constants); pass 2 walks back to front with the division-free suffix recurrence of SURVEY Appendix B for d/d(alpha_k)
 // -> opacity and distance -> vertex gradients.  Loops are warp-uniform (trip count = warp max) so that the aggregation
 // helpers run converged.
-template <bool DETACH, bool ALPHA>
+#define DBW_ALPHA_SMEM_MAX 512      // opacity entries per view that a CTA may pre-accumulate in shared memory
+
+// K1: faces_per_pixel == 1 (the environment pass): no record prefetch registers, at most one trip through the loops
+template <bool DETACH, bool ALPHA, bool K1>
 __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW_BWD_BARY_MINB) raster_backward_kernel(const RasterParams P) {
-  extern __shared__ float4 s_dyn[];             // [k][tid] (alpha, cdot, e, occ), then [k][tid] record bits
+  extern __shared__ float4 s_dyn[];             // [k][tid] (alpha, cdot, e, occ), [k][tid] record bits, the map table, opacity sums
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.z;
   const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
@@ -808,32 +909,52 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
   if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
   if ((int)(blockIdx.y * (DBW_BWD_NT / 16)) >= row_hi || (int)((blockIdx.y + 1) * (DBW_BWD_NT / 16)) <= row_lo) return;
   const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
-  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = live ? (size_t)yi * P.W + xi : 0;
-  const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
-  float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
-  if (live) { gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane]; }
-  if (P.grad_scale) { const float gs = __ldg(P.grad_scale); gr *= gs; gg *= gs; gb *= gs; ga *= gs; }
   float4* const s_q = s_dyn + tid;
   int* const s_bits = reinterpret_cast<int*>(s_dyn + (size_t)P.K * DBW_BWD_NT) + tid;
+  int4* const s_desc = reinterpret_cast<int4*>(reinterpret_cast<int*>(s_dyn + (size_t)P.K * DBW_BWD_NT) + (size_t)P.K * DBW_BWD_NT);
+  float* const s_galpha = reinterpret_cast<float*>(s_desc + P.M);
+  const float4* frag = P.frag + (size_t)view * P.K * plane + pix;
+  const float4* frag_rgb = P.frag_rgb + (size_t)view * P.K * plane + pix;
+  // ---- every first-level load of the pixel is issued before anything waits: gradient, fragment count, the first two records
+  // (speculatively: their addresses are valid workspace whether or not a fragment exists), this thread's map-table entry
+  const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
+  float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
+  int n_px = 0;
+  float4 rec_cur = make_float4(0.f, 0.f, 0.f, 0.f), rgb_cur = rec_cur, rec_nxt = rec_cur, rgb_nxt = rec_cur;
+  if (live) {
+    gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane];
+    n_px = (int)P.nfrag[(size_t)view * plane + pix];
+    rec_cur = frag[0]; rgb_cur = frag_rgb[0];
+    if (!K1 && P.K > 1) { rec_nxt = frag[plane]; rgb_nxt = frag_rgb[plane]; }
+  }
+  const float gs = P.grad_scale ? __ldg(P.grad_scale) : 1.f;
+  stage_map_table(P, s_desc, tid, DBW_BWD_NT);
+  const bool want_alpha = ALPHA && P.g_faces_alpha != nullptr;
+  const bool alpha_in_smem = want_alpha && P.n_alpha <= DBW_ALPHA_SMEM_MAX;       // few opacity entries: hot addresses
+  if (alpha_in_smem) for (int i = tid; i < P.n_alpha; i += DBW_BWD_NT) s_galpha[i] = 0.f;
+  __syncthreads();
+  gr *= gs; gg *= gs; gb *= gs; ga *= gs;
+  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
   const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
   const size_t slot_base = (size_t)view * 2 * P.F;
-  const float4* frag = P.frag + (size_t)view * P.K * plane + pix;
+  if (!any_grad) n_px = 0;
 
-  // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count); the record of
-  // layer k+1 is prefetched while layer k is processed
-  int n_px = any_grad ? (int)P.nfrag[(size_t)view * plane + pix] : 0;
+  // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count); the records of
+  // layers k+1 and k+2 are in flight while layer k is processed
   int n_warp = n_px;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n_warp = max(n_warp, __shfl_xor_sync(0xffffffffu, n_warp, o));
   int n = 0;
   float occ = 1.f;
-  float4 rec_next = n_px > 0 ? frag[0] : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < n_warp; ++k) {
-    const float4 fr = rec_next;
+    const float4 fr = rec_cur, fc = rgb_cur;
+    if (!K1) {
+      rec_cur = rec_nxt; rgb_cur = rgb_nxt;
+      if (k + 2 < n_px) { rec_nxt = frag[(size_t)(k + 2) * plane]; rgb_nxt = frag_rgb[(size_t)(k + 2) * plane]; }
+    }
     const bool have = k < n_px && occ != 0.f;      // everything behind a fully opaque fragment has zero weight and zero gradient
-    if (k + 1 < n_px && occ != 0.f) rec_next = frag[(size_t)(k + 1) * plane];
     int key = -1, ckey = -1, tkey = -1, t01 = -1, t10 = -1, t11 = -1;
     float gv9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float gc9[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -846,11 +967,13 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
       Texel4 tx;
       Shade s;
       const bool bary_path = !DETACH && face >= P.n_static_faces;
-      if (bary_path) {
+      const int4 desc = s_desc[(unsigned)bits >> DBW_FRAG_MAP_SHIFT];
+      if (bary_path) {              // the gradient through (u, v) needs the four texels and the face's geometry again
         shade_geometry(P, view, slot, p, s);
-        fetch_color(P, s.u, s.v, s.q1, tx);
-      } else {
-        fetch_color(P, fr.y, fr.z, __ldg(&P.rec2[(slot_base + slot) * 2 + 1]), tx);
+        fetch_color(P, s.u, s.v, desc, tx);
+      } else {                      // texture / opacity / distance gradients: the saved colour and tap addresses suffice
+        tap_only(fr.y, fr.z, desc, tx);
+        tx.color = {fc.x, fc.y, fc.z};
       }
       const float e = frag_alpha(d, P.sigma, P.clip_inside);
       const float fa = ALPHA ? __ldg(&P.faces_alpha[alpha_index(P, view, face)]) : 1.f;
@@ -878,12 +1001,12 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
           const float giy = (d10 - d00) * ex + (d11 - d01) * wx;
           const float gu = gix * tx.tap.mx, gv = giy * tx.tap.my;
           f3 gbu = {gu * s.uv01.x + gv * s.uv01.y, gu * s.uv01.z + gv * s.uv01.w, gu * s.u2 + gv * s.v2};
-          const size_t gs = slot_base + slot;
+          const size_t gsl = slot_base + slot;
           f3 gbc = gbu;
           if (s.t.flags & 1) {
             // z-clipped face (the ground plane under the camera is one): bu = bc @ conv, so the conversion matrix gets
             // gradient too; it is accumulated per slot with the same warp aggregation as the vertex gradient below
-            const float* cv = P.conv + gs * 9;
+            const float* cv = P.conv + gsl * 9;
             gbc.x = cv[0] * gbu.x + cv[1] * gbu.y + cv[2] * gbu.z;
             gbc.y = cv[3] * gbu.x + cv[4] * gbu.y + cv[5] * gbu.z;
             gbc.z = cv[6] * gbu.x + cv[7] * gbu.y + cv[8] * gbu.z;
@@ -913,46 +1036,65 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
-  const bool want_alpha = ALPHA && P.g_faces_alpha != nullptr;
   const bool want_dist = P.sigma > 0.f && P.g_tri != nullptr;
-  if (!want_alpha && !want_dist) return;
-  for (int k = n_warp - 1; k >= 0; --k) {
-    int akey = -1, vkey = -1;
-    float aval = 0.f;
-    float gv4[4] = {0.f, 0.f, 0.f, 0.f};        // (x, y) of the two vertices of the closest edge
-    if (k < n) {
-      const float4 q = s_q[k * DBW_BWD_NT];      // (alpha, cdot, e, occ)
-      const float g_alpha = q.w * (q.y - Tacc);
-      Tacc = q.x * q.y + (1.f - q.x) * Tacc;
-      if (g_alpha != 0.f) {
-        const int bits = s_bits[k * DBW_BWD_NT], slot = bits & DBW_FRAG_SLOT_MASK;
-        const int face = slot >= P.F ? slot - P.F : slot;
-        if (want_alpha) { akey = alpha_index(P, view, face); aval = g_alpha * q.z; }
-        if (want_dist) {
-          // gradient w.r.t. the SIGNED squared distance: alpha = e(d) * fa, so fa * e = alpha
-          const bool inside = !(bits & DBW_FRAG_OUTSIDE_BIT);
-          float g_sd = 0.f;
-          if (P.clip_inside) { if (!inside) g_sd = g_alpha * (-q.x / P.sigma); }          // clamp(d, 0): flat inside the face
-          else g_sd = g_alpha * (-q.x * (1.f - q.z) / P.sigma);
-          const float g_dist = inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
-          if (g_dist != 0.f) {
-            const int edge = (bits >> DBW_FRAG_EDGE_SHIFT) & 3;
-            const size_t gs = slot_base + slot;
-            const float4 r0 = __ldg(&P.rec[gs * 4]), r3 = __ldg(&P.rec[gs * 4 + 3]);
-            const float2 r1 = __ldg(reinterpret_cast<const float2*>(&P.rec[gs * 4 + 1]));
-            const f2 v0 = {r0.x, r0.y}, v1 = {r0.z, r0.w}, v2 = {r1.x, r1.y};
-            const f2 ea = edge == 2 ? v1 : v0, eb = edge == 0 ? v1 : v2;
-            const float il = edge == 0 ? r3.y : (edge == 1 ? r3.z : r3.w);
-            f2 g_a = {0.f, 0.f}, g_b = {0.f, 0.f};
-            seg_backward(p, ea, eb, il, g_dist, g_a, g_b);
-            vkey = slot * 4 + edge;
-            gv4[0] = g_a.x; gv4[1] = g_a.y; gv4[2] = g_b.x; gv4[3] = g_b.y;
+  if (want_alpha || want_dist) {
+    // the edge geometry of a halo fragment (2 vertices + 1 / |edge|^2, from the face record) is loaded one layer ahead
+    struct EdgeGeom { float4 r0; float2 r1; float4 r3; };
+    auto load_edge = [&](int kk, EdgeGeom& g) {
+      g.r0 = make_float4(0.f, 0.f, 0.f, 0.f); g.r1 = make_float2(0.f, 0.f); g.r3 = g.r0;
+      if (!want_dist || kk < 0 || kk >= n) return;
+      const int bits = s_bits[kk * DBW_BWD_NT];
+      if (P.clip_inside && !(bits & DBW_FRAG_OUTSIDE_BIT)) return;          // clamp(d, 0): no distance gradient inside the face
+      const size_t gsl = slot_base + (bits & DBW_FRAG_SLOT_MASK);
+      g.r0 = __ldg(&P.rec[gsl * 4]); g.r3 = __ldg(&P.rec[gsl * 4 + 3]);
+      g.r1 = __ldg(reinterpret_cast<const float2*>(&P.rec[gsl * 4 + 1]));
+    };
+    EdgeGeom eg_next;
+    load_edge(n_warp - 1, eg_next);
+    for (int k = n_warp - 1; k >= 0; --k) {
+      const EdgeGeom eg = eg_next;
+      load_edge(k - 1, eg_next);
+      int akey = -1, vkey = -1;
+      float aval = 0.f;
+      float gv4[4] = {0.f, 0.f, 0.f, 0.f};        // (x, y) of the two vertices of the closest edge
+      if (k < n) {
+        const float4 q = s_q[k * DBW_BWD_NT];      // (alpha, cdot, e, occ)
+        const float g_alpha = q.w * (q.y - Tacc);
+        Tacc = q.x * q.y + (1.f - q.x) * Tacc;
+        if (g_alpha != 0.f) {
+          const int bits = s_bits[k * DBW_BWD_NT], slot = bits & DBW_FRAG_SLOT_MASK;
+          const int face = slot >= P.F ? slot - P.F : slot;
+          if (want_alpha) { akey = alpha_index(P, alpha_in_smem ? 0 : view, face); aval = g_alpha * q.z; }
+          if (want_dist) {
+            // gradient w.r.t. the SIGNED squared distance: alpha = e(d) * fa, so fa * e = alpha
+            const bool inside = !(bits & DBW_FRAG_OUTSIDE_BIT);
+            float g_sd = 0.f;
+            if (P.clip_inside) { if (!inside) g_sd = g_alpha * (-q.x / P.sigma); }          // clamp(d, 0): flat inside the face
+            else g_sd = g_alpha * (-q.x * (1.f - q.z) / P.sigma);
+            const float g_dist = inside ? -g_sd : g_sd;    // signed = inside ? -dist : dist
+            if (g_dist != 0.f) {
+              const int edge = (bits >> DBW_FRAG_EDGE_SHIFT) & 3;
+              const f2 v0 = {eg.r0.x, eg.r0.y}, v1 = {eg.r0.z, eg.r0.w}, v2 = {eg.r1.x, eg.r1.y};
+              const f2 ea = edge == 2 ? v1 : v0, eb = edge == 0 ? v1 : v2;
+              const float il = edge == 0 ? eg.r3.y : (edge == 1 ? eg.r3.z : eg.r3.w);
+              f2 g_a = {0.f, 0.f}, g_b = {0.f, 0.f};
+              seg_backward(p, ea, eb, il, g_dist, g_a, g_b);
+              vkey = slot * 4 + edge;
+              gv4[0] = g_a.x; gv4[1] = g_a.y; gv4[2] = g_b.x; gv4[3] = g_b.y;
+            }
           }
         }
       }
+      if (want_alpha && __ballot_sync(0xffffffffu, akey >= 0)) warp_agg_add1(alpha_in_smem ? s_galpha : P.g_faces_alpha, akey, aval, lane);
+      if (want_dist && __ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_edge(P.g_tri + slot_base * 9, vkey, gv4, lane);
     }
-    if (want_alpha && __ballot_sync(0xffffffffu, akey >= 0)) warp_agg_add1(P.g_faces_alpha, akey, aval, lane);
-    if (want_dist && __ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_edge(P.g_tri + slot_base * 9, vkey, gv4, lane);
+  }
+  if (alpha_in_smem) {               // one global atomic per (CTA, opacity entry) instead of one per (warp, layer, entry)
+    __syncthreads();
+    for (int i = tid; i < P.n_alpha; i += DBW_BWD_NT) {
+      const float v = s_galpha[i];
+      if (v != 0.f) atomicAdd(&P.g_faces_alpha[(size_t)view * P.alpha_stride + i], v);
+    }
   }
 }
 
@@ -1118,21 +1260,25 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   P.B = s.n_views; P.H = s.height; P.W = s.width; P.K = s.faces_per_pixel; P.V = s.n_verts; P.F = s.n_faces; P.M = s.n_maps;
   P.alpha_stride = s.alpha_view_stride; P.inv_alpha_group = 1.f / (float)(s.alpha_group > 0 ? s.alpha_group : 1);
   P.n_static_faces = s.n_static_faces; P.view_rows = s.view_rows;
+  P.n_alpha = s.n_faces / (s.alpha_group > 0 ? s.alpha_group : 1);
   P.sigma = s.sigma; P.blur = s.blur_radius; P.sqrt_blur = sqrtf(s.blur_radius); P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
   P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
   P.frag = s.save_fragment_state ? w.frag : nullptr; P.nfrag = s.save_fragment_state ? w.nfrag : nullptr;
+  P.frag_rgb = s.save_fragment_state ? w.frag_rgb : nullptr;
   return P;
 }
 
 // dynamic shared memory of the raster kernels: K list entries (forward) / K saved scalars (backward) of 20 B per thread
-static size_t frag_smem_bytes(int K, int NT) { return (size_t)K * NT * (sizeof(float4) + sizeof(float)); }
+static size_t frag_smem_bytes(int K, int NT, int M, int n_alpha = 0) {
+  return (size_t)K * NT * (sizeof(float4) + sizeof(float)) + (size_t)M * sizeof(int4) + (n_alpha <= 512 ? (size_t)n_alpha * sizeof(float) : 0);
+}
 
 template <int NT>
 static cudaError_t launch_forward(const RasterParams& P, cudaStream_t st) {
   const dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16), P.B);
-  const size_t smem = frag_smem_bytes(P.K, NT);
+  const size_t smem = frag_smem_bytes(P.K, NT, P.M);
   auto go = [&](auto kern) -> cudaError_t {
     if (smem > 40 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     kern<<<grid, NT, smem, st>>>(P);
@@ -1211,6 +1357,7 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
   }
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
+  P.map_table = map_table;
   P.out_rgba = out_rgba; P.topk = topk_ids; P.face_shade = face_shade; P.out_dists = out_dists;
   if (ep) {
     CK(cudaMemsetAsync(ep->loss_partials, 0, (size_t)ep->n_partials * sizeof(float), st));
@@ -1257,10 +1404,11 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
   CK(cudaMemsetAsync(bwd_scratch, 0, g.total, st));
   RasterParams P = make_params(*s, w, faces_alpha);
   if (s->maps_are_texels4) P.maps4 = (const float4*)maps;
+  P.map_table = map_table;
   P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = need_geom ? g.g_tri : nullptr; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
   dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16), B);
-  const size_t smem = frag_smem_bytes(s->faces_per_pixel, DBW_BWD_NT);
+  const size_t smem = frag_smem_bytes(s->faces_per_pixel, DBW_BWD_NT, s->n_maps, P.n_alpha);
   {
     auto launch = [&](auto kern) -> cudaError_t {
       if (smem > 40 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
@@ -1268,9 +1416,11 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
       kern<<<grid, DBW_BWD_NT, smem, st>>>(P);
       return cudaSuccess;
     };
-    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr;
-    cudaError_t e = det ? (al ? launch(raster_backward_kernel<true, true>) : launch(raster_backward_kernel<true, false>))
-                        : (al ? launch(raster_backward_kernel<false, true>) : launch(raster_backward_kernel<false, false>));
+    const bool det = s->detach_bary != 0, al = faces_alpha != nullptr, k1 = s->faces_per_pixel == 1;
+    cudaError_t e = k1  ? (det ? (al ? launch(raster_backward_kernel<true, true, true>) : launch(raster_backward_kernel<true, false, true>))
+                               : (al ? launch(raster_backward_kernel<false, true, true>) : launch(raster_backward_kernel<false, false, true>)))
+                  : det ? (al ? launch(raster_backward_kernel<true, true, false>) : launch(raster_backward_kernel<true, false, false>))
+                        : (al ? launch(raster_backward_kernel<false, true, false>) : launch(raster_backward_kernel<false, false, false>));
     if (e != cudaSuccess) return fail("raster_backward_kernel attribute", e);
   }
   LAUNCH_CK("raster_backward_kernel");

@@ -114,6 +114,8 @@ class DifferentiableBlocksWorld(nn.Module):
         self.fused_loss = True            # compositing + MSE in the rasterizer's epilogue (fused_loss.py) when nothing else reads rec
         self._passes = None
         self.overlap_passes = False       # environment pass on a side stream (measured: +1 %)
+        import os as _os
+        self.alpha_group_faces = int(_os.environ.get('DBW_ALPHA_GROUP', 0)) or None      # experiment switch: 1 = one opacity entry per face
         self.n_total_views = None         # data-parallel context (parallel.py): views of the whole step
         self.noise_generator = None       # RNG shared by all ranks for opacity noise / overlap samples
         self.opacity_noise_buffer = None  # pre-drawn randn (N,) used instead of drawing inside forward (graph.py)
@@ -365,6 +367,8 @@ class DifferentiableBlocksWorld(nn.Module):
         rows, cols = atlas.shape[1], atlas.shape[2]
         table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
         alpha = None if hard_filter else self._alpha          # one opacity per block: alpha_group = BNF faces share an entry
+        if alpha is not None and self.alpha_group_faces == 1:
+            alpha = alpha[:, None].expand(-1, self.BNF).reshape(-1)
         self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
         return (env_verts, env_atlas, env_table), (blk_verts, atlas.reshape(-1, 4), table, fmap, alpha)
 
@@ -382,7 +386,7 @@ class DifferentiableBlocksWorld(nn.Module):
             env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
                                     R, T, None, texels4=True, n_static_faces=self.bkg_n_faces)
         fg_rgba = self._raster(renderer, blk_verts, st['faces_b'], st['fvu_b'], fmap, atlas, table, R, T, alpha, texels4=True,
-                               alpha_group=self.BNF)
+                               alpha_group=self.alpha_group_faces or self.BNF)
         if stream is not main:
             main.wait_stream(stream)
             env_rgba.record_stream(main)
@@ -404,7 +408,7 @@ class DifferentiableBlocksWorld(nn.Module):
         if self._passes is None or self._passes[0] != key:
             self._passes = (key, ScenePass(st['faces_e'], st['fvu_e'], st['fmap_e'], env_table, self.renderer_env,
                                            n_static_faces=self.bkg_n_faces),
-                            ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer, alpha_group=self.BNF))
+                            ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer, alpha_group=self.alpha_group_faces or self.BNF))
         return scene_mse(env_verts, env_atlas, blk_verts, atlas, alpha, inp['R'], inp['T'], inp['imgs'], self._passes[1],
                          self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']), view_rows=inp.get('rows'))
 

@@ -348,6 +348,68 @@ def predict(tpl, p, R, T, K, image_size, sigma=1e-4, faces_per_pixel=10, z_clip=
     return rec_fg * mask + (1 - mask) * rec_env
 
 
+def predict_joint(tpl, p, R, T, K, image_size, sigma=1e-4, faces_per_pixel=10, z_clip=0.001, fine=False, keep=None,
+                  decimate=0, alpha_noise=None):
+    """DifferentiableBlocksWorld.predict, decouple_rendering=False branch (dbw.py:225-232): background + ground + blocks as ONE
+    scene through the (detach_bary) block renderer, environment faces at opacity 1."""
+    env = tpl.build_env(p, decimate=decimate)
+    blocks, alpha = tpl.build_blocks(p, keep=keep, decimate=decimate, alpha_noise=alpha_noise)
+    scene = env if blocks is None else join_scenes([env, blocks])
+    faces_alpha = None
+    if not fine:
+        n_env = env['faces'].shape[0]
+        parts = [torch.ones(n_env, dtype=alpha.dtype)] + ([alpha.repeat_interleave(tpl.BNF)] if blocks is not None else [])
+        faces_alpha = torch.cat(parts).repeat(R.shape[0])
+    return render(scene, R, T, K, image_size, sigma=sigma, faces_per_pixel=faces_per_pixel, z_clip=z_clip, detach_bary=True,
+                  faces_alpha=faces_alpha)[:, :3]
+
+
+def safe_pow(t, exponent, eps=1e-6):
+    """src/utils/pytorch.py:35-36"""
+    return t.clamp(eps).pow(exponent)
+
+
+def implicit_sq(points, eps1, eps2):
+    """src/utils/superquadric.py:17-38 with safe=True, as_sdf=2 (the variant dbw.py:400 calls)"""
+    points = points.clamp(-5, 5)
+    x2, y2, z2 = [points[..., k].pow(2) for k in range(3)]
+    x, y, z = safe_pow(x2, 1 / eps2), safe_pow(y2, 1 / eps1), safe_pow(z2, 1 / eps2)
+    res = safe_pow(x + z, eps2 / eps1) + y
+    return safe_pow(res, eps1 / 2) - 1
+
+
+def regularisers(tpl, p, coarse=True, keep=None, tv_type='l2sq', unit_samples=None, weights=(1.0, 1.0, 1.0)):
+    """the parameter-only terms of compute_losses (dbw.py:373-405): parsimony, total variation, overlap -> dict.
+    keep: the kill_blocks / filter mask folded into _alpha_full (dbw.py:316-328); unit_samples: the U(0,1) draws of
+    dbw.py:393 (N,1000,3), passed in so that both sides of a comparison use the same points."""
+    tv_norm = {'l1': lambda t: t.abs().sum(-1), 'l2': lambda t: safe_pow(t.pow(2).sum(-1), 0.5), 'l2sq': lambda t: t.pow(2).sum(-1)}[tv_type]
+    alpha_full = torch.sigmoid(p['alpha_logit'])
+    if keep is not None:
+        alpha_full = alpha_full * keep
+    out = {}
+    a = alpha_full if coarse else (alpha_full > 0.5).to(alpha_full)
+    out['parsimony'] = weights[0] * (1 if coarse else 0) * safe_pow(a, 0.5).mean()
+    factor = 1 if coarse else 0.1
+    bkg, ground, blocks = torch.sigmoid(p['texture_bkg']), torch.sigmoid(p['texture_ground']), torch.sigmoid(p['textures'])
+    tv = sum(tv_norm(torch.diff(bkg, dim=k)).mean() for k in (1, 2))
+    dx = tv_norm(torch.diff(blocks, dim=2, append=blocks[:, :, 0:1]))
+    dy = tv_norm(torch.diff(blocks, dim=1))
+    tv = tv + dx.sum(0).mean() + dy.sum(0).mean()
+    tv = tv + sum(tv_norm(torch.diff(ground, dim=k)).mean() for k in (1, 2)) * factor
+    out['tv'] = weights[1] * factor * tv
+    N = tpl.n_blocks
+    S, Rm, T = p['S'].exp() + tpl.scale_min, pt3d.rotation_6d_to_matrix(p['R_6d']), p['T']
+    eps1, eps2 = (torch.sigmoid(p['sq_eps']) * 1.8 + 0.1).split([1, 1], dim=-1)
+    with torch.no_grad():
+        pts = unit_samples.to(S) * 2 - 1
+        pts = (pts * tpl.ratio * S[:, None]) @ Rm + T[:, None]
+        pts = pts.reshape(-1, 3)[None].expand(N, -1, -1)
+    inv = ((pts - T[:, None]) @ Rm.transpose(1, 2)) / (S[:, None] * tpl.ratio)
+    occ = torch.sigmoid(-implicit_sq(inv, eps1, eps2) / 0.005) * a[:, None]
+    out['overlap'] = weights[2] * (1 if coarse else 0) * (occ.sum(0) - 1.95).clamp(0).mean()
+    return out
+
+
 def mse_loss(imgs, rec):
     return ((imgs - rec) ** 2).mean()
 

@@ -28,3 +28,18 @@ def extract(relpath, names, extra_ns=None):
             code = compile(ast.Module(body=[node], type_ignores=[]), relpath, 'exec')
             exec(code, ns)
     return ns
+
+
+def extract_method(relpath, cls_name, method, extra_ns=None):
+    """one method of a class of the reference as a plain function (its `self` is whatever the caller passes)"""
+    src = open(os.path.join(REF, relpath)).read()
+    ns = {'torch': torch, 'np': np, 'F': torch.nn.functional}
+    ns.update(extra_ns or {})
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls_name:
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == method:
+                    sub.decorator_list = []
+                    exec(compile(ast.Module(body=[sub], type_ignores=[]), relpath, 'exec'), ns)
+                    return ns[method]
+    raise KeyError(f'{cls_name}.{method} not found in {relpath}')

@@ -153,17 +153,33 @@ def _leaf_gradient_parity(model, tpl, size, R, T, K, Kf, sigma, fine, max_masked
     assert abs(losses['rgb'].item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
     losses['total'].backward()
     loss_ref.backward()
-    worst = {}
+    # Tolerance model (fp64 run = truth, fp32 run of the SAME reference arithmetic = what fp32 can deliver): the
+    # ground plane passes under the camera, its z-clipped faces have vertices at z = z_clip whose NDC coordinates are ~1e3-1e4,
+    # and the edge functions (p - a) x (b - a) of such faces cancel ~4 digits in fp32 -- in PyTorch3D's fp32 kernels as well.
+    # Their barycentric gradients (the only path to R_6d_ground / T_ground) therefore carry ~1e-3 relative noise in ANY fp32
+    # evaluation; a leaf may deviate from fp64 by max(1e-3, 2 x the fp32 oracle's own deviation).
+    p32 = {k: v.detach().float().clone().requires_grad_(True) for k, v in p.items()}
+    rec32 = D.predict(tpl, p32, R.float(), T.float(), K.float(), size, sigma=sigma, faces_per_pixel=Kf, z_clip=0.001, fine=fine,
+                      keep=keep, decimate=0 if fine else 8, alpha_noise=None if noise is None else noise.float())
+    bad32 = bad | ((rec32.detach().double() - rec_ref.detach()).abs() > 1e-4).any(1, keepdim=True)
+    D.mse_loss(torch.where(bad32, rec32.detach(), imgs.float()), rec32).backward()
+    p64b = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    rec64b = D.predict(tpl, p64b, R, T, K, size, sigma=sigma, faces_per_pixel=Kf, z_clip=0.001, fine=fine, keep=keep,
+                       decimate=0 if fine else 8, alpha_noise=noise)
+    D.mse_loss(torch.where(bad32, rec64b.detach(), imgs), rec64b).backward()
+    worst, model32 = {}, {}
     for name, prm in model.named_parameters():
         g_ref = p[name].grad
         if g_ref is None or g_ref.abs().max() == 0:
             assert prm.grad is None or prm.grad.abs().max().item() < 1e-12, name
             continue
         worst[name] = _rel(prm.grad.cpu().double(), g_ref)
-    print(f'leaf gradients ({size[0]}x{size[1]}, {"fine" if fine else "coarse"}): masked pixels {masked * 100:.4f}%; rel err '
+        model32[name] = _rel(p32[name].grad.double(), p64b[name].grad)
+    print(f'leaf gradients ({size[0]}x{size[1]}, {"fine" if fine else "coarse"}): masked pixels {masked * 100:.4f}%; rel err CUDA vs fp64 '
           + ', '.join(f'{k} {v:.1e}' for k, v in worst.items()))
+    print('                fp32 ORACLE vs fp64 oracle: ' + ', '.join(f'{k} {v:.1e}' for k, v in model32.items()))
     for name, rel in worst.items():
-        assert rel < GRAD_REL, f'{name}: rel grad err {rel:.3e}'
+        assert rel < max(GRAD_REL, 2 * model32[name]), f'{name}: rel grad err {rel:.3e} (fp32 oracle: {model32[name]:.3e})'
 
 
 @pytest.mark.parametrize('fine', [False, True])

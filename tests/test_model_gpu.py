@@ -64,13 +64,18 @@ def test_predict_and_rgb_gradients(fine):
     sigma = 5e-6 if fine else 1e-4
     rec_ref = D.predict(tpl, p, R, T, K, (48, 64), sigma=sigma, faces_per_pixel=10, z_clip=0.001, fine=fine, keep=keep,
                         decimate=decim)
-    rec = model.predict(inp)
-    err = (rec.detach().cpu().double() - rec_ref.detach()).abs()
+    rec = model.predict(inp).detach().cpu().double()
+    err = (rec - rec_ref.detach()).abs()
     assert (err > 1e-4).float().mean().item() < 1e-3, f'max err {err.max().item():.3e}'
-    # loss + gradients: only the rgb term (the regularisers are plain torch on parameters)
+    # loss + gradients: only the rgb term (the regularisers have their own test).  The few pixels where fp32 takes a different
+    # discrete decision than the fp64 oracle (colour off by > 1e-4) get a target equal to each side's own reconstruction:
+    # zero residual, zero gradient on BOTH sides -- everything else must agree to the north star's 1e-3
+    bad = (err > 1e-4).any(1, keepdim=True)
+    print(f'decision-masked pixels: {bad.double().mean().item() * 100:.4f}%')
+    inp['imgs'] = torch.where(bad, rec, imgs).float().to(dev)
     model.loss_weights = {'rgb': 1.0}
     losses = model(inp, None)
-    loss_ref = D.mse_loss(imgs, rec_ref)
+    loss_ref = D.mse_loss(torch.where(bad, rec_ref.detach(), imgs), rec_ref)
     assert abs(losses['rgb'].item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
     losses['total'].backward()
     loss_ref.backward()
@@ -81,8 +86,7 @@ def test_predict_and_rgb_gradients(fine):
             assert g is None or g.abs().max().item() < 1e-12, name
             continue
         rel = ((g.cpu().double() - g_ref).norm() / g_ref.norm()).item()
-        # a few pixels take a different discrete decision in fp32 than in the fp64 oracle (see test_render_parity)
-        assert rel < 2e-2, f'{name}: rel grad err {rel:.3e}'
+        assert rel < 1e-3, f'{name}: rel grad err {rel:.3e}'
 
 
 def test_full_loss_dict_runs_and_is_finite():
@@ -332,3 +336,198 @@ def test_optimisation_descends_with_the_reference_optimizer_layout():
         hist.append(loss['rgb'].item())
     assert all(torch.isfinite(p).all() for p in model.parameters())
     assert hist[-1] < 0.85 * hist[0] and min(hist[-10:]) < min(hist[:10]), (hist[0], hist[-1])   # measured: 1.01e-3 -> 7.4e-4
+
+
+# ------------------------------------------------------------------------------------------------ branches round 1 left untested
+def test_joint_render_mode_matches_oracle():
+    """decouple_rendering=False (dbw.py:225-232): background + ground + blocks rendered as ONE scene by the block renderer,
+    environment faces at opacity 1 -- predict() and the RGB-loss gradients against the oracle's restatement"""
+    from copy import deepcopy
+    from dbw_b200.dbw import DifferentiableBlocksWorld
+    cfg = deepcopy(CFG)
+    cfg['rend_optim'].update(decouple_rendering=False, kill_blocks=False)
+    cfg['loss'] = {'rgb_weight': 1}
+    torch.manual_seed(5)
+    dev = torch.device('cuda:0')
+    model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
+    model.train()
+    tpl = D.SceneTemplate(n_blocks=5, txt_size=32)
+    p = {k: v.detach().cpu().double().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    inp, imgs, R, T, K = _inputs(dev)
+    rec_ref = D.predict_joint(tpl, p, R, T, K, (48, 64), sigma=1e-4, faces_per_pixel=10, z_clip=0.001, decimate=8)
+    rec = model.predict(inp)
+    err = (rec.detach().cpu().double() - rec_ref.detach()).abs()
+    bad = (err > 1e-4).any(1, keepdim=True)
+    assert bad.double().mean().item() < 2e-3, f'max err {err.max().item():.3e}'
+    # gradients, with the (few) deviating pixels given zero residual on both sides
+    inp['imgs'] = torch.where(bad, rec.detach().cpu().double(), imgs).float().to(dev)
+    losses = model(inp, None)
+    loss_ref = D.mse_loss(torch.where(bad, rec_ref.detach(), imgs), rec_ref)
+    assert abs(losses['rgb'].item() - loss_ref.item()) < 1e-5 * max(1.0, abs(loss_ref.item()))
+    losses['total'].backward()
+    loss_ref.backward()
+    for name, prm in model.named_parameters():
+        g_ref = p[name].grad
+        if g_ref is None or g_ref.abs().max() == 0:
+            continue
+        rel = ((prm.grad.cpu().double() - g_ref).norm() / g_ref.norm()).item()
+        assert rel < 2e-3, f'{name}: rel grad err {rel:.3e}'
+
+
+def test_regularisers_match_oracle_restatement():
+    """parsimony / TV / overlap (dbw.py:373-405) of model(inp) against oracle.regularisers -- itself pinned to the reference's
+    compute_losses in tests/test_oracle_golden.py -- values and leaf gradients, with shared overlap sample points"""
+    for tv_type in ('l2sq', 'l2'):
+        from copy import deepcopy
+        from dbw_b200.dbw import DifferentiableBlocksWorld
+        cfg = deepcopy(CFG)
+        cfg['loss'] = {'rgb_weight': 1, 'parsimony_weight': 0.01, 'tv_weight': 0.1, 'overlap_weight': 1, 'tv_type': tv_type}
+        torch.manual_seed(5)
+        dev = torch.device('cuda:0')
+        model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
+        model.train()
+        with torch.no_grad():
+            model.T.mul_(0.05)
+            model.alpha_logit.copy_(torch.tensor([3.0, 2.5, 2.0, 1.0, -6.0]))
+        tpl = D.SceneTemplate(n_blocks=5, txt_size=32)
+        p = {k: v.detach().cpu().double().clone().requires_grad_(True) for k, v in model.named_parameters()}
+        inp, *_ = _inputs(dev)
+        u01 = torch.rand(5, 1000, 3, generator=torch.Generator().manual_seed(9))
+        model.overlap_samples_buffer = u01.to(dev)
+        losses = model(inp, None)
+        ref = D.regularisers(tpl, p, coarse=True, keep=torch.sigmoid(p['alpha_logit'].detach()) > 0.01, tv_type=tv_type,
+                             unit_samples=u01.double(), weights=(0.01, 0.1, 1.0))
+        assert ref['overlap'].item() > 0
+        for k in ('parsimony', 'tv', 'overlap'):
+            assert abs(losses[k].item() - ref[k].item()) <= 2e-5 * max(abs(ref[k].item()), 1e-3), (tv_type, k, losses[k].item(), ref[k].item())
+        (losses['parsimony'] + losses['tv'] + losses['overlap']).backward()
+        sum(ref.values()).backward()
+        for name, prm in model.named_parameters():
+            g_ref = p[name].grad
+            if g_ref is None or g_ref.abs().max() == 0:
+                continue
+            rel = ((prm.grad.cpu().double() - g_ref).norm() / g_ref.norm()).item()
+            assert rel < 1e-3, f'{tv_type} {name}: rel grad err {rel:.3e}'
+
+
+def test_perceptual_hand_off_reaches_the_leaves():
+    """a stand-in perceptual callable through model(inp): `rec` feeds it, its gradient on rec enters dbw_composite_mse_backward
+    (g_rec) next to the MSE's and reaches every leaf -- checked against the oracle with the same callable (dbw.py:369-371)"""
+    model, tpl, p, dev = _model_and_oracle()
+    inp, imgs, R, T, K = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0, 'perceptual': 0.1}
+    g = torch.Generator().manual_seed(3)
+    kern = torch.randn(4, 3, 5, 5, generator=g, dtype=torch.float64) * 0.2
+
+    def perceptual(a, b):                      # a small fixed conv "feature" distance: smooth, touches every pixel
+        k = kern.to(a)
+        return (torch.nn.functional.conv2d(a, k) - torch.nn.functional.conv2d(b, k)).pow(2).mean()
+
+    model.set_perceptual_loss(perceptual)
+    assert not model._fused_loss_ok(inp['imgs'])                 # another consumer of rec: the separate composite kernel is used
+    keep = torch.sigmoid(p['alpha_logit'].detach()) > 0.01
+    rec_ref = D.predict(tpl, p, R, T, K, (48, 64), sigma=1e-4, faces_per_pixel=10, z_clip=0.001, keep=keep, decimate=8)
+    rec = model.predict(inp).detach().cpu().double()
+    bad = ((rec - rec_ref.detach()).abs() > 1e-4).any(1, keepdim=True)
+    assert bad.double().mean().item() < 2e-3
+    inp['imgs'] = torch.where(bad, rec, imgs).float().to(dev)
+    imgs_ref = torch.where(bad, rec_ref.detach(), imgs)
+    losses = model(inp, None)
+    ref_p = 0.1 * perceptual(imgs_ref, rec_ref)
+    ref_total = D.mse_loss(imgs_ref, rec_ref) + ref_p
+    assert abs(losses['perceptual'].item() - ref_p.item()) < 2e-4 * max(abs(ref_p.item()), 1e-6)
+    losses['total'].backward()
+    ref_total.backward()
+    for name, prm in model.named_parameters():
+        g_ref = p[name].grad
+        if g_ref is None or g_ref.abs().max() == 0:
+            continue
+        rel = ((prm.grad.cpu().double() - g_ref).norm() / g_ref.norm()).item()
+        assert rel < 2e-2, f'{name}: rel grad err {rel:.3e}'      # masked pixels still carry the (dense) perceptual gradient
+    # the term really contributes: dropping it changes the texture gradient
+    g_with = model.textures.grad.clone()
+    model.zero_grad(set_to_none=True)
+    model.loss_weights = {'rgb': 1.0}
+    model(inp, None)['total'].backward()
+    assert (g_with - model.textures.grad).norm() > 1e-3 * g_with.norm()
+
+
+def test_pipelined_steps_each_draw_their_own_opacity_noise():
+    """two GraphedSteps on one model (PipelinedGraphedStep): each replays against ITS captured noise buffer, refreshed before
+    every replay from a shared generator -- round 1's second capture orphaned the first one's buffer (ADVICE)"""
+    from dbw_b200.parallel import ViewParallel
+    from dbw_b200.graph import PipelinedGraphedStep
+    model, tpl, p, dev = _model_and_oracle()
+    model.opacity_noise = True
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    vp = ViewParallel(model, seed=5)
+    piped = PipelinedGraphedStep(vp, inp, len(inp['imgs']))
+    host = {k: v.cpu().pin_memory() for k, v in inp.items()}
+    seen = []
+    for it in range(4):
+        losses = piped.run(host, host)
+        torch.cuda.synchronize()
+        step = piped.steps[it % 2]
+        assert step.noise_buf.abs().max().item() > 0                        # drawn, not the stale zeros
+        assert model.opacity_noise_buffer is step.noise_buf
+        seen.append((step.noise_buf.clone(), losses['rgb'].item()))
+    assert all(not torch.equal(seen[i][0], seen[j][0]) for i in range(4) for j in range(i))      # consecutive draws of one generator
+    assert len({round(l, 9) for _, l in seen}) == 4                         # and the loss follows the noise
+    # an eager step with step 3's noise reproduces step 3's loss
+    model.opacity_noise_buffer = seen[3][0]
+    assert abs(model(inp, None)['rgb'].item() - seen[3][1]) < 1e-7
+
+
+def test_row_band_shards_sum_to_the_batch():
+    """(view, row band) sharding (parallel.shard_row_bands + dbw_render.h view_rows): the loss and every leaf gradient of the
+    full batch == the sum over 3 'ranks' that each render their bands of the views they touch"""
+    from dbw_b200.parallel import shard_row_bands
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev, B=3)
+    model.loss_weights = {'rgb': 1.0}
+    model.n_total_views = 3
+    model.zero_grad(set_to_none=True)
+    full = model(inp, None)
+    full['total'].backward()
+    g_full = {n: prm.grad.clone() for n, prm in model.named_parameters() if prm.grad is not None}
+    tot, g_sum = 0.0, None
+    for rank in range(3):
+        pieces = shard_row_bands(3, 48, 3, rank)                # 48 rows = 3 bands per view: ranks own whole views here...
+        pieces = [(v, a, b) for v, a, b in pieces]
+        if rank == 0:                                            # ...so cut unevenly by hand: rank 0 gets view 0 + top of view 1
+            pieces = [(0, 0, 48), (1, 0, 16)]
+        elif rank == 1:
+            pieces = [(1, 16, 48), (2, 0, 32)]
+        else:
+            pieces = [(2, 32, 48)]
+        idx = [v for v, _, _ in pieces]
+        local = {k: v[idx[0]:idx[-1] + 1].contiguous() for k, v in inp.items()}
+        local['rows'] = torch.tensor([[a, b] for _, a, b in pieces], dtype=torch.int32, device=dev)
+        model.zero_grad(set_to_none=True)
+        out = model(local, None)
+        out['total'].backward()
+        tot += out['rgb'].item()
+        g = {n: prm.grad.clone() for n, prm in model.named_parameters() if prm.grad is not None}
+        g_sum = g if g_sum is None else {n: g_sum[n] + g[n] for n in g}
+    assert abs(tot - full['rgb'].item()) < 1e-6 * max(1.0, abs(tot))
+    for n in g_full:
+        assert (g_sum[n] - g_full[n]).norm() <= 1e-4 * g_full[n].norm() + 1e-12, (n, (g_sum[n] - g_full[n]).norm().item(), g_full[n].norm().item())
+
+
+def test_quantitative_and_qualitative_eval(tmp_path):
+    """the two evaluation entry points the trainer calls at the end of a run (trainer.py:246-249): the final_scores.tsv columns
+    of dbw.py:464-493 and the still images / OBJ meshes of dbw.py:495-554"""
+    model, tpl, p, dev = _model_and_oracle(fine=True)
+    inp, *_ = _inputs(dev, B=4)
+    loader = [({k: v[:2].cpu() for k, v in inp.items()}, {}), ({k: v[2:].cpu() for k, v in inp.items()}, {})]
+    scores = model.quantitative_eval(loader, dev, hard_inference=True)
+    assert list(scores)[:6] == ['n_blocks', 'L_tot', 'L_rec', 'PSNR', 'SSIM', 'LPIPS'] and list(scores)[6:] == [f'alpha{k}' for k in range(5)]
+    assert scores['n_blocks'] == 3 and 3 < scores['PSNR'] < 20 and -0.2 < scores['SSIM'] < 0.5 and scores['L_rec'] > 0
+    n = model.qualitative_eval(loader, dev, path=tmp_path)
+    assert n == 4
+    names = {f.name for f in tmp_path.iterdir()} | {f'textures/{f.name}' for f in (tmp_path / 'textures').iterdir()}
+    assert {'mesh.obj', 'mesh_full.obj', '0_inp.png', '0_rec.png', '0_rec_col.png', '0_rec_col_inp.png', '0_rec_syn_nobkg.png',
+            '0_rec_syn_nobkg_edged.png', '3_rec.png', 'textures/bkg.png', 'textures/ground.png', 'textures/block_04.png'} <= names
+    faces = sum(1 for l in open(tmp_path / 'mesh.obj') if l.startswith('f '))
+    assert faces == 128 + 3 * 80                                   # reduced ground + the three opaque blocks

@@ -1,0 +1,136 @@
+"""Multi-GPU (skipped on a 1-GPU box; run with `gpurun --gpus 2`): the hand-written NVLink peer-memory all-reduce
+(csrc/dbw_comm.cu) against ncclAllReduce, eagerly and captured inside a CUDA graph, and a row-band-sharded 2-rank step
+against the single-GPU step."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+
+
+def _w_allreduce(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    import dbw_b200  # noqa: F401
+    from dbw_b200.parallel import PeerAllReduce
+    res = {}
+    for n in (64, 36864, 2_400_004):                         # one-shot (small), one-shot (the pooled bucket), two-shot (9.6 MB)
+        n4 = (n + 3) // 4 * 4
+        comm = PeerAllReduce(n4, dev)
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        ok = True
+        for it in range(5):                                  # several epochs: parity double buffering, flag stamps
+            x = torch.randn(n4, device=dev, generator=g)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            y = x.clone()
+            comm.all_reduce(y)
+            torch.cuda.synchronize()
+            ok = ok and bool((y - ref).abs().max() <= 1e-5 * ref.abs().max())
+            gathered = [torch.empty_like(y) for _ in range(world)]
+            dist.all_gather(gathered, y)
+            ok = ok and all(torch.equal(gathered[0], t) for t in gathered)       # bit-identical on every rank
+        # captured in a CUDA graph and replayed
+        static = torch.zeros(n4, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            comm.all_reduce(static)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            comm.all_reduce(static)
+        for it in range(3):
+            x = torch.randn(n4, device=dev, generator=g)
+            ref = x.clone()
+            dist.all_reduce(ref)
+            static.copy_(x)
+            graph.replay()
+            torch.cuda.synchronize()
+            ok = ok and bool((static - ref).abs().max() <= 1e-5 * ref.abs().max())
+        res[n] = (ok, comm.error())
+        dist.barrier()
+        comm.close()
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+@needs2
+def test_peer_memory_all_reduce_matches_nccl():
+    world = min(torch.cuda.device_count(), 8)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_w_allreduce, args=(world, 29500 + os.getpid() % 1000, out), nprocs=world, join=True)
+    for rank in range(world):
+        for n, (ok, err) in out[rank].items():
+            assert ok and err == 0, (rank, n, ok, err)
+
+
+def _w_step(rank, world, port, out, collective):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    import dbw_b200  # noqa: F401
+    from dbw_b200.parallel import ViewParallel
+    from dbw_b200.graph import GraphedStep
+    from tests.test_model_gpu import CFG
+    from dbw_b200.dbw import DifferentiableBlocksWorld
+    from oracle import dbw_path as D
+    from copy import deepcopy
+    cfg = deepcopy(CFG)
+    cfg['loss'] = {'rgb_weight': 1}
+    torch.manual_seed(5)
+    model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
+    model.train()
+    R, T, K = D.ring_cameras(5, jitter=0.3, seed=7)
+    g = torch.Generator().manual_seed(7)
+    inp = {'imgs': torch.rand(5, 3, 48, 64, generator=g), 'R': R, 'T': T, 'K': K[None].expand(5, -1, -1).contiguous()}
+    vp = ViewParallel(model, seed=5, row_bands=True, collective=collective)
+    local, n_total = vp.shard(inp)
+    local = {k: v.to(dev) for k, v in local.items()}
+    graphed = GraphedStep(vp, local, n_total)
+    graphed.run()
+    torch.cuda.synchronize()
+    out[rank] = (vp.bucket.flat.cpu(), graphed.capture_all_reduce, local['rows'].cpu().tolist(), graphed.noise_buf.cpu())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@needs2
+@pytest.mark.parametrize('collective', ['p2p', 'nccl'])
+def test_two_rank_row_band_step_equals_single_gpu_step(collective):
+    """5 views of 48 rows over 2 ranks = 7.5 bands each: the ranks split view 2 in the middle; the all-reduced gradient bucket
+    (peer-memory kernel captured inside the step's CUDA graph, or NCCL after the replay) == the single-GPU step's"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_w_step, args=(2, 29600 + os.getpid() % 1000, out, collective), nprocs=2, join=True)
+    assert out[0][1] == (collective == 'p2p')
+    assert out[0][2][-1][1] < 48 and out[1][2][0][0] > 0             # view 2 is shared
+    assert torch.equal(out[0][0], out[1][0]) if collective == 'p2p' else torch.allclose(out[0][0], out[1][0], rtol=1e-6, atol=1e-9)
+    import dbw_b200  # noqa: F401
+    from dbw_b200.parallel import ViewParallel
+    from tests.test_model_gpu import CFG
+    from dbw_b200.dbw import DifferentiableBlocksWorld
+    from oracle import dbw_path as D
+    from copy import deepcopy
+    cfg = deepcopy(CFG)
+    cfg['loss'] = {'rgb_weight': 1}
+    torch.manual_seed(5)
+    dev = torch.device('cuda:0')
+    model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
+    model.train()
+    R, T, K = D.ring_cameras(5, jitter=0.3, seed=7)
+    g = torch.Generator().manual_seed(7)
+    inp = {'imgs': torch.rand(5, 3, 48, 64, generator=g).to(dev), 'R': R.to(dev), 'T': T.to(dev), 'K': K[None].expand(5, -1, -1).to(dev)}
+    vp = ViewParallel(model, seed=5)
+    model.opacity_noise_buffer = out[0][3].to(dev)
+    vp.forward_backward(inp)
+    ref = vp.bucket.flat.cpu()
+    assert (out[0][0] - ref).norm() <= 1e-4 * ref.norm(), ((out[0][0] - ref).norm().item(), ref.norm().item())

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import dbw_path as D, pt3d
-from tests._refextract import extract, have_reference
+from tests._refextract import extract, extract_method, have_reference
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -183,3 +183,38 @@ def test_restatements_match_reference_source():
         f, uv = nsm['get_icosphere_uvs'](lvl, fix_continuity=True, fix_poles=True)
         fo, uvo = D.get_icosphere_uvs(lvl)
         assert torch.equal(f, fo) and torch.equal(uv, uvo)
+
+
+@pytest.mark.skipif(not have_reference(), reason='needs the reference checkout (/root/reference)')
+@pytest.mark.parametrize('coarse', [True, False])
+@pytest.mark.parametrize('tv_type', ['l2sq', 'l2', 'l1'])
+def test_regulariser_restatement_matches_reference_compute_losses(coarse, tv_type):
+    """oracle.regularisers (parsimony / TV / overlap) against the reference's own DifferentiableBlocksWorld.compute_losses
+    (src/model/dbw.py:361-408), extracted with ast and run on a stand-in `self` that carries the state build_* leaves behind"""
+    ns = extract('src/utils/pytorch.py', ['safe_pow', 'SQRT_EPS'])
+    nsq = extract('src/utils/superquadric.py', ['implicit_sq'], {'safe_pow': ns['safe_pow']})
+    nsl = extract('src/model/loss.py', ['tv_norm_funcs'], {'safe_pow': ns['safe_pow']})
+    fn = extract_method('src/model/dbw.py', 'DifferentiableBlocksWorld', 'compute_losses',
+                        {'safe_pow': ns['safe_pow'], 'implicit_sq': nsq['implicit_sq'], 'OVERLAP_N_POINTS': 1000,
+                         'OVERLAP_N_BLOCKS': 1.95, 'OVERLAP_TEMPERATURE': 0.005})
+    tpl = D.SceneTemplate(n_blocks=4, txt_size=16)
+    p = D.init_params(4, 16, seed=2, boxy=True)
+    p['alpha_logit'] = torch.tensor([3.0, 2.5, 2.0, -6.0])
+    p['T'] = p['T'] * 0.02                                           # crowd the blocks: the overlap term must be active
+    keep = torch.sigmoid(p['alpha_logit']) > 0.01                    # kill_blocks
+    alpha_full = torch.sigmoid(p['alpha_logit']) * keep
+    S, Rm = p['S'].exp() + tpl.scale_min, pt3d.rotation_6d_to_matrix(p['R_6d'])
+    eps = torch.sigmoid(p['sq_eps']) * 1.8 + 0.1
+    me = SimpleNamespace(loss_weights={'parsimony': 0.01, 'tv': 0.1, 'overlap': 1.0}, is_live=lambda name: coarse,
+                         _alpha_full=alpha_full, _bkg_maps=torch.sigmoid(p['texture_bkg']), _ground_maps=torch.sigmoid(p['texture_ground']),
+                         _blocks_maps=torch.sigmoid(p['textures']), tv_norm=nsl['tv_norm_funcs'][tv_type], n_blocks=4,
+                         ratio_block_scene=tpl.ratio, _blocks_SRT=(S, Rm, p['T']), _blocks_eps=(eps[:, :1], eps[:, 1:]))
+    torch.manual_seed(77)
+    ref = fn(me, torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4))
+    torch.manual_seed(77)
+    u01 = torch.rand(4, 1000, 3)
+    got = D.regularisers(tpl, p, coarse=coarse, keep=keep, tv_type=tv_type, unit_samples=u01, weights=(0.01, 0.1, 1.0))
+    for k in ('parsimony', 'tv', 'overlap'):
+        assert torch.allclose(got[k], ref[k], rtol=1e-6, atol=1e-9), (k, got[k].item(), ref[k].item())
+    if coarse:
+        assert ref['overlap'] > 0 and ref['parsimony'] > 0
