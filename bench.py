@@ -137,7 +137,7 @@ def make_passes(local, rows, w):
     """split this rank's views into passes of equal shape: [{imgs, R, T, K, rows}] (host, pinned).  Padding entries of the
     last pass repeat view 0 with an EMPTY row range, so that one captured graph serves every pass."""
     B_local, H, W, K = len(local['imgs']), w['height'], w['width'], w['faces_per_pixel']
-    per_view = H * W * (16 * K + 17 + 16 * 6 + 12)          # fragment records + count (both passes), RGBA-sized images, target
+    per_view = H * W * (32 * K + 33 + 16 * 6 + 12)          # fragment records + count (both passes), RGBA-sized images, target
     cap = max(1, int(PASS_BYTES // per_view))
     n_pass = -(-B_local // cap)
     size = -(-B_local // n_pass)
@@ -199,20 +199,26 @@ def run_ours(args):
             vp.bucket.all_reduce(vp.group)
 
     graphed = piped = None
+    nocoll = None
     if not args.no_graph:
-        piped = PipelinedGraphedStep(vp, dev_passes[0], B)
+        # the peer-memory all-reduce is captured inside the graph when the step is a single pass (it then cannot be skipped:
+        # a second graph without it serves the "what does the collective add" measurement)
+        in_graph = vp.graph_capturable_collective and n_pass == 1
+        piped = PipelinedGraphedStep(vp, dev_passes[0], B, capture_all_reduce=in_graph)
         graphed = piped.steps[0]
+        nocoll = GraphedStep(vp, dev_passes[0], B, capture_all_reduce=False) if (in_graph and world > 1) else graphed
 
     def step_resident(collective=True):
         if graphed is None:
             return step_eager(collective)
+        g = graphed if collective else nocoll
         for i, p in enumerate(dev_passes):
-            graphed.run(p if n_pass > 1 else None, all_reduce=False)
+            g.run(p if n_pass > 1 else None, all_reduce=False)          # a collective captured in the graph runs regardless
             if acc is not None:
                 acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
         if acc is not None:
             vp.bucket.flat.copy_(acc)
-        if collective:
+        if collective and not g.capture_all_reduce:
             vp.bucket.all_reduce(vp.group)
 
     def step_e2e():
@@ -234,7 +240,8 @@ def run_ours(args):
                 loss = loss + losses['rgb']
         if acc is not None:
             vp.bucket.flat.copy_(acc)
-        vp.bucket.all_reduce(vp.group)
+        if piped is None or not piped.steps[0].capture_all_reduce:
+            vp.bucket.all_reduce(vp.group)
         return float(loss.item())                                                 # D2H read of the step's result
 
     def barrier():

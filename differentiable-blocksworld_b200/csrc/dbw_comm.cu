@@ -27,7 +27,7 @@ int dbw_fail_(const char* what, cudaError_t e);
 void dbw_count_launch_(void);
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return dbw_fail_(#call, _e); } while (0)
 
-#define COMM_MAX_WORLD 16
+#define COMM_MAX_WORLD 8
 #define COMM_BLOCKS 48
 #define COMM_THREADS 512
 #define ONE_SHOT_BYTES (512 * 1024)
@@ -93,6 +93,20 @@ __device__ __forceinline__ void rank_barrier(const CommDev& c, unsigned* ctl, in
   }
 }
 
+// sum of element i over the W ranks' staged addends, in rank order; all W (x UNROLL) peer loads are issued before the first
+// add waits: a peer load costs ~2 us over NVLink, a chain of them per element would cost world x that
+template <int W>
+__device__ __forceinline__ float4 sum_ranks(const CommDev& c, int par, size_t i) {
+  float4 v[W];
+#pragma unroll
+  for (int p = 0; p < W; ++p) v[p] = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
+  float4 acc = v[0];
+#pragma unroll
+  for (int p = 1; p < W; ++p) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
+  return acc;
+}
+
+template <int W>
 __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev c, float* __restrict__ buf, size_t n4) {
   unsigned* ctl = c.ctrl[c.rank];
   const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];     // stable until block 0 advances them after barrier A
@@ -108,36 +122,45 @@ __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev 
   const bool one_shot = n4 * sizeof(float4) <= ONE_SHOT_BYTES;
   if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + (one_shot ? 2u : 4u) * G; }
   if (one_shot) {
-    for (size_t i = tid; i < n4; i += nthr) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int p = 0; p < c.world; ++p) {
-        const float4 v = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      buf4[i] = acc;
+    size_t i = tid;
+    for (; i + nthr < n4; i += 2 * nthr) {                            // two elements per trip: 2 W loads in flight
+      const float4 a0 = sum_ranks<W>(c, par, i), a1 = sum_ranks<W>(c, par, i + nthr);
+      buf4[i] = a0; buf4[i + nthr] = a1;
     }
+    if (i < n4) buf4[i] = sum_ranks<W>(c, par, i);
     return;
   }
   // ---- two-shot: reduce my slice, publish it, gather the others
-  const size_t slice = (n4 + c.world - 1) / c.world;
+  const size_t slice = (n4 + W - 1) / W;
   const size_t lo = (size_t)c.rank * slice, hi = lo + slice < n4 ? lo + slice : n4;
   float4* myred = reinterpret_cast<float4*>(c.red[c.rank][par]);
-  for (size_t i = lo + tid; i < hi; i += nthr) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < c.world; ++p) {
-      const float4 v = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  {
+    size_t i = lo + tid;
+    for (; i + nthr < hi; i += 2 * nthr) {
+      const float4 a0 = sum_ranks<W>(c, par, i), a1 = sum_ranks<W>(c, par, i + nthr);
+      myred[i - lo] = a0; buf4[i] = a0; myred[i + nthr - lo] = a1; buf4[i + nthr] = a1;
     }
-    myred[i - lo] = acc; buf4[i] = acc;
+    if (i < hi) { const float4 a0 = sum_ranks<W>(c, par, i); myred[i - lo] = a0; buf4[i] = a0; }
   }
   grid_barrier(ctl, base + 3u * G);
   rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every rank's reduced slice is complete and visible
   grid_barrier(ctl, base + 4u * G);
-  for (int q = 1; q < c.world; ++q) {
-    const int p = (c.rank + q) % c.world;                             // start at different owners: spread the NVSwitch load
-    const size_t plo = (size_t)p * slice, phi = plo + slice < n4 ? plo + slice : n4;
-    const float4* src = reinterpret_cast<const float4*>(c.red[p][par]);
-    for (size_t i = plo + tid; i < phi; i += nthr) buf4[i] = ld_peer(src + (i - plo));
+  // gather: element j of the (W - 1) foreign slices, 4 loads in flight per thread
+  const size_t foreign = slice * (W - 1);
+  for (size_t j0 = tid; j0 < foreign; j0 += 4 * nthr) {
+    float4 v[4]; size_t dst[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t j = j0 + (size_t)u * nthr;
+      dst[u] = (size_t)-1;
+      if (j < foreign) {
+        const int p = (c.rank + 1 + (int)(j / slice)) % W;            // start at different owners: spread the NVSwitch load
+        const size_t off = j % slice, gi = (size_t)p * slice + off;
+        if (gi < n4) { dst[u] = gi; v[u] = ld_peer(reinterpret_cast<const float4*>(c.red[p][par]) + off); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (dst[u] != (size_t)-1) buf4[dst[u]] = v[u];
   }
 }
 
@@ -150,7 +173,7 @@ static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_data, si
 
 extern "C" int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out) {
   if (!comm_out || world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world || max_floats == 0)
-    return dbw_fail_("dbw_comm_create: bad arguments (1 <= world <= 16, 0 <= rank < world, max_floats > 0)", cudaSuccess);
+    return dbw_fail_("dbw_comm_create: bad arguments (1 <= world <= 8, 0 <= rank < world, max_floats > 0)", cudaSuccess);
   Comm* c = new Comm();
   memset(c, 0, sizeof(Comm));
   c->d.world = world; c->d.rank = rank; c->d.cap_floats = (max_floats + 3) / 4 * 4;
@@ -206,7 +229,18 @@ extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void
   if (n_floats % 4 || n_floats > c->d.cap_floats) return dbw_fail_("dbw_comm_all_reduce: n_floats must be a multiple of 4 and <= the capacity", cudaSuccess);
   if (((uintptr_t)buf) % 16) return dbw_fail_("dbw_comm_all_reduce: buf must be 16-byte aligned", cudaSuccess);
   if (c->d.world == 1 || n_floats == 0) return 0;
-  all_reduce_kernel<<<COMM_BLOCKS, COMM_THREADS, 0, (cudaStream_t)stream>>>(c->d, buf, n_floats / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n4 = n_floats / 4;
+  switch (c->d.world) {
+    case 2: all_reduce_kernel<2><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 3: all_reduce_kernel<3><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 4: all_reduce_kernel<4><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 5: all_reduce_kernel<5><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 6: all_reduce_kernel<6><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 7: all_reduce_kernel<7><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    case 8: all_reduce_kernel<8><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+    default: return dbw_fail_("dbw_comm_all_reduce: world sizes 2..8 are compiled in (one NVSwitch node)", cudaSuccess);
+  }
   dbw_count_launch_();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return dbw_fail_("all_reduce_kernel", e);
