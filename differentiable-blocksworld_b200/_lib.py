@@ -49,7 +49,7 @@ EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_work
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
            'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward',
-           'dbw_comm_create', 'dbw_comm_ipc_handle', 'dbw_comm_connect', 'dbw_comm_all_reduce', 'dbw_comm_error', 'dbw_comm_destroy']
+           'dbw_comm_create', 'dbw_comm_buffer', 'dbw_comm_ipc_handle', 'dbw_comm_connect', 'dbw_comm_all_reduce', 'dbw_comm_error', 'dbw_comm_destroy']
 
 _lib = None
 
@@ -85,6 +85,7 @@ def lib():
         L.dbw_texture_prep_forward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp]
         L.dbw_texture_prep_backward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp, vp]
         L.dbw_comm_create.argtypes = [ctypes.c_int32, ctypes.c_int32, sz, ctypes.POINTER(vp)]
+        L.dbw_comm_buffer.argtypes = [vp, ctypes.POINTER(vp)]
         L.dbw_comm_ipc_handle.argtypes = [vp, vp]
         L.dbw_comm_connect.argtypes = [vp, vp]
         L.dbw_comm_all_reduce.argtypes = [vp, vp, sz, vp]

@@ -4,16 +4,16 @@
 //
 // One process per GPU.  Every rank owns an arena (cudaMalloc, exported with cudaIpcGetMemHandle, opened by its peers):
 //     control:  flagsA[world], flagsB[world] (written BY the peers), epoch, grid-barrier counters
-//     data[2]   the rank's addends of this / the previous all-reduce          (parity = epoch & 1)
-//     red[2]    the slice of the sum this rank reduced (two-shot path)
-// all_reduce(buf, n):
-//     stage buf -> data[parity];  barrier A (every rank's addends are visible)
-//     one-shot (payload <= ONE_SHOT_BYTES): every rank sums all peers' data in rank order                -> buf
-//     two-shot: rank r sums slice r of all peers' data -> red[parity] and buf;  barrier B;  the other slices are read
-//               from their owners' red                                                                   -> buf
-// Every rank adds in the same order (0..world-1), so the result is bit-identical on all ranks.  The parity double buffering
-// replaces the trailing barrier: a rank can overwrite data[p] / red[p] of epoch e only in epoch e+2, which it reaches after
-// barrier A of e+1, i.e. after every peer has launched e+1 and therefore finished reading epoch e (stream order).
+//     flat      the gradient bucket itself (dbw_comm_buffer: the caller's tensors live HERE, nothing is staged)
+//     inbox     world slices: the addends the peers push for the slice of the sum this rank owns
+// all_reduce(n) is a PUSH protocol -- every remote access is a posted store, no rank ever waits for a load over NVLink:
+//     scatter   element i of my bucket goes to inbox[my rank] of its owner (owner = i / slice); my own slice stays local
+//     barrier A (every rank's pushes have landed)
+//     reduce    the owner adds its world inbox slices in rank order and stores the sum into EVERY rank's bucket
+//     barrier B (every rank's results have landed)
+// Every sum is formed once, by its owner, in rank order: the result is bit-identical on all ranks.  Hazards: a peer writes
+// results into my bucket only after barrier A, which I pass only after my scatter has read it; my next scatter writes the
+// peers' inboxes only after barrier B of this epoch, which an owner signals after its reduce has read them.
 // Barriers are epoch-stamped flags stored into the PEERS' arenas with st.release.sys and polled locally with
 // ld.acquire.sys; a poll that exceeds ~2 s sets the arena's error word instead of hanging the GPU.
 #include <cuda_runtime.h>
@@ -28,7 +28,7 @@ void dbw_count_launch_(void);
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return dbw_fail_(#call, _e); } while (0)
 
 #define COMM_MAX_WORLD 8
-#define COMM_BLOCKS 48
+#define COMM_BLOCKS 96
 #define COMM_THREADS 512
 #define ONE_SHOT_BYTES (512 * 1024)
 #define CTRL_BYTES 4096
@@ -36,9 +36,9 @@ void dbw_count_launch_(void);
 struct CommDev {
   int world, rank;
   unsigned* ctrl[COMM_MAX_WORLD];        // each rank's control block: [0,world) flagsA, [64, 64+world) flagsB
-  float* data[COMM_MAX_WORLD][2];
-  float* red[COMM_MAX_WORLD][2];
-  size_t cap_floats;
+  float* flat[COMM_MAX_WORLD];           // each rank's bucket
+  float* inbox[COMM_MAX_WORLD];          // each rank's inbox: world slices of slice_floats
+  size_t cap_floats, slice_floats;
 };
 // local control words (indices into ctrl[rank]): 128 epoch, 129 grid-barrier arrivals, 130 barrier base, 131 error
 #define CW_FLAGS_A 0
@@ -93,82 +93,59 @@ __device__ __forceinline__ void rank_barrier(const CommDev& c, unsigned* ctl, in
   }
 }
 
-// sum of element i over the W ranks' staged addends, in rank order; all W (x UNROLL) peer loads are issued before the first
-// add waits: a peer load costs ~2 us over NVLink, a chain of them per element would cost world x that
-template <int W>
-__device__ __forceinline__ float4 sum_ranks(const CommDev& c, int par, size_t i) {
-  float4 v[W];
-#pragma unroll
-  for (int p = 0; p < W; ++p) v[p] = ld_peer(reinterpret_cast<const float4*>(c.data[p][par]) + i);
-  float4 acc = v[0];
-#pragma unroll
-  for (int p = 1; p < W; ++p) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
-  return acc;
+__device__ __forceinline__ void st_peer(float4* p, float4 v) {       // posted store into a peer's arena
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 template <int W>
 __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev c, float* __restrict__ buf, size_t n4) {
   unsigned* ctl = c.ctrl[c.rank];
   const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];     // stable until block 0 advances them after barrier A
-  const int par = epoch & 1u, G = gridDim.x;
+  const int G = gridDim.x, r = c.rank;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)G * blockDim.x;
-  float4* buf4 = reinterpret_cast<float4*>(buf);
-  // ---- stage this rank's addends where the peers can read them
-  float4* mine = reinterpret_cast<float4*>(c.data[c.rank][par]);
-  for (size_t i = tid; i < n4; i += nthr) mine[i] = buf4[i];
-  grid_barrier(ctl, base + 1u * G);
-  rank_barrier(c, ctl, CW_FLAGS_A, epoch);                            // A: every rank's data[par] is complete and visible
-  grid_barrier(ctl, base + 2u * G);
-  const bool one_shot = n4 * sizeof(float4) <= ONE_SHOT_BYTES;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + (one_shot ? 2u : 4u) * G; }
-  if (one_shot) {
-    size_t i = tid;
-    for (; i + nthr < n4; i += 2 * nthr) {                            // two elements per trip: 2 W loads in flight
-      const float4 a0 = sum_ranks<W>(c, par, i), a1 = sum_ranks<W>(c, par, i + nthr);
-      buf4[i] = a0; buf4[i + nthr] = a1;
-    }
-    if (i < n4) buf4[i] = sum_ranks<W>(c, par, i);
-    return;
-  }
-  // ---- two-shot: reduce my slice, publish it, gather the others
-  const size_t slice = (n4 + W - 1) / W;
-  const size_t lo = (size_t)c.rank * slice, hi = lo + slice < n4 ? lo + slice : n4;
-  float4* myred = reinterpret_cast<float4*>(c.red[c.rank][par]);
-  {
-    size_t i = lo + tid;
-    for (; i + nthr < hi; i += 2 * nthr) {
-      const float4 a0 = sum_ranks<W>(c, par, i), a1 = sum_ranks<W>(c, par, i + nthr);
-      myred[i - lo] = a0; buf4[i] = a0; myred[i + nthr - lo] = a1; buf4[i + nthr] = a1;
-    }
-    if (i < hi) { const float4 a0 = sum_ranks<W>(c, par, i); myred[i - lo] = a0; buf4[i] = a0; }
-  }
-  grid_barrier(ctl, base + 3u * G);
-  rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every rank's reduced slice is complete and visible
-  grid_barrier(ctl, base + 4u * G);
-  // gather: element j of the (W - 1) foreign slices, 4 loads in flight per thread
-  const size_t foreign = slice * (W - 1);
-  for (size_t j0 = tid; j0 < foreign; j0 += 4 * nthr) {
-    float4 v[4]; size_t dst[4];
+  const float4* src = reinterpret_cast<const float4*>(buf);
+  const size_t slice = (n4 + W - 1) / W;                              // float4 elements per owner
+  const size_t cap4 = c.slice_floats / 4;                             // inbox stride between the ranks' slices
+  // ---- scatter: push every element to its owner's inbox (my own slice: a local copy)
+  for (size_t i0 = tid; i0 < n4; i0 += 4 * nthr) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const size_t i = i0 + (size_t)u * nthr; if (i < n4) v[u] = src[i]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const size_t j = j0 + (size_t)u * nthr;
-      dst[u] = (size_t)-1;
-      if (j < foreign) {
-        const int p = (c.rank + 1 + (int)(j / slice)) % W;            // start at different owners: spread the NVSwitch load
-        const size_t off = j % slice, gi = (size_t)p * slice + off;
-        if (gi < n4) { dst[u] = gi; v[u] = ld_peer(reinterpret_cast<const float4*>(c.red[p][par]) + off); }
+      const size_t i = i0 + (size_t)u * nthr;
+      if (i < n4) {
+        const int owner = (int)(i / slice);
+        st_peer(reinterpret_cast<float4*>(c.inbox[owner]) + (size_t)r * cap4 + (i - (size_t)owner * slice), v[u]);
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) if (dst[u] != (size_t)-1) buf4[dst[u]] = v[u];
   }
+  grid_barrier(ctl, base + 1u * G);
+  rank_barrier(c, ctl, CW_FLAGS_A, epoch);                            // A: every rank's pushes into my inbox have landed
+  grid_barrier(ctl, base + 2u * G);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + 3u * G; }
+  // ---- reduce my slice in rank order, broadcast the sums into every rank's bucket
+  const size_t lo = (size_t)r * slice, hi = lo + slice < n4 ? lo + slice : n4;
+  const float4* in = reinterpret_cast<const float4*>(c.inbox[r]);
+  for (size_t i = lo + tid; i < hi; i += nthr) {
+    float4 v[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) v[q] = ld_peer(in + (size_t)q * cap4 + (i - lo));      // local memory, written remotely: not via L1
+    float4 acc = v[0];
+#pragma unroll
+    for (int q = 1; q < W; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+#pragma unroll
+    for (int q = 0; q < W; ++q) st_peer(reinterpret_cast<float4*>(c.flat[(r + q) % W]) + i, acc);
+  }
+  grid_barrier(ctl, base + 3u * G);
+  rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every owner's sums have landed in my bucket
 }
 
-static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_data, size_t* off_red, size_t* slice_floats) {
+static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_flat, size_t* off_inbox, size_t* slice_floats) {
   const size_t cap = (cap_floats + 3) / 4 * 4;
   const size_t slice = ((cap / 4 + world - 1) / world) * 4;
-  *off_data = CTRL_BYTES; *off_red = CTRL_BYTES + 2 * cap * sizeof(float); *slice_floats = slice;
-  return *off_red + 2 * slice * sizeof(float);
+  *off_flat = CTRL_BYTES; *off_inbox = CTRL_BYTES + cap * sizeof(float); *slice_floats = slice;
+  return *off_inbox + world * slice * sizeof(float);
 }
 
 extern "C" int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out) {
@@ -213,18 +190,27 @@ extern "C" int dbw_comm_connect(void* comm, const void* all_handles) {
     c->peer_base[p] = base;
     char* b = (char*)base;
     c->d.ctrl[p] = (unsigned*)b;
-    for (int q = 0; q < 2; ++q) {
-      c->d.data[p][q] = (float*)(b + od) + (size_t)q * c->d.cap_floats;
-      c->d.red[p][q] = (float*)(b + orr) + (size_t)q * sl;
-    }
+    c->d.flat[p] = (float*)(b + od);
+    c->d.inbox[p] = (float*)(b + orr);
   }
+  c->d.slice_floats = sl;
   c->connected = true;
+  return 0;
+}
+
+extern "C" int dbw_comm_buffer(void* comm, float** out) {
+  Comm* c = (Comm*)comm;
+  if (!c || !out) return dbw_fail_("dbw_comm_buffer: null argument", cudaSuccess);
+  size_t od, orr, sl;
+  arena_layout(c->d.cap_floats, c->d.world, &od, &orr, &sl);
+  *out = (float*)((char*)c->arena + od);
   return 0;
 }
 
 extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void* stream) {
   Comm* c = (Comm*)comm;
   if (!c || !buf) return dbw_fail_("dbw_comm_all_reduce: null argument", cudaSuccess);
+  if (c->connected && buf != c->d.flat[c->d.rank]) return dbw_fail_("dbw_comm_all_reduce: buf must be the arena's bucket (dbw_comm_buffer)", cudaSuccess);
   if (!c->connected) return dbw_fail_("dbw_comm_all_reduce: dbw_comm_connect has not run", cudaSuccess);
   if (n_floats % 4 || n_floats > c->d.cap_floats) return dbw_fail_("dbw_comm_all_reduce: n_floats must be a multiple of 4 and <= the capacity", cudaSuccess);
   if (((uintptr_t)buf) % 16) return dbw_fail_("dbw_comm_all_reduce: buf must be 16-byte aligned", cudaSuccess);

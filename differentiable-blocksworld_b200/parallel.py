@@ -57,6 +57,14 @@ class PeerAllReduce:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.handle = ctypes.c_void_p()
         _lib.check(L.dbw_comm_create(self.world, self.rank, max_floats, ctypes.byref(self.handle)), 'dbw_comm_create')
+        ptr = ctypes.c_void_p()
+        _lib.check(L.dbw_comm_buffer(self.handle, ctypes.byref(ptr)), 'dbw_comm_buffer')
+
+        class _Arena:          # zero-copy view of the arena's bucket as a tensor (CUDA array interface)
+            __cuda_array_interface__ = {'shape': (int(max_floats),), 'typestr': '<f4', 'data': (ptr.value, False), 'version': 3,
+                                        'strides': None}
+        self._arena = _Arena()
+        self.flat = torch.as_tensor(self._arena, device=device)      # the bucket the gradients are gathered into
         mine = (ctypes.c_ubyte * 64)()
         _lib.check(L.dbw_comm_ipc_handle(self.handle, mine), 'dbw_comm_ipc_handle')
         t = torch.tensor(list(mine), dtype=torch.uint8, device=device)
@@ -84,13 +92,20 @@ class PeerAllReduce:
 class GradBucket:
     """All parameter gradients as views into one flat buffer -> a single all-reduce per step."""
 
-    def __init__(self, params):
+    def __init__(self, params, peer_factory=None):
+        """peer_factory(n_floats, device) -> PeerAllReduce or None: when given and successful, the flat buffer IS the peer-memory
+        arena's bucket (csrc/dbw_comm.cu) and all_reduce() is its kernel; else a plain tensor and torch.distributed"""
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.n = n
-        self.flat = torch.zeros((n + 3) // 4 * 4, dtype=ref.dtype, device=ref.device)     # padded: 128-bit all-reduce lanes
-        self.peer = None               # PeerAllReduce once ViewParallel has set it up
+        n_pad = (n + 3) // 4 * 4                     # padded: 128-bit all-reduce lanes
+        self.peer = peer_factory(n_pad, ref.device) if peer_factory is not None else None
+        if self.peer is not None:
+            self.flat = self.peer.flat
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
         self._zeros = {}
         off, self.views = 0, []
         for p in self.params:
@@ -147,17 +162,22 @@ class ViewParallel:
         self.row_bands = row_bands          # shard at (view, row band) granularity (needs the model's fused-loss path)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.bucket = GradBucket(model.parameters())
-        self._step = 0
-        self.collective_name = 'none (1 rank)' if self.world_size == 1 else 'ncclAllReduce'
-        if self.world_size > 1 and collective in ('p2p', 'auto') and self.bucket.flat.is_cuda:
+        def peer_factory(n_floats, device):
+            if not (self.world_size > 1 and collective in ('p2p', 'auto') and device.type == 'cuda'):
+                return None
             try:
-                self.bucket.peer = PeerAllReduce(self.bucket.flat.numel(), self.bucket.flat.device, group)
-                self.collective_name = 'hand-written NVLink peer-memory kernel (dbw_comm_all_reduce), inside the CUDA graph'
+                return PeerAllReduce(n_floats, device, group)
             except Exception as exc:          # e.g. no peer access between the GPUs of this node
                 if collective == 'p2p':
                     raise
                 print(f'[dbw_b200] peer-memory all-reduce unavailable ({exc}); using NCCL')
+                return None
+
+        self.bucket = GradBucket(model.parameters(), peer_factory)
+        self._step = 0
+        self.collective_name = 'none (1 rank)' if self.world_size == 1 else 'ncclAllReduce'
+        if self.bucket.peer is not None:
+            self.collective_name = 'hand-written NVLink peer-memory push kernel (dbw_comm_all_reduce), inside the CUDA graph'
 
     @property
     def graph_capturable_collective(self):

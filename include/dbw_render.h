@@ -242,14 +242,17 @@ void dbw_timing_reset(void);
  * The step's one gradient exchange (views shard with no data-path collective; ONE all-reduce(SUM) of the flat
  * parameter-gradient bucket) as a hand-written all-reduce over NVLink peer memory -- a plain kernel launch on `stream`,
  * hence capturable inside the step's CUDA graph.  One process per GPU of one node:
- *   dbw_comm_create      allocates this rank's arena (2 x max_floats + control; cudaMalloc)
+ *   dbw_comm_create      allocates this rank's arena (bucket of max_floats + inbox of the same size + control; cudaMalloc)
+ *   dbw_comm_buffer      the arena's bucket: the caller keeps its gradients THERE (nothing is staged or copied)
  *   dbw_comm_ipc_handle  64-byte cudaIpcMemHandle of the arena, to be all-gathered by the caller (torch.distributed)
  *   dbw_comm_connect     opens the peers' arenas: all_handles = world x 64 bytes in rank order
- *   dbw_comm_all_reduce  in-place SUM of buf[0..n_floats) over the ranks (n_floats % 4 == 0, buf 16-byte aligned); every rank
- *                        adds in rank order: bit-identical results everywhere.  One-shot below 512 KB, two-shot above
+ *   dbw_comm_all_reduce  in-place SUM of the bucket's first n_floats over the ranks (n_floats % 4 == 0; buf must be the
+ *                        pointer dbw_comm_buffer returned).  Push protocol: slices are pushed to their owners, summed there
+ *                        in rank order (bit-identical results everywhere) and pushed back -- only posted stores cross NVLink
  *   dbw_comm_error       0, or which barrier timed out (a peer did not arrive within ~2 s: results are garbage, no hang)
  */
 int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out);
+int dbw_comm_buffer(void* comm, float** out);
 int dbw_comm_ipc_handle(void* comm, void* out_handle64);
 int dbw_comm_connect(void* comm, const void* all_handles);
 int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void* stream);

@@ -25,11 +25,12 @@ def _w_allreduce(rank, world, port, out):
         comm = PeerAllReduce(n4, dev)
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         ok = True
-        for it in range(5):                                  # several epochs: parity double buffering, flag stamps
+        for it in range(5):                                  # several epochs: flag stamps, inbox / bucket reuse
             x = torch.randn(n4, device=dev, generator=g)
             ref = x.clone()
             dist.all_reduce(ref)
-            y = x.clone()
+            y = comm.flat                                    # the arena's bucket: the all-reduce works in place on it
+            y.copy_(x)
             comm.all_reduce(y)
             torch.cuda.synchronize()
             ok = ok and bool((y - ref).abs().max() <= 1e-5 * ref.abs().max())
@@ -37,7 +38,7 @@ def _w_allreduce(rank, world, port, out):
             dist.all_gather(gathered, y)
             ok = ok and all(torch.equal(gathered[0], t) for t in gathered)       # bit-identical on every rank
         # captured in a CUDA graph and replayed
-        static = torch.zeros(n4, device=dev)
+        static = comm.flat
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
