@@ -429,6 +429,15 @@ __device__ __forceinline__ void shade_geometry(const RasterParams& P, int view, 
 #define DBW_BWD_BARY_MINB 4       // backward with the barycentric path: more live state (128 registers)
 #endif
 
+// CTA -> (view, tile) mapping of the raster kernels.  CTAs are dispatched in linear grid order, so the grid is laid out as
+// (view, tile column, tile row RANK) with the rows ranked centre-out: every view's central rows -- where the blocks are and the
+// CTAs run longest -- are dispatched first, the cheap border rows last.  With the few waves a view-sharded rank has (8750 CTAs
+// at 8 GPUs = 8 waves), the last wave otherwise holds the heavy tiles of the last view while most SMs idle.
+__device__ __forceinline__ int centre_out(int rank, int n) {
+  const int c = n >> 1;
+  return (rank & 1) ? c - ((rank + 1) >> 1) : c + (rank >> 1);
+}
+
 // One kernel for every K: the per-pixel list of the K nearest fragments lives in (dynamic) shared memory (dbw_fraglist.cuh).
 // EP: with the compositing + MSE loss epilogue (DbwLossEpilogue); a template flag so that plain renders carry none of it
 template <int NT, bool EP>
@@ -449,8 +458,9 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
 
   constexpr int TILE_H = NT / 16;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int view = blockIdx.z;
-  const int tx0 = blockIdx.x * TILE_W, ty0 = blockIdx.y * TILE_H;
+  const int view = blockIdx.x;
+  const int tile_y = centre_out(blockIdx.z, gridDim.z);
+  const int tx0 = blockIdx.y * TILE_W, ty0 = tile_y * TILE_H;
   // a warp covers an 8x4 pixel patch; 2x4 warps cover the 16x16 tile
   const int xi = tx0 + (warp & 1) * 8 + (lane & 7);
   const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
@@ -687,7 +697,7 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) ep_sq += __shfl_xor_sync(0xffffffffu, ep_sq, off);
     if (lane == 0 && ep_sq != 0.f) {
-      const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      const unsigned cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;      // any spread over the strip will do
       atomicAdd(&P.ep_partials[(cta * (NT / 32) + warp) & P.ep_part_mask], ep_sq * P.ep_inv_count);
     }
   }
@@ -902,12 +912,13 @@ template <bool DETACH, bool ALPHA, bool K1>
 __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW_BWD_BARY_MINB) raster_backward_kernel(const RasterParams P) {
   extern __shared__ float4 s_dyn[];             // [k][tid] (alpha, cdot, e, occ), [k][tid] record bits, the map table, opacity sums
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int view = blockIdx.z;
-  const int xi = blockIdx.x * TILE_W + (warp & 1) * 8 + (lane & 7);
-  const int yi = blockIdx.y * (DBW_BWD_NT / 16) + (warp >> 1) * 4 + (lane >> 3);
+  const int view = blockIdx.x;
+  const int tile_y = centre_out(blockIdx.z, gridDim.z);
+  const int xi = blockIdx.y * TILE_W + (warp & 1) * 8 + (lane & 7);
+  const int yi = tile_y * (DBW_BWD_NT / 16) + (warp >> 1) * 4 + (lane >> 3);
   int row_lo = 0, row_hi = P.H;
   if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
-  if ((int)(blockIdx.y * (DBW_BWD_NT / 16)) >= row_hi || (int)((blockIdx.y + 1) * (DBW_BWD_NT / 16)) <= row_lo) return;
+  if (tile_y * (DBW_BWD_NT / 16) >= row_hi || (tile_y + 1) * (DBW_BWD_NT / 16) <= row_lo) return;
   const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
   const size_t plane = (size_t)P.H * P.W;
   const size_t pix = live ? (size_t)yi * P.W + xi : 0;
@@ -1277,7 +1288,7 @@ static size_t frag_smem_bytes(int K, int NT, int M, int n_alpha = 0) {
 
 template <int NT>
 static cudaError_t launch_forward(const RasterParams& P, cudaStream_t st) {
-  const dim3 grid((P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16), P.B);
+  const dim3 grid(P.B, (P.W + TILE_W - 1) / TILE_W, (P.H + NT / 16 - 1) / (NT / 16));       // see centre_out()
   const size_t smem = frag_smem_bytes(P.K, NT, P.M);
   auto go = [&](auto kern) -> cudaError_t {
     if (smem > 40 * 1024) { cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
@@ -1407,7 +1418,7 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
   P.map_table = map_table;
   P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = need_geom ? g.g_tri : nullptr; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
-  dim3 grid((s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16), B);
+  dim3 grid(B, (s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16));       // see centre_out()
   const size_t smem = frag_smem_bytes(s->faces_per_pixel, DBW_BWD_NT, s->n_maps, P.n_alpha);
   {
     auto launch = [&](auto kern) -> cudaError_t {

@@ -34,5 +34,19 @@ with open(f'profiles/ncu_full_{tag}_summary.txt', 'w') as f:
     for w in want:
         if w in idx:
             f.write(f'{w:70s} [{units[idx[w]]:>14s}] ' + ' | '.join(r[idx[w]][:24] for r in data) + '\n')
+# bytes per launch of the four raster kernels for bench.py's roofline.traffic, tied to the kernel sources they were measured on
+import json
+sys.path.insert(0, os.getcwd())
+import bench
+names = ['raster_forward[env K=1]', 'raster_forward[blocks K=10]', 'raster_backward[blocks K=10]', 'raster_backward[env K=1]']
+def col(name):
+    i = idx[name]; u = units[i]
+    mult = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+    return [float(r[i].replace(',', '')) * mult for r in data]
+rd, wr = col('dram__bytes_read.sum'), col('dram__bytes_write.sum')
+if len(rd) == 4 and '--no-traffic-json' not in sys.argv:
+    json.dump({'kernel_fingerprint': bench.kernel_fingerprint(), 'workload': 'dtu', 'source': f'profiles/ncu_full_{tag}_summary.txt',
+               'bytes_per_launch': {n: rd[i] + wr[i] for i, n in enumerate(names)}}, open('profiles/ncu_traffic.json', 'w'), indent=1)
+    print('wrote profiles/ncu_traffic.json', bench.kernel_fingerprint())
 print(open(f'profiles/launches_{tag}_summary.txt').read()[:1800])
 print(open(f'profiles/ncu_full_{tag}_summary.txt').read())
