@@ -44,7 +44,7 @@ class DbwMapDesc(ctypes.Structure):
                 ('reserved', ctypes.c_int32)]
 
 
-EXPORTS = ['dbw_abi_version', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_forward_ex', 'dbw_render_backward',
+EXPORTS = ['dbw_abi_version', 'dbw_debug_generic_kernel_only', 'dbw_sizeof_settings', 'dbw_last_error', 'dbw_workspace_bytes', 'dbw_render_forward', 'dbw_render_forward_ex', 'dbw_render_backward',
            'dbw_render_forward_loss', 'dbw_render_backward_scaled',
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
@@ -91,6 +91,8 @@ def lib():
         L.dbw_comm_all_reduce.argtypes = [vp, vp, sz, vp]
         L.dbw_comm_error.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
         L.dbw_comm_destroy.argtypes = [vp]
+        L.dbw_debug_generic_kernel_only.restype = None
+        L.dbw_debug_generic_kernel_only.argtypes = [ctypes.c_int]
         L.dbw_timing_enable.restype = None
         L.dbw_timing_reset.restype = None
         L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]

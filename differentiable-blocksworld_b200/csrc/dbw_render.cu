@@ -45,6 +45,9 @@ void dbw_count_launch_(void) { ++g_launches; }
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) return fail(#call, _e); } while (0)
 #define LAUNCH_CK(name) do { ++g_launches; cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail(name, _e); } while (0)
 
+static int g_no_hard_kernel = 0;
+// test hook: 1 routes hard single-layer renders through the generic kernel (the two must agree bit for bit)
+extern "C" void dbw_debug_generic_kernel_only(int on) { g_no_hard_kernel = on; }
 extern "C" int dbw_abi_version(void) { return DBW_ABI_VERSION; }
 extern "C" size_t dbw_sizeof_settings(void) { return sizeof(DbwRenderSettings); }
 extern "C" const char* dbw_last_error(void) { return g_err; }
@@ -85,6 +88,7 @@ extern "C" void dbw_timing_reset(void) {
 
 struct Workspace {
   float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4;
+  int* view_nvis; int* vis_list;
   float4* frag; float4* frag_rgb; unsigned char* nfrag; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
@@ -97,6 +101,8 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.conv = (float*)(p + off);      off += align_up(B * S * 9 * sizeof(float));
   w.view_flags = (int*)(p + off);  off += align_up(B * sizeof(int));
   w.view_bbox = (int*)(p + off);   off += align_up(B * 4 * sizeof(int));
+  w.view_nvis = (int*)(p + off);   off += align_up(B * sizeof(int));
+  w.vis_list = (int*)(p + off);    off += align_up(B * S * sizeof(int));
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   const size_t npx = B * (size_t)s.height * s.width;
   w.frag = (float4*)(p + off);     off += s.save_fragment_state ? align_up(npx * (size_t)s.faces_per_pixel * sizeof(float4)) : 0;
@@ -153,11 +159,11 @@ __global__ void fold_gmaps_kernel(const float4* __restrict__ g4, float* __restri
 // ------------------------------------------------------------------------------------------------ projection (A1)
 __global__ void project_verts_kernel(const float* __restrict__ vw, const float* __restrict__ R, const float* __restrict__ T,
                                      float fx, float fy, float px, float py, float eps, int B, int V, float* __restrict__ out,
-                                     int* __restrict__ view_bbox, int* __restrict__ view_flags) {
+                                     int* __restrict__ view_bbox, int* __restrict__ view_flags, int* __restrict__ view_nvis) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   // per-view state face_setup accumulates into (it runs after this kernel on the same stream): reset here, no extra launch
   if (i < B * 4) view_bbox[i] = (i & 1) ? (int)0x807fffff : (int)0x7f800000;     // f2ord(-inf) : f2ord(+inf)
-  if (i < B) view_flags[i] = 0;
+  if (i < B) { view_flags[i] = 0; view_nvis[i] = 0; }
   if (i >= B * V) return;
   const int b = i / V, v = i - b * V;
   const float X = vw[v * 3], Y = vw[v * 3 + 1], Z = vw[v * 3 + 2];
@@ -243,17 +249,18 @@ __device__ __forceinline__ void write_slot(float4* bbox, float4* rec, float4* re
   }
 }
 
-__global__ void init_view_bbox_kernel(int* vb, int* flags, int B) {      // only when the vertices come in as NDC
+__global__ void init_view_bbox_kernel(int* vb, int* flags, int* nvis, int B) {      // only when the vertices come in as NDC
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B * 4) vb[i] = (i & 1) ? f2ord(-INFINITY) : f2ord(INFINITY);
-  if (i < B) flags[i] = 0;
+  if (i < B) { flags[i] = 0; nvis[i] = 0; }
 }
 
 __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int* __restrict__ faces, int B, int V, int F,
                                   float z_clip, int persp, float sqrt_blur, const float* __restrict__ faces_uvs,
                                   const int* __restrict__ face_map, const DbwMapDesc* __restrict__ map_table,
                                   float4* __restrict__ bbox, float4* __restrict__ rec, float4* __restrict__ rec2,
-                                  float* __restrict__ conv, int* __restrict__ view_flags, int* __restrict__ view_bbox) {
+                                  float* __restrict__ conv, int* __restrict__ view_flags, int* __restrict__ view_bbox,
+                                  int* __restrict__ view_nvis, int* __restrict__ vis_list, float screen_x, float screen_y) {
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   const bool tail = i0 >= B * F;                    // tail lanes redo the last face (idempotent writes) so that the warp
   const int i = tail ? B * F - 1 : i0;              // stays converged for the shuffles below
@@ -278,6 +285,16 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   write_slot(bbox, rec, rec2, conv, s0, r.ntri >= 1 ? r.tri[0] : inval, r.conv[0], r.clipped, f, r.ntri == 2 ? F + f : -1, sqrt_blur, uv01, uv2m);
   write_slot(bbox, rec, rec2, conv, s1, r.ntri == 2 ? r.tri[1] : inval, r.conv[1], r.clipped, f, r.ntri == 2 ? f : -1, sqrt_blur, uv01, uv2m);
   if (r.ntri == 2) atomicOr(&view_flags[b], 1);
+  // the view's list of slots whose (blur-expanded) box reaches the screen at all: the hard single-layer kernel scans this
+  // instead of all 2F slots (32-40 of the 896 environment slots at the DTU cameras)
+  if (!tail) {
+    for (int q = 0; q < r.ntri; ++q) {
+      const size_t sl = q == 0 ? s0 : s1;
+      const float4 bb = bbox[sl];
+      if (bb.x <= screen_x && bb.y >= -screen_x && bb.z <= screen_y && bb.w >= -screen_y)
+        vis_list[(size_t)b * 2 * F + atomicAdd(&view_nvis[b], 1)] = q == 0 ? f : F + f;
+    }
+  }
   // union of the (blur-expanded) face boxes of the view: tiles outside it skip the binning scan altogether
   float ux0 = INFINITY, ux1 = -INFINITY, uy0 = INFINITY, uy1 = -INFINITY;
   for (int q = 0; q < r.ntri; ++q) {
@@ -320,6 +337,7 @@ struct RasterParams {
   float sigma, blur, sqrt_blur, bg0, bg1, bg2;
   int clip_inside, persp, clipb, detach_bary;
   const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags; const int* view_bbox;
+  const int* view_nvis; const int* vis_list;
   const float4* maps4;
   const float* faces_alpha;
   float* out_rgba; int* topk;        // topk may be NULL
@@ -701,6 +719,140 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
       atomicAdd(&P.ep_partials[(cta * (NT / 32) + warp) & P.ep_part_mask], ep_sq * P.ep_inv_count);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ hard single-layer forward
+// K = 1, sigma = 0 (the environment pass, src/model/dbw.py:135-138,219; VizMeshRenderer's 4x supersampled renders,
+// renderer.py:56-60): the nearest face that CONTAINS the pixel -- no halo, no distances, no per-pixel list.  The generic
+// kernel spends two thirds of its instructions on machinery this case does not need (a scan of all 2F slots per tile, TMA
+// staging, the shared-memory fragment lists); here a tile tests only the view's visible slots (face_setup's vis_list), keeps
+// the best fragment in registers and derives its texture coordinates once, after the walk.  Results (image, records, ids) are
+// identical to the generic kernel's: same edge functions, same (depth, slot) order.
+#define HARD_NT 256
+#define HARD_CAP 64
+__global__ void __launch_bounds__(HARD_NT, 5) raster_hard_forward_kernel(const RasterParams P) {
+  __shared__ float4 s_bbox[HARD_CAP];
+  __shared__ float4 s_rec[HARD_CAP * 4];
+  __shared__ int s_slot[HARD_CAP];
+  __shared__ int s_count;
+  __shared__ float s_ndc[32];
+  extern __shared__ float4 s_dyn[];            // the map table
+  int4* const s_desc = reinterpret_cast<int4*>(s_dyn);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int view = blockIdx.x;
+  const int tile_y = centre_out(blockIdx.z, gridDim.z);
+  const int tx0 = blockIdx.y * 16, ty0 = tile_y * 16;
+  const int xi = tx0 + (warp & 1) * 8 + (lane & 7);
+  const int yi = ty0 + (warp >> 1) * 4 + (lane >> 3);
+  int row_lo = 0, row_hi = P.H;
+  if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
+  if (ty0 >= row_hi || ty0 + 16 <= row_lo) return;
+  const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
+  if (tid < 16) s_ndc[tid] = pix_to_ndc(P.W - 1 - min(tx0 + tid, P.W - 1), P.W, P.H);
+  else if (tid < 32) s_ndc[tid] = pix_to_ndc(P.H - 1 - min(ty0 + tid - 16, P.H - 1), P.H, P.W);
+  if (tid == 0) s_count = 0;
+  const int nvis = __ldg(P.view_nvis + view);
+  const size_t slot_base = (size_t)view * 2 * P.F;
+  const int* vis = P.vis_list + slot_base;
+  for (int m = tid; m < P.M; m += HARD_NT) { const DbwMapDesc d = P.map_table[m]; s_desc[m] = make_int4(d.offset / 3, d.height, d.width, 0); }
+  __syncthreads();
+  const f2 p = {s_ndc[xi - tx0], s_ndc[16 + yi - ty0]};
+  const int tx1 = min(tx0 + 16, P.W) - 1, ty1 = min(ty0 + 16, P.H) - 1;
+  const float t_xmin = s_ndc[tx1 - tx0], t_xmax = s_ndc[0], t_ymin = s_ndc[16 + ty1 - ty0], t_ymax = s_ndc[16];
+  // the nearest containing fragment of this pixel
+  unsigned best_pz = 0xffffffffu; int best_slot = 0x7fffffff, best_j = -1;
+  f3 best_bc = {0.f, 0.f, 0.f};
+  for (int base = 0; base < nvis; base += HARD_NT) {
+    // ---- which visible slots touch the tile?  (box overlap, then no edge line with the whole tile on its outer side)
+    const int i = base + tid;
+    bool hit = false; int slot = 0; float4 bb = make_float4(0, 0, 0, 0);
+    if (i < nvis) {
+      slot = __ldg(vis + i);
+      bb = __ldg(&P.bbox[slot_base + slot]);
+      hit = !(bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin);
+      if (hit) {
+        const float4 r0 = __ldg(&P.rec[(slot_base + slot) * 4]);
+        const float2 r1 = __ldg(reinterpret_cast<const float2*>(&P.rec[(slot_base + slot) * 4 + 1]));
+        hit = tri_overlaps_rect({r0.x, r0.y}, {r0.z, r0.w}, {r1.x, r1.y}, t_xmin, t_xmax, t_ymin, t_ymax);
+      }
+    }
+    // lists of at most HARD_CAP entries per round: ballots in warp order, the overflow is taken in further rounds
+    bool pending = hit;
+    while (__syncthreads_or(pending)) {
+      const unsigned m = __ballot_sync(0xffffffffu, pending);
+      int wbase = 0;
+      if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      const int pos = wbase + __popc(m & ((1u << lane) - 1u));
+      if (pending && pos < HARD_CAP) {
+        s_slot[pos] = slot; s_bbox[pos] = bb;
+        const float4* r = &P.rec[(slot_base + slot) * 4];
+        s_rec[pos * 4] = __ldg(r); s_rec[pos * 4 + 1] = __ldg(r + 1); s_rec[pos * 4 + 2] = __ldg(r + 2); s_rec[pos * 4 + 3] = __ldg(r + 3);
+        pending = false;
+      }
+      __syncthreads();
+      const int cnt = min(s_count, HARD_CAP);
+      if (live) {
+        for (int j = 0; j < cnt; ++j) {
+          const float4 b4 = s_bbox[j];
+          if (p.x > b4.y || p.x < b4.x || p.y > b4.w || p.y < b4.z) continue;
+          const TriGeom t = unpack_tri(s_rec[j * 4], s_rec[j * 4 + 1], s_rec[j * 4 + 2], s_rec[j * 4 + 3]);
+          const Edges ed = eval_edges(p, t);
+          if (!ed.inside) continue;
+          const Bary b = bary_from_edges(ed, t, P.persp, P.clipb);
+          if (b.pz < 0.f) continue;
+          const unsigned pzb = __float_as_uint(b.pz + 0.f);
+          const int sl = s_slot[j];
+          if (pzb < best_pz || (pzb == best_pz && sl < best_slot)) { best_pz = pzb; best_slot = sl; best_bc = b.bc; best_j = j; }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      // (the next round's atomics come after the barrier at the top of the loop)
+    }
+  }
+  if (!live) return;
+  const size_t plane = (size_t)P.H * P.W;
+  const size_t pix = (size_t)yi * P.W + xi;
+  float* o = P.out_rgba + (size_t)view * 4 * plane + pix;
+  if (best_j < 0) {
+    o[0] = P.bg0; o[plane] = P.bg1; o[2 * plane] = P.bg2; o[3 * plane] = 0.f;
+    if (P.nfrag) P.nfrag[(size_t)view * plane + pix] = 0;
+    if (P.topk) P.topk[(size_t)view * plane + pix] = -1;
+    return;
+  }
+  // texture coordinates of the winner (its record is read back from global memory: the tile list may have been recycled)
+  const size_t gs = slot_base + best_slot;
+  f3 bu = best_bc;
+  if (__float_as_int(__ldg(&P.rec[gs * 4 + 2]).w) & 1) {
+    const float* cv = P.conv + gs * 9;
+    bu.x = best_bc.x * cv[0] + best_bc.y * cv[3] + best_bc.z * cv[6];
+    bu.y = best_bc.x * cv[1] + best_bc.y * cv[4] + best_bc.z * cv[7];
+    bu.z = best_bc.x * cv[2] + best_bc.y * cv[5] + best_bc.z * cv[8];
+  }
+  const float4 q0 = __ldg(&P.rec2[gs * 2]), q1 = __ldg(&P.rec2[gs * 2 + 1]);
+  const float u = bu.x * q0.x + bu.y * q0.z + bu.z * q1.x;
+  const float v = bu.x * q0.y + bu.y * q0.w + bu.z * q1.y;
+  const int map_id = __float_as_int(q1.z);
+  Texel4 tx;
+  fetch_color(P, u, v, s_desc[map_id], tx);
+  const int face = best_slot >= P.F ? best_slot - P.F : best_slot;
+  float a = 1.f;                                     // inside a face of a hard pass: opacity 1 (x the face's entry)
+  if (P.faces_alpha) a *= __ldg(&P.faces_alpha[alpha_index(P, view, face)]);
+  if (P.face_shade) {
+    const float* m = P.face_shade + ((size_t)view * P.F + face) * 3;
+    tx.color.x *= __ldg(m); tx.color.y *= __ldg(m + 1); tx.color.z *= __ldg(m + 2);
+  }
+  if (P.frag) {
+    const size_t fi = (size_t)view * plane + pix;
+    P.frag[fi] = make_float4(__int_as_float(best_slot | (map_id << DBW_FRAG_MAP_SHIFT)), u, v, -1.f);
+    P.frag_rgb[fi] = make_float4(tx.color.x, tx.color.y, tx.color.z, 0.f);
+    P.nfrag[fi] = 1;
+  }
+  if (P.topk) P.topk[(size_t)view * plane + pix] = best_slot;
+  const float occ = 1.f - a;
+  o[0] = a * tx.color.x + occ * P.bg0; o[plane] = a * tx.color.y + occ * P.bg1; o[2 * plane] = a * tx.color.z + occ * P.bg2;
+  o[3 * plane] = a;
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -1275,6 +1427,7 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   P.sigma = s.sigma; P.blur = s.blur_radius; P.sqrt_blur = sqrtf(s.blur_radius); P.bg0 = s.background[0]; P.bg1 = s.background[1]; P.bg2 = s.background[2];
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
+  P.view_nvis = w.view_nvis; P.vis_list = w.vis_list;
   P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
   P.frag = s.save_fragment_state ? w.frag : nullptr; P.nfrag = s.save_fragment_state ? w.nfrag : nullptr;
   P.frag_rgb = s.save_fragment_state ? w.frag_rgb : nullptr;
@@ -1349,16 +1502,18 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
   if (!s->verts_are_ndc) {
     const int n_thr = B * (V > 4 ? V : 4);          // the kernel also resets the per-view bbox / flags (4 ints per view)
     project_verts_kernel<<<(n_thr + 255) / 256, 256, 0, st>>>(verts, R, T, s->fx, s->fy, s->px, s->py, s->proj_eps, B, V, w.verts_ndc,
-                                                              w.view_bbox, w.view_flags);
+                                                              w.view_bbox, w.view_flags, w.view_nvis);
     LAUNCH_CK("project_verts_kernel");
     verts_ndc = w.verts_ndc;
   } else {
-    init_view_bbox_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(w.view_bbox, w.view_flags, B);
+    init_view_bbox_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(w.view_bbox, w.view_flags, w.view_nvis, B);
     LAUNCH_CK("init_view_bbox_kernel");
   }
   face_setup_kernel<<<(B * F + 127) / 128, 128, 0, st>>>(verts_ndc, faces, B, V, F, s->z_clip, s->perspective_correct,
                                                          sqrtf(s->blur_radius), faces_uvs, face_map, map_table, w.bbox, w.rec,
-                                                         w.rec2, w.conv, w.view_flags, w.view_bbox);
+                                                         w.rec2, w.conv, w.view_flags, w.view_bbox, w.view_nvis, w.vis_list,
+                                                         s->width > s->height ? (float)s->width / s->height : 1.f,
+                                                         s->height > s->width ? (float)s->height / s->width : 1.f);
   LAUNCH_CK("face_setup_kernel");
   if (!s->maps_are_texels4) {
     const int n_texels = s->n_map_floats / 3;
@@ -1378,8 +1533,15 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
   const int K = s->faces_per_pixel;
   {
     ScopedTimer timer(0, K, st);
-    const cudaError_t e = K <= 4 ? launch_forward<DBW_FWD_NT_SMALLK>(P, st) : launch_forward<DBW_FWD_NT>(P, st);
-    if (e != cudaSuccess) return fail("raster_forward_kernel attribute", e);
+    // a hard single-layer render without distances has its own kernel (DBW_NO_HARD_KERNEL=1 in the environment: generic one)
+    static const bool no_hard = getenv("DBW_NO_HARD_KERNEL") != nullptr;
+    if (K == 1 && s->sigma == 0.f && s->blur_radius == 0.f && !out_dists && !ep && !no_hard && !g_no_hard_kernel) {
+      const dim3 grid(P.B, (P.W + 15) / 16, (P.H + 15) / 16);
+      raster_hard_forward_kernel<<<grid, HARD_NT, (size_t)P.M * sizeof(int4), st>>>(P);
+    } else {
+      const cudaError_t e = K <= 4 ? launch_forward<DBW_FWD_NT_SMALLK>(P, st) : launch_forward<DBW_FWD_NT>(P, st);
+      if (e != cudaSuccess) return fail("raster_forward_kernel attribute", e);
+    }
   }
   LAUNCH_CK("raster_forward_kernel");
   return 0;

@@ -75,6 +75,8 @@ typedef struct DbwRenderSettings {
 typedef struct DbwMapDesc { int32_t offset, height, width, reserved; } DbwMapDesc;
 
 int dbw_abi_version(void);
+/* Test hook: 1 = hard single-layer renders (K = 1, sigma = 0) go through the generic raster kernel instead of their dedicated one. */
+void dbw_debug_generic_kernel_only(int on);
 /* sizeof(DbwRenderSettings) as compiled into the library: lets a binding verify its mirror of the struct. */
 size_t dbw_sizeof_settings(void);
 const char* dbw_last_error(void);

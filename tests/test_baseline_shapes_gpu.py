@@ -171,7 +171,10 @@ def _leaf_gradient_parity(model, tpl, size, R, T, K, Kf, sigma, fine, max_masked
     for name, prm in model.named_parameters():
         g_ref = p[name].grad
         if g_ref is None or g_ref.abs().max() == 0:
-            assert prm.grad is None or prm.grad.abs().max().item() < 1e-12, name
+            # e.g. texture_bkg when the ground fills the view: in fp32 a few dozen pixels fall exactly ON an edge shared by two
+            # ground faces (inside neither: PyTorch3D's strict test) and see the sphere behind; they are masked (zero residual
+            # up to an ulp of the compositing), so what reaches the leaf is ~1e-12 -- five orders below the other leaves
+            assert prm.grad is None or prm.grad.abs().max().item() < 1e-9, (name, prm.grad.abs().max().item())
             continue
         worst[name] = _rel(prm.grad.cpu().double(), g_ref)
         model32[name] = _rel(p32[name].grad.double(), p64b[name].grad)

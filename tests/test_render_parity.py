@@ -265,3 +265,29 @@ def test_render_edges_matches_oracle():
     img = torch.rand(2, 3, 24, 32, device=dev)
     drawn = rend.draw_edges(img, scene.extend(2), R.to(dev), T.to(dev), colors=(1, 0, 0), linewidth=1)
     assert drawn.shape == img.shape and torch.isfinite(drawn).all() and (drawn - img).abs().max() > 0.1
+
+
+@pytest.mark.parametrize('size,dist', [((64, 64), 2.75), ((400, 400), 2.75), ((72, 96), 0.45)])
+def test_hard_single_layer_kernel_equals_generic_kernel(size, dist):
+    """K = 1, sigma = 0 renders have a dedicated kernel (visible-slot lists, register-resident best fragment): image, ids and
+    the backward's gradients must equal the generic kernel's bit for bit (same edge functions, same (depth, slot) order)"""
+    from dbw_b200 import _lib
+    dev = _dev()
+    tpl, p, R, T, K = _setup(n_blocks=3, n_views=3, dist=dist)
+    if dist < 1:
+        K = K.clone(); K[0, 0] = K[1, 1] = 1.2
+    scene = D.join_scenes([tpl.build_env(p), tpl.build_blocks(p)[0]])
+    outs = []
+    for generic in (1, 0):
+        _lib.lib().dbw_debug_generic_kernel_only(generic)
+        try:
+            sc = scene_to_device(scene, dev, requires_grad=True)
+            out, ids = render_product(sc, R.to(dev), T.to(dev), K, size, 0.0, 1, z_clip=0.001 if dist > 1 else 0.05, return_ids=True)
+            (out * torch.linspace(0.5, 1.5, out.numel(), device=dev).view_as(out)).sum().backward()
+            outs.append((out.detach().clone(), ids.clone(), sc['verts'].grad.clone(), sc['maps'].grad.clone()))
+        finally:
+            _lib.lib().dbw_debug_generic_kernel_only(0)
+    (a, ia, gva, gma), (b, ib, gvb, gmb) = outs
+    assert torch.equal(ia, ib), f'{(ia != ib).float().mean().item() * 100:.4f}% of the ids differ'
+    assert torch.equal(a, b)
+    assert (gva - gvb).norm() <= 1e-5 * gva.norm() and (gma - gmb).norm() <= 1e-5 * gma.norm()      # atomics: order only
