@@ -1058,6 +1058,11 @@ __device__ __forceinline__ void warp_agg_add_edge(float* __restrict__ g_tri, int
 // -> opacity and distance -> vertex gradients.  Loops are warp-uniform (trip count = warp max) so that the aggregation
 // helpers run converged.
 #define DBW_ALPHA_SMEM_MAX 512      // opacity entries per view that a CTA may pre-accumulate in shared memory
+// 16 x 8 tiles a backward CTA walks (each warp its own patch of every tile, no barrier between, the next patch's first-level
+// loads in flight).  Measured on B200 (cfg 2): a single-layer pass is a chain of DRAM latencies per pixel and gains from 8
+// (0.449 -> 0.410 ms); the K = 10 blocks pass LOSES (0.95 / 1.03 / 1.11 / 1.18 ms at 1 / 2 / 4 / 8: longer CTAs, worse tails)
+#define DBW_BWD_TILES_K1 8
+#define DBW_BWD_TILES_KN 1
 
 // K1: faces_per_pixel == 1 (the environment pass): no record prefetch registers, at most one trip through the loops
 template <bool DETACH, bool ALPHA, bool K1>
@@ -1065,44 +1070,59 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
   extern __shared__ float4 s_dyn[];             // [k][tid] (alpha, cdot, e, occ), [k][tid] record bits, the map table, opacity sums
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int view = blockIdx.x;
-  const int tile_y = centre_out(blockIdx.z, gridDim.z);
+  constexpr int DBW_BWD_TILES = K1 ? DBW_BWD_TILES_K1 : DBW_BWD_TILES_KN;
+  const int strip = centre_out(blockIdx.z, gridDim.z);          // DBW_BWD_TILES vertically adjacent 16 x 8 tiles per CTA
   const int xi = blockIdx.y * TILE_W + (warp & 1) * 8 + (lane & 7);
-  const int yi = tile_y * (DBW_BWD_NT / 16) + (warp >> 1) * 4 + (lane >> 3);
   int row_lo = 0, row_hi = P.H;
   if (P.view_rows) { row_lo = P.view_rows[view * 2]; row_hi = P.view_rows[view * 2 + 1]; }
-  if (tile_y * (DBW_BWD_NT / 16) >= row_hi || (tile_y + 1) * (DBW_BWD_NT / 16) <= row_lo) return;
-  const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
+  constexpr int TH = DBW_BWD_NT / 16;
+  if (strip * DBW_BWD_TILES * TH >= row_hi || (strip + 1) * DBW_BWD_TILES * TH <= row_lo) return;
   const size_t plane = (size_t)P.H * P.W;
-  const size_t pix = live ? (size_t)yi * P.W + xi : 0;
   float4* const s_q = s_dyn + tid;
   int* const s_bits = reinterpret_cast<int*>(s_dyn + (size_t)P.K * DBW_BWD_NT) + tid;
   int4* const s_desc = reinterpret_cast<int4*>(reinterpret_cast<int*>(s_dyn + (size_t)P.K * DBW_BWD_NT) + (size_t)P.K * DBW_BWD_NT);
   float* const s_galpha = reinterpret_cast<float*>(s_desc + P.M);
-  const float4* frag = P.frag + (size_t)view * P.K * plane + pix;
-  const float4* frag_rgb = P.frag_rgb + (size_t)view * P.K * plane + pix;
-  // ---- every first-level load of the pixel is issued before anything waits: gradient, fragment count, the first two records
-  // (speculatively: their addresses are valid workspace whether or not a fragment exists), this thread's map-table entry
-  const float* go = P.grad_rgba + (size_t)view * 4 * plane + pix;
-  float gr = 0.f, gg = 0.f, gb = 0.f, ga = 0.f;
-  int n_px = 0;
-  float4 rec_cur = make_float4(0.f, 0.f, 0.f, 0.f), rgb_cur = rec_cur, rec_nxt = rec_cur, rgb_nxt = rec_cur;
-  if (live) {
-    gr = go[0]; gg = go[plane]; gb = go[2 * plane]; ga = go[3 * plane];
-    n_px = (int)P.nfrag[(size_t)view * plane + pix];
-    rec_cur = frag[0]; rgb_cur = frag_rgb[0];
-    if (!K1 && P.K > 1) { rec_nxt = frag[plane]; rgb_nxt = frag_rgb[plane]; }
-  }
   const float gs = P.grad_scale ? __ldg(P.grad_scale) : 1.f;
   stage_map_table(P, s_desc, tid, DBW_BWD_NT);
   const bool want_alpha = ALPHA && P.g_faces_alpha != nullptr;
   const bool alpha_in_smem = want_alpha && P.n_alpha <= DBW_ALPHA_SMEM_MAX;       // few opacity entries: hot addresses
   if (alpha_in_smem) for (int i = tid; i < P.n_alpha; i += DBW_BWD_NT) s_galpha[i] = 0.f;
-  __syncthreads();
-  gr *= gs; gg *= gs; gb *= gs; ga *= gs;
-  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
-  const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
+  const bool want_dist = P.sigma > 0.f && P.g_tri != nullptr;
   const size_t slot_base = (size_t)view * 2 * P.F;
-  if (!any_grad) n_px = 0;
+  __syncthreads();
+
+  // Every warp walks ITS 8x4 patch of the strip's tiles on its own: no barrier between tiles, and the first-level loads of
+  // the next patch -- gradient pixel, fragment count, first record pair -- are issued before the current patch is processed,
+  // so that their DRAM latency is covered by work instead of by the other (few) resident warps.
+  struct First { float g0, g1, g2, g3; int n; float4 rec, rgb; };
+  auto load_first = [&](int t, First& f) {
+    f.g0 = f.g1 = f.g2 = f.g3 = 0.f; f.n = 0; f.rec = make_float4(0.f, 0.f, 0.f, 0.f); f.rgb = f.rec;
+    const int y = (strip * DBW_BWD_TILES + t) * TH + (warp >> 1) * 4 + (lane >> 3);
+    if (t < DBW_BWD_TILES && xi < P.W && y < P.H && y >= row_lo && y < row_hi) {
+      const size_t px = (size_t)y * P.W + xi;
+      const float* go = P.grad_rgba + (size_t)view * 4 * plane + px;
+      f.g0 = go[0]; f.g1 = go[plane]; f.g2 = go[2 * plane]; f.g3 = go[3 * plane];
+      f.n = (int)P.nfrag[(size_t)view * plane + px];
+      f.rec = P.frag[(size_t)view * P.K * plane + px];          // speculative: a valid workspace address whether or not a
+      f.rgb = P.frag_rgb[(size_t)view * P.K * plane + px];      // fragment exists
+    }
+  };
+  First first_next;
+  load_first(0, first_next);
+  for (int t = 0; t < DBW_BWD_TILES; ++t) {
+  const First first = first_next;
+  load_first(t + 1, first_next);
+  const int yi = (strip * DBW_BWD_TILES + t) * TH + (warp >> 1) * 4 + (lane >> 3);
+  const bool live = xi < P.W && yi < P.H && yi >= row_lo && yi < row_hi;
+  const size_t pix = live ? (size_t)yi * P.W + xi : 0;
+  const float4* frag = P.frag + (size_t)view * P.K * plane + pix;
+  const float4* frag_rgb = P.frag_rgb + (size_t)view * P.K * plane + pix;
+  const float gr = first.g0 * gs, gg = first.g1 * gs, gb = first.g2 * gs, ga = first.g3 * gs;
+  const bool any_grad = live && ((gr != 0.f) || (gg != 0.f) || (gb != 0.f) || (ga != 0.f));
+  const int n_px = any_grad ? first.n : 0;
+  float4 rec_cur = first.rec, rgb_cur = first.rgb, rec_nxt = make_float4(0.f, 0.f, 0.f, 0.f), rgb_nxt = rec_nxt;
+  if (!K1 && n_px > 1) { rec_nxt = frag[plane]; rgb_nxt = frag_rgb[plane]; }
+  const f2 p = {pix_to_ndc(P.W - 1 - xi, P.W, P.H), pix_to_ndc(P.H - 1 - yi, P.H, P.W)};
 
   // fragments are walked front to back until every lane of the warp has run out (warp-uniform trip count); the records of
   // layers k+1 and k+2 are in flight while layer k is processed
@@ -1199,7 +1219,6 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
 
   // pass 2: suffix recurrence on the stored per-fragment scalars -- no division (alpha may be exactly 1)
   float Tacc = P.bg0 * gr + P.bg1 * gg + P.bg2 * gb - ga;
-  const bool want_dist = P.sigma > 0.f && P.g_tri != nullptr;
   if (want_alpha || want_dist) {
     // the edge geometry of a halo fragment (2 vertices + 1 / |edge|^2, from the face record) is loaded one layer ahead
     struct EdgeGeom { float4 r0; float2 r1; float4 r3; };
@@ -1252,6 +1271,7 @@ __global__ void __launch_bounds__(DBW_BWD_NT, DETACH ? DBW_BWD_DETACH_MINB : DBW
       if (want_dist && __ballot_sync(0xffffffffu, vkey >= 0)) warp_agg_add_edge(P.g_tri + slot_base * 9, vkey, gv4, lane);
     }
   }
+  }   // tiles of the strip
   if (alpha_in_smem) {               // one global atomic per (CTA, opacity entry) instead of one per (warp, layer, entry)
     __syncthreads();
     for (int i = tid; i < P.n_alpha; i += DBW_BWD_NT) {
@@ -1580,7 +1600,8 @@ extern "C" int dbw_render_backward_scaled(const DbwRenderSettings* s, const floa
   P.map_table = map_table;
   P.grad_rgba = grad_rgba; P.grad_scale = grad_scale; P.g_tri = need_geom ? g.g_tri : nullptr; P.g_conv = g.g_conv;
   P.g_faces_alpha = g_faces_alpha; P.g_maps4 = g_maps ? (s->maps_are_texels4 ? (float4*)g_maps : g.g_maps4) : nullptr;
-  dim3 grid(B, (s->width + TILE_W - 1) / TILE_W, (s->height + DBW_BWD_NT / 16 - 1) / (DBW_BWD_NT / 16));       // see centre_out()
+  const int strip_rows = (s->faces_per_pixel == 1 ? DBW_BWD_TILES_K1 : DBW_BWD_TILES_KN) * (DBW_BWD_NT / 16);
+  dim3 grid(B, (s->width + TILE_W - 1) / TILE_W, (s->height + strip_rows - 1) / strip_rows);       // see centre_out()
   const size_t smem = frag_smem_bytes(s->faces_per_pixel, DBW_BWD_NT, s->n_maps, P.n_alpha);
   {
     auto launch = [&](auto kern) -> cudaError_t {
