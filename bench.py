@@ -386,7 +386,8 @@ def cpu_threads():
 
 def cpu_baseline(workload, n_views=None):
     w = WORKLOADS[workload]
-    n_views = n_views or max(1, int(16 * 160000 / (w['height'] * w['width'])))
+    # about 10-30 s of host work: 16 views of the DTU shape, scaled by pixels and faces
+    n_views = n_views or max(1, int(16 * 160000 / (w['height'] * w['width']) * min(1.0, 10 / w['n_blocks'])))
     views = sample_views(w['n_views'], n_views)
     torch.set_num_threads(cpu_threads())
     oracle_step(workload, views[:1])                  # warm-up (page in the library, thread pools)

@@ -39,6 +39,12 @@ class DbwLossEpilogue(ctypes.Structure):
                 ('loss_partials', ctypes.c_void_p), ('n_partials', ctypes.c_int32), ('inv_count', ctypes.c_float)]
 
 
+class DbwTexJob(ctypes.Structure):
+    _fields_ = [('textures', ctypes.c_void_p), ('atlas', ctypes.c_void_p), ('g_textures', ctypes.c_void_p),
+                ('n_maps', ctypes.c_int32), ('txt_size', ctypes.c_int32), ('p_left', ctypes.c_int32), ('p_right', ctypes.c_int32),
+                ('decimate', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
 class DbwMapDesc(ctypes.Structure):
     _fields_ = [('offset', ctypes.c_int32), ('height', ctypes.c_int32), ('width', ctypes.c_int32),
                 ('reserved', ctypes.c_int32)]
@@ -49,6 +55,7 @@ EXPORTS = ['dbw_abi_version', 'dbw_debug_generic_kernel_only', 'dbw_sizeof_setti
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
            'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward',
+           'dbw_texture_prep_forward_multi', 'dbw_texture_prep_backward_multi',
            'dbw_comm_create', 'dbw_comm_buffer', 'dbw_comm_ipc_handle', 'dbw_comm_connect', 'dbw_comm_all_reduce', 'dbw_comm_error', 'dbw_comm_destroy']
 
 _lib = None
@@ -93,6 +100,8 @@ def lib():
         L.dbw_comm_destroy.argtypes = [vp]
         L.dbw_debug_generic_kernel_only.restype = None
         L.dbw_debug_generic_kernel_only.argtypes = [ctypes.c_int]
+        L.dbw_texture_prep_forward_multi.argtypes = [ctypes.POINTER(DbwTexJob), ctypes.c_int32, vp]
+        L.dbw_texture_prep_backward_multi.argtypes = [ctypes.POINTER(DbwTexJob), ctypes.c_int32, vp]
         L.dbw_timing_enable.restype = None
         L.dbw_timing_reset.restype = None
         L.dbw_timing_read.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)]

@@ -86,9 +86,13 @@ extern "C" void dbw_timing_reset(void) {
   g_timed.clear();
 }
 
+#ifndef DBW_CBIN
+#define DBW_CBIN 64            // coarse bin edge in pixels (a multiple of every raster tile's width and height)
+#endif
 struct Workspace {
   float* verts_ndc; float4* bbox; float4* rec; float4* rec2; float* conv; int* view_flags; int* view_bbox; float4* maps4;
   int* view_nvis; int* vis_list;
+  int* cbin_count; int* cbin_list; int cbin_nx, cbin_ny;       // coarse bins (DBW_CBIN x DBW_CBIN pixels): slot lists per (view, bin)
   float4* frag; float4* frag_rgb; unsigned char* nfrag; size_t total;
 };
 static Workspace carve(const DbwRenderSettings& s, void* base) {
@@ -103,6 +107,12 @@ static Workspace carve(const DbwRenderSettings& s, void* base) {
   w.view_bbox = (int*)(p + off);   off += align_up(B * 4 * sizeof(int));
   w.view_nvis = (int*)(p + off);   off += align_up(B * sizeof(int));
   w.vis_list = (int*)(p + off);    off += align_up(B * S * sizeof(int));
+  // coarse bins: every list can hold all 2F slots (worst case), so they are only used while that stays below 1 GB
+  w.cbin_nx = (s.width + DBW_CBIN - 1) / DBW_CBIN; w.cbin_ny = (s.height + DBW_CBIN - 1) / DBW_CBIN;
+  const size_t nb = (size_t)w.cbin_nx * w.cbin_ny;
+  const bool use_bins = B * nb * S * sizeof(int) <= ((size_t)1 << 30) && nb > 1;
+  w.cbin_count = use_bins ? (int*)(p + off) : nullptr;  off += use_bins ? align_up(B * nb * sizeof(int)) : 0;
+  w.cbin_list = use_bins ? (int*)(p + off) : nullptr;   off += use_bins ? align_up(B * nb * S * sizeof(int)) : 0;
   w.maps4 = (float4*)(p + off);    off += s.maps_are_texels4 ? 0 : align_up((size_t)(s.n_map_floats / 3) * sizeof(float4));
   const size_t npx = B * (size_t)s.height * s.width;
   w.frag = (float4*)(p + off);     off += s.save_fragment_state ? align_up(npx * (size_t)s.faces_per_pixel * sizeof(float4)) : 0;
@@ -326,6 +336,39 @@ __global__ void face_setup_kernel(const float* __restrict__ verts_ndc, const int
   }
 }
 
+// ------------------------------------------------------------------------------------------------ coarse binning
+// One CTA per (view, 64 x 64 pixel bin): the slots whose blur-expanded box reaches the bin, compacted into the bin's list.
+// A raster tile then scans its bin's list (tens of slots) instead of the view's 2F (800 - 8000): at the stress shape the
+// per-tile scan of all 8000 slots was half of the forward's instructions.
+__global__ void coarse_bin_kernel(const float4* __restrict__ bbox, const int* __restrict__ view_flags, int F, int H, int W,
+                                  int nbx, int nby, int* __restrict__ cbin_count, int* __restrict__ cbin_list) {
+  __shared__ int s_n;
+  const int view = blockIdx.x, bin = blockIdx.y, bx = bin % nbx, by = bin / nbx;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  const int x0 = bx * DBW_CBIN, x1 = min(x0 + DBW_CBIN, W) - 1, y0 = by * DBW_CBIN, y1 = min(y0 + DBW_CBIN, H) - 1;
+  // NDC extents of the bin's pixel centres (+X is left, +Y is up: the last column / row has the smallest coordinate)
+  const float xmin = pix_to_ndc(W - 1 - x1, W, H), xmax = pix_to_ndc(W - 1 - x0, W, H);
+  const float ymin = pix_to_ndc(H - 1 - y1, H, W), ymax = pix_to_ndc(H - 1 - y0, H, W);
+  const int nslots = (view_flags[view] & 1) ? 2 * F : F;
+  const float4* bb = bbox + (size_t)view * 2 * F;
+  int* list = cbin_list + ((size_t)view * gridDim.y + bin) * 2 * F;
+  for (int base = 0; base < nslots; base += blockDim.x) {
+    const int sl = base + tid;
+    bool hit = false;
+    if (sl < nslots) { const float4 b = __ldg(&bb[sl]); hit = !(b.x > xmax || b.y < xmin || b.z > ymax || b.w < ymin); }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m == 0u) continue;
+    int wbase = 0;
+    if (lane == 0) wbase = atomicAdd(&s_n, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (hit) list[wbase + __popc(m & ((1u << lane) - 1u))] = sl;
+  }
+  __syncthreads();
+  if (tid == 0) cbin_count[(size_t)view * gridDim.y + bin] = s_n;
+}
+
 // ------------------------------------------------------------------------------------------------ raster + shade + blend, forward
 struct RasterParams {
   int B, H, W, K, V, F, M;
@@ -338,6 +381,7 @@ struct RasterParams {
   int clip_inside, persp, clipb, detach_bary;
   const float4* bbox; const float4* rec; const float4* rec2; const float* conv; const int* view_flags; const int* view_bbox;
   const int* view_nvis; const int* vis_list;
+  const int* cbin_count; const int* cbin_list; int cbin_nx, cbin_ny;
   const float4* maps4;
   const float* faces_alpha;
   float* out_rgba; int* topk;        // topk may be NULL
@@ -511,7 +555,14 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   float* const lV = reinterpret_cast<float*>(s_dyn + (size_t)K * NT) + tid;
   int n = 0;
 
-  const int nslots = tile_empty ? 0 : ((vflags & 1) ? 2 * P.F : P.F);
+  // the slots this tile scans: its coarse bin's list when there is one, else every slot of the view
+  const int* clist = nullptr;
+  int nslots = tile_empty ? 0 : ((vflags & 1) ? 2 * P.F : P.F);
+  if (P.cbin_list && !tile_empty) {
+    const size_t b = (size_t)view * P.cbin_nx * P.cbin_ny + (size_t)(ty0 / DBW_CBIN) * P.cbin_nx + tx0 / DBW_CBIN;
+    clist = P.cbin_list + b * 2 * P.F;
+    nslots = __ldg(P.cbin_count + b);
+  }
   const size_t slot_base = (size_t)view * 2 * P.F;
   const float4* bbox = P.bbox + slot_base;
   const float4* rec = P.rec + slot_base * 4;
@@ -567,8 +618,9 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   // slots is tested and compacted with NO block barrier in between (ballot + one shared atomic per warp); hits beyond the
   // list capacity are counted but not stored, and only then the chunked path below (barrier per batch) is taken.
   const float rx0 = t_xmin - P.sqrt_blur, rx1 = t_xmax + P.sqrt_blur, ry0 = t_ymin - P.sqrt_blur, ry1 = t_ymax + P.sqrt_blur;
-  auto scan_hit = [&](int s, float4& bb) -> bool {
+  auto scan_hit = [&](int& s, float4& bb) -> bool {
     if (s >= nslots) return false;
+    if (clist) s = __ldg(clist + s);
     bb = __ldg(&bbox[s]);
     if (bb.x > t_xmax || bb.y < t_xmin || bb.z > t_ymax || bb.w < t_ymin) return false;
     const float4 r0 = __ldg(&rec[(size_t)s * 4]);
@@ -577,15 +629,17 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
   };
   // four batches per trip, their box loads issued together: the scan is a chain of L2 latencies otherwise
   for (int base = 0; base < nslots; base += 4 * NT) {
-    float4 bb[4];
+    float4 bb[4]; int sid[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int sl = base + q * NT + tid;
-      bb[q] = sl < nslots ? __ldg(&bbox[sl]) : make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+      const int i = base + q * NT + tid;
+      sid[q] = i < nslots ? (clist ? __ldg(clist + i) : i) : -1;
     }
 #pragma unroll
+    for (int q = 0; q < 4; ++q) bb[q] = sid[q] >= 0 ? __ldg(&bbox[sid[q]]) : make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int sl = base + q * NT + tid;
+      const int sl = sid[q];
       bool hit = !(bb[q].x > t_xmax || bb[q].y < t_xmin || bb[q].z > t_ymax || bb[q].w < t_ymin);
       if (hit) {
         const float4 r0 = __ldg(&rec[(size_t)sl * 4]);
@@ -615,14 +669,15 @@ __global__ void __launch_bounds__(NT, NT <= 128 ? DBW_FWD_MINB : DBW_FWD_SMALLK_
     constexpr int BS = NT < CAP ? NT : CAP;          // slots scanned per batch: a batch never overflows an empty list
     for (int base = 0; base < nslots; base += BS) {
       float4 bb = make_float4(0, 0, 0, 0);
-      const bool hit = tid < BS && scan_hit(base + tid, bb);
+      int sl = base + tid;
+      const bool hit = tid < BS && scan_hit(sl, bb);
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       int wbase = 0;
       if (lane == 0 && m) wbase = atomicAdd(&s_count, __popc(m));
       wbase = __shfl_sync(0xffffffffu, wbase, 0);
       if (hit) {
         const int pos = wbase + __popc(m & ((1u << lane) - 1u));
-        s_slot[pos] = base + tid; s_bbox[pos] = bb;
+        s_slot[pos] = sl; s_bbox[pos] = bb;
       }
       __syncthreads();
       const int cnt = s_count;
@@ -1448,6 +1503,7 @@ static RasterParams make_params(const DbwRenderSettings& s, const Workspace& w, 
   P.clip_inside = s.clip_inside; P.persp = s.perspective_correct; P.clipb = s.clip_barycentric; P.detach_bary = s.detach_bary;
   P.bbox = w.bbox; P.rec = w.rec; P.rec2 = w.rec2; P.conv = w.conv; P.view_flags = w.view_flags; P.view_bbox = w.view_bbox;
   P.view_nvis = w.view_nvis; P.vis_list = w.vis_list;
+  P.cbin_count = w.cbin_count; P.cbin_list = w.cbin_list; P.cbin_nx = w.cbin_nx; P.cbin_ny = w.cbin_ny;
   P.maps4 = w.maps4; P.faces_alpha = faces_alpha;
   P.frag = s.save_fragment_state ? w.frag : nullptr; P.nfrag = s.save_fragment_state ? w.nfrag : nullptr;
   P.frag_rgb = s.save_fragment_state ? w.frag_rgb : nullptr;
@@ -1555,7 +1611,15 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
     ScopedTimer timer(0, K, st);
     // a hard single-layer render without distances has its own kernel (DBW_NO_HARD_KERNEL=1 in the environment: generic one)
     static const bool no_hard = getenv("DBW_NO_HARD_KERNEL") != nullptr;
-    if (K == 1 && s->sigma == 0.f && s->blur_radius == 0.f && !out_dists && !ep && !no_hard && !g_no_hard_kernel) {
+    const bool hard = K == 1 && s->sigma == 0.f && s->blur_radius == 0.f && !out_dists && !ep && !no_hard && !g_no_hard_kernel;
+    if (!hard && w.cbin_list) {
+      coarse_bin_kernel<<<dim3(B, w.cbin_nx * w.cbin_ny), 256, 0, st>>>(w.bbox, w.view_flags, F, s->height, s->width, w.cbin_nx,
+                                                                        w.cbin_ny, w.cbin_count, w.cbin_list);
+      ++g_launches;
+    } else {
+      P.cbin_list = nullptr; P.cbin_count = nullptr;
+    }
+    if (hard) {
       const dim3 grid(P.B, (P.W + 15) / 16, (P.H + 15) / 16);
       raster_hard_forward_kernel<<<grid, HARD_NT, (size_t)P.M * sizeof(int4), st>>>(P);
     } else {

@@ -159,10 +159,20 @@ extern "C" int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const floa
 // ------------------------------------------------------------------------------------------------ textures
 // one thread per SOURCE texel (m, y, x); decimation cells are f x f (f = 1: none) and never straddle a warp row segment:
 // with f = 8 each run of 8 lanes shares a cell column, rows are combined through shared memory.
-__global__ void texture_prep_forward_kernel(const float* __restrict__ tex, int M, int TS, int p_left, int p_right, int f,
-                                            float4* __restrict__ atlas) {
+// up to DBW_MAX_TEX_JOBS texture stacks per launch (background, ground, blocks: ONE launch each way per step instead of three,
+// and the two environment maps land in one atlas without a concatenation)
+struct TexJobs { DbwTexJob j[DBW_MAX_TEX_JOBS]; int n; int zoff[DBW_MAX_TEX_JOBS + 1]; };
+
+__global__ void texture_prep_forward_kernel(const TexJobs J) {
   // block = (32, 8): 32 texels along x, 8 rows -> with f = 8 a block holds 4 complete cells
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z;
+  int job = 0;
+  while (job + 1 < J.n && (int)blockIdx.z >= J.zoff[job + 1]) ++job;
+  const DbwTexJob& jb = J.j[job];
+  const float* __restrict__ tex = jb.textures;
+  float4* __restrict__ atlas = reinterpret_cast<float4*>(jb.atlas);
+  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate;
+  if ((int)blockIdx.x * 32 >= TS || (int)blockIdx.y * 8 >= TS) return;          // the grid is sized for the largest stack
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z - J.zoff[job];
   __shared__ float s_sum[8][32][3];
   float s[3] = {0.f, 0.f, 0.f};
   const bool ok = x < TS && y < TS;
@@ -196,9 +206,16 @@ __global__ void texture_prep_forward_kernel(const float* __restrict__ tex, int M
   if (x >= TS - p_left) row[x - (TS - p_left)] = val;        // and on the left: the last p_left columns
 }
 
-__global__ void texture_prep_backward_kernel(const float* __restrict__ tex, int M, int TS, int p_left, int p_right, int f,
-                                             const float4* __restrict__ g_atlas, float* __restrict__ g_tex) {
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z;
+__global__ void texture_prep_backward_kernel(const TexJobs J) {
+  int job = 0;
+  while (job + 1 < J.n && (int)blockIdx.z >= J.zoff[job + 1]) ++job;
+  const DbwTexJob& jb = J.j[job];
+  const float* __restrict__ tex = jb.textures;
+  const float4* __restrict__ g_atlas = reinterpret_cast<const float4*>(jb.atlas);
+  float* __restrict__ g_tex = jb.g_textures;
+  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate;
+  if ((int)blockIdx.x * 32 >= TS || (int)blockIdx.y * 8 >= TS) return;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z - J.zoff[job];
   __shared__ float s_sum[8][32][3];
   const bool ok = x < TS && y < TS;
   float g[3] = {0.f, 0.f, 0.f};
@@ -242,23 +259,38 @@ static int check_tex(const char* who, int M, int TS, int p_left, int p_right, in
   return 0;
 }
 
+static int launch_tex(const DbwTexJob* jobs, int n_jobs, bool backward, void* stream) {
+  const char* who = backward ? "dbw_texture_prep_backward" : "dbw_texture_prep_forward";
+  if (!jobs || n_jobs < 1 || n_jobs > DBW_MAX_TEX_JOBS) return dbw_fail_("texture prep: 1 .. DBW_MAX_TEX_JOBS jobs", cudaSuccess);
+  TexJobs J;
+  memset(&J, 0, sizeof(J));
+  J.n = n_jobs;
+  int ts_max = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const DbwTexJob& j = jobs[i];
+    if (!j.textures || !j.atlas || (backward && !j.g_textures)) return dbw_fail_("texture prep: null pointer argument", cudaSuccess);
+    if (check_tex(who, j.n_maps, j.txt_size, j.p_left, j.p_right, j.decimate)) return -1;
+    J.j[i] = j; J.zoff[i + 1] = J.zoff[i] + j.n_maps;
+    ts_max = j.txt_size > ts_max ? j.txt_size : ts_max;
+  }
+  dim3 grid((ts_max + 31) / 32, (ts_max + 7) / 8, J.zoff[n_jobs]), block(32, 8);
+  if (backward) texture_prep_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(J);
+  else texture_prep_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(J);
+  SCENE_LAUNCH_CK(backward ? "texture_prep_backward_kernel" : "texture_prep_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_texture_prep_forward_multi(const DbwTexJob* jobs, int32_t n_jobs, void* stream) { return launch_tex(jobs, n_jobs, false, stream); }
+extern "C" int dbw_texture_prep_backward_multi(const DbwTexJob* jobs, int32_t n_jobs, void* stream) { return launch_tex(jobs, n_jobs, true, stream); }
+
 extern "C" int dbw_texture_prep_forward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
                                         int32_t decimate, float* atlas_out, void* stream) {
-  if (!textures || !atlas_out) return dbw_fail_("dbw_texture_prep_forward: null pointer argument", cudaSuccess);
-  if (check_tex("dbw_texture_prep_forward: bad sizes", n_maps, txt_size, p_left, p_right, decimate)) return -1;
-  dim3 grid((txt_size + 31) / 32, (txt_size + 7) / 8, n_maps), block(32, 8);
-  texture_prep_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(textures, n_maps, txt_size, p_left, p_right, decimate, (float4*)atlas_out);
-  SCENE_LAUNCH_CK("texture_prep_forward_kernel");
-  return 0;
+  DbwTexJob j = {textures, atlas_out, nullptr, n_maps, txt_size, p_left, p_right, decimate, 0};
+  return launch_tex(&j, 1, false, stream);
 }
 
 extern "C" int dbw_texture_prep_backward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
                                          int32_t decimate, const float* g_atlas, float* g_textures, void* stream) {
-  if (!textures || !g_atlas || !g_textures) return dbw_fail_("dbw_texture_prep_backward: null pointer argument", cudaSuccess);
-  if (check_tex("dbw_texture_prep_backward: bad sizes", n_maps, txt_size, p_left, p_right, decimate)) return -1;
-  dim3 grid((txt_size + 31) / 32, (txt_size + 7) / 8, n_maps), block(32, 8);
-  texture_prep_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(textures, n_maps, txt_size, p_left, p_right, decimate,
-                                                                         (const float4*)g_atlas, g_textures);
-  SCENE_LAUNCH_CK("texture_prep_backward_kernel");
-  return 0;
+  DbwTexJob j = {textures, const_cast<float*>(g_atlas), g_textures, n_maps, txt_size, p_left, p_right, decimate, 0};
+  return launch_tex(&j, 1, true, stream);
 }

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
 from .fused_loss import ScenePass, scene_mse
-from .scene_ops import scene_geometry_parts, texture_atlas
+from .scene_ops import scene_geometry_parts, texture_atlas, scene_atlases
 from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
 # accepted keys and defaults of the config sub-dicts (configs/*/*.yml -> model.{mesh,rend_optim,loss}); unknown keys are
@@ -357,13 +357,12 @@ class DifferentiableBlocksWorld(nn.Module):
                                                        st['geom'])
         # environment: constant background sphere + posed ground, two square maps in one atlas
         env_verts = torch.cat([st['bkg_world'], ground_verts])
-        env_atlas = torch.cat([texture_atlas(self.texture_bkg, 0, 0, decim_env).reshape(-1, 4),
-                               texture_atlas(self.texture_ground, 0, 0, decim_env).reshape(-1, 4)])
+        env_atlas, atlas = scene_atlases(self.texture_bkg, self.texture_ground, self.textures, self.txt_padding, decim_env, decim_blocks)
+        env_atlas = env_atlas.reshape(-1, 4)
         side = self.texture_bkg.shape[1]
         env_table = [(0, side, side), (side * side * 3, side, side)]
         # blocks
         fmap = self._opacities(hard_filter, coarse_training)
-        atlas = texture_atlas(self.textures, *self.txt_padding, decim_blocks)
         rows, cols = atlas.shape[1], atlas.shape[2]
         table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
         alpha = None if hard_filter else self._alpha          # one opacity per block: alpha_group = BNF faces share an entry

@@ -6,7 +6,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import DbwSceneGeometry
+from ._lib import DbwSceneGeometry, DbwTexJob
 from .renderer import _c, _stream
 
 
@@ -91,3 +91,43 @@ def texture_atlas(textures, p_left=0, p_right=0, decimate=1):
     """(M,TS,TS,3) logits -> (M, TS, p_left+TS+p_right, 4) float4 texels: sigmoid, optional 8x8 box decimation, circular
     padding along u -- the layout the rasterizer samples directly (render_scene(..., maps_are_texels4=True))."""
     return _TextureAtlasFn.apply(textures, int(p_left), int(p_right), int(decimate))
+
+
+class _SceneAtlasesFn(torch.autograd.Function):
+    """the three texture stacks of a step -- background, ground, blocks (src/model/dbw.py:276-279,291-294,307,331-341) -- to
+    the two float4 atlases the passes sample, in ONE launch each way: (env atlas = background then ground, blocks atlas)"""
+
+    @staticmethod
+    def forward(ctx, tex_bkg, tex_ground, tex_blocks, pad, decim_env, decim_blocks):
+        tb, tg, tk = (t.detach().contiguous().float() for t in (tex_bkg, tex_ground, tex_blocks))
+        se, N, TS = tb.shape[1], tk.shape[0], tk.shape[1]
+        assert tb.shape == tg.shape and tb.shape[0] == 1
+        env = torch.empty(2, se, se, 4, device=tb.device, dtype=torch.float32)
+        blk = torch.empty(N, TS, TS + pad[0] + pad[1], 4, device=tb.device, dtype=torch.float32)
+        jobs = (DbwTexJob * 3)(DbwTexJob(tb.data_ptr(), env[0].data_ptr(), None, 1, se, 0, 0, decim_env, 0),
+                               DbwTexJob(tg.data_ptr(), env[1].data_ptr(), None, 1, se, 0, 0, decim_env, 0),
+                               DbwTexJob(tk.data_ptr(), blk.data_ptr(), None, N, TS, pad[0], pad[1], decim_blocks, 0))
+        _lib.check(_lib.lib().dbw_texture_prep_forward_multi(jobs, 3, _stream()), 'dbw_texture_prep_forward_multi')
+        ctx.save_for_backward(tb, tg, tk)
+        ctx.cfg = (pad, decim_env, decim_blocks)
+        return env, blk
+
+    @staticmethod
+    def backward(ctx, g_env, g_blk):
+        tb, tg, tk = ctx.saved_tensors
+        pad, decim_env, decim_blocks = ctx.cfg
+        se, N, TS = tb.shape[1], tk.shape[0], tk.shape[1]
+        g_env, g_blk = g_env.contiguous().float(), g_blk.contiguous().float()
+        flat = torch.empty(tb.numel() + tg.numel() + tk.numel(), device=tb.device, dtype=torch.float32)
+        gb, gg, gk = flat[:tb.numel()].view_as(tb), flat[tb.numel():tb.numel() + tg.numel()].view_as(tg), flat[tb.numel() + tg.numel():].view_as(tk)
+        jobs = (DbwTexJob * 3)(DbwTexJob(tb.data_ptr(), g_env[0].data_ptr(), gb.data_ptr(), 1, se, 0, 0, decim_env, 0),
+                               DbwTexJob(tg.data_ptr(), g_env[1].data_ptr(), gg.data_ptr(), 1, se, 0, 0, decim_env, 0),
+                               DbwTexJob(tk.data_ptr(), g_blk.data_ptr(), gk.data_ptr(), N, TS, pad[0], pad[1], decim_blocks, 0))
+        _lib.check(_lib.lib().dbw_texture_prep_backward_multi(jobs, 3, _stream()), 'dbw_texture_prep_backward_multi')
+        return gb, gg, gk, None, None, None
+
+
+def scene_atlases(texture_bkg, texture_ground, textures, pad, decim_env=1, decim_blocks=1):
+    """(env atlas (2, S, S, 4): background then ground; blocks atlas (N, TS, p_left + TS + p_right, 4)) from the three texture
+    parameters in one launch (and one for all three gradients)"""
+    return _SceneAtlasesFn.apply(texture_bkg, texture_ground, textures, (int(pad[0]), int(pad[1])), int(decim_env), int(decim_blocks))

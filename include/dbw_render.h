@@ -214,6 +214,17 @@ int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const float* g_verts,
 
 /* textures (M,TS,TS,3) logits -> atlas (M, TS, p_left+TS+p_right) float4 texels: sigmoid, optional `decimate`xdecimate box
  * filter (1 = off, 8 = dbw.py:331-334), circular padding along u (dbw.py:339-341).  Backward: g_atlas -> g_textures. */
+/* One texture stack of a multi-stack texture preparation: (n_maps, txt_size, txt_size, 3) logits -> float4 texel atlas
+ * (n_maps, txt_size, p_left + txt_size + p_right) [forward: `atlas` is written; backward: `atlas` is the atlas GRADIENT that is read
+ * and `g_textures` receives d/d logits]. */
+#define DBW_MAX_TEX_JOBS 4
+typedef struct DbwTexJob {
+  const float* textures; float* atlas; float* g_textures;
+  int32_t n_maps, txt_size, p_left, p_right, decimate, reserved;
+} DbwTexJob;
+/* Several stacks in ONE launch (the step's three: background, ground, blocks; `jobs` is a HOST array of n_jobs <= 4). */
+int dbw_texture_prep_forward_multi(const DbwTexJob* jobs, int32_t n_jobs, void* stream);
+int dbw_texture_prep_backward_multi(const DbwTexJob* jobs, int32_t n_jobs, void* stream);
 int dbw_texture_prep_forward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,
                              int32_t decimate, float* atlas_out, void* stream);
 int dbw_texture_prep_backward(const float* textures, int32_t n_maps, int32_t txt_size, int32_t p_left, int32_t p_right,

@@ -531,3 +531,22 @@ def test_quantitative_and_qualitative_eval(tmp_path):
             '0_rec_syn_nobkg_edged.png', '3_rec.png', 'textures/bkg.png', 'textures/ground.png', 'textures/block_04.png'} <= names
     faces = sum(1 for l in open(tmp_path / 'mesh.obj') if l.startswith('f '))
     assert faces == 128 + 3 * 80                                   # reduced ground + the three opaque blocks
+
+
+@pytest.mark.parametrize('decim', [(1, 1), (8, 8), (8, 1)])
+def test_scene_atlases_one_launch_equals_three(decim):
+    """dbw_texture_prep_*_multi (background + ground + blocks in one launch each way) == the three single-stack calls"""
+    from dbw_b200.scene_ops import texture_atlas, scene_atlases
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(4)
+    tb, tg = (torch.randn(1, 64, 64, 3, generator=g).to(dev).requires_grad_(True) for _ in range(2))
+    tk = torch.randn(3, 32, 32, 3, generator=g).to(dev).requires_grad_(True)
+    env, blk = scene_atlases(tb, tg, tk, (3, 5), decim[0], decim[1])
+    ref_env = torch.stack([texture_atlas(tb, 0, 0, decim[0])[0], texture_atlas(tg, 0, 0, decim[0])[0]])
+    ref_blk = texture_atlas(tk, 3, 5, decim[1])
+    assert torch.equal(env, ref_env) and torch.equal(blk, ref_blk)
+    we, wb = torch.randn_like(env), torch.randn_like(blk)
+    ga = torch.autograd.grad((env * we).sum() + (blk * wb).sum(), [tb, tg, tk])
+    gr = torch.autograd.grad((ref_env * we).sum() + (ref_blk * wb).sum(), [tb, tg, tk])
+    for a, b in zip(ga, gr):
+        assert torch.equal(a, b)
