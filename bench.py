@@ -298,10 +298,14 @@ def run_ours(args):
         step_e2e()
     ms_e2e_local = timed(step_e2e, args.steps)
 
-    t = torch.tensor([ms_local, ms_e2e_local, ms_nocoll_local], device=dev, dtype=torch.float64)
+    comm_err = vp.bucket.peer.error() if vp.bucket.peer is not None else 0        # a barrier of the peer all-reduce timed out?
+    t = torch.tensor([ms_local, ms_e2e_local, ms_nocoll_local, float(comm_err)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e_total, ms_nocoll_total = t.tolist()
+    ms_total, ms_e2e_total, ms_nocoll_total, comm_err = t.tolist()
+    if comm_err:
+        raise RuntimeError(f'the peer-memory all-reduce reported a barrier time-out (code {int(comm_err)}): the timed steps are invalid; '
+                           f're-run with --collective nccl')
 
     if rank == 0:
         ms_per_step = ms_total / args.steps
