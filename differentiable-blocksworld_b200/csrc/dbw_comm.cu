@@ -15,7 +15,7 @@
 // results into my bucket only after barrier A, which I pass only after my scatter has read it; my next scatter writes the
 // peers' inboxes only after barrier B of this epoch, which an owner signals after its reduce has read them.
 // Barriers are epoch-stamped flags stored into the PEERS' arenas with st.release.sys and polled locally with
-// ld.acquire.sys; a poll that exceeds ~2 s sets the arena's error word instead of hanging the GPU.
+// ld.acquire.sys; a poll that exceeds ~30 s sets the arena's error word instead of hanging the GPU.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,7 +69,7 @@ __device__ __forceinline__ float4 ld_peer(const float4* p) {          // peer me
   float4 v; asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory"); return v;
 }
 
-#define SPIN_LIMIT (4000000000ll)        // ~2 s of SM clocks
+#define SPIN_LIMIT (60000000000ll)       // ~30 s of SM clocks: ranks may reach their first exchange seconds apart (start-up skew)
 
 // barrier over the blocks of THIS kernel (all co-resident: COMM_BLOCKS <= SMs)
 __device__ __forceinline__ void grid_barrier(unsigned* ctl, unsigned target) {
@@ -233,7 +233,7 @@ extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void
   return 0;
 }
 
-// 0: fine; 1 / 2: a grid / rank barrier timed out (a peer did not arrive within ~2 s) -- results are then garbage
+// 0: fine; 1 / 2: a grid / rank barrier timed out (a peer did not arrive within ~30 s) -- results are then garbage
 extern "C" int dbw_comm_error(void* comm, int32_t* out) {
   Comm* c = (Comm*)comm;
   if (!c || !out) return dbw_fail_("dbw_comm_error: null argument", cudaSuccess);

@@ -262,7 +262,7 @@ void dbw_timing_reset(void);
  *   dbw_comm_all_reduce  in-place SUM of the bucket's first n_floats over the ranks (n_floats % 4 == 0; buf must be the
  *                        pointer dbw_comm_buffer returned).  Push protocol: slices are pushed to their owners, summed there
  *                        in rank order (bit-identical results everywhere) and pushed back -- only posted stores cross NVLink
- *   dbw_comm_error       0, or which barrier timed out (a peer did not arrive within ~2 s: results are garbage, no hang)
+ *   dbw_comm_error       0, or which barrier timed out (a peer did not arrive within ~30 s: results are garbage, no hang)
  */
 int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out);
 int dbw_comm_buffer(void* comm, float** out);

@@ -291,3 +291,27 @@ def test_hard_single_layer_kernel_equals_generic_kernel(size, dist):
     assert torch.equal(ia, ib), f'{(ia != ib).float().mean().item() * 100:.4f}% of the ids differ'
     assert torch.equal(a, b)
     assert (gva - gvb).norm() <= 1e-5 * gva.norm() and (gma - gmb).norm() <= 1e-5 * gma.norm()      # atomics: order only
+
+
+def test_hard_single_layer_kernel_many_visible_faces():
+    """4000 crowded faces, all on screen: the visible list takes 16 rounds of 256 slots per tile and tile lists overflow
+    their 64 entries (several rounds per batch) -- image and ids still equal the generic kernel's bit for bit"""
+    from dbw_b200 import _lib
+    dev = _dev()
+    tpl = D.SceneTemplate(n_blocks=50, txt_size=16)
+    p = D.init_params(50, 16, seed=7, boxy=True)
+    p['T'] = p['T'] * 0.2
+    R, T, K = D.ring_cameras(2, jitter=0.3, seed=7, dist=1.6)
+    blocks, _ = tpl.build_blocks(p)
+    outs = []
+    for generic in (1, 0):
+        _lib.lib().dbw_debug_generic_kernel_only(generic)
+        try:
+            out, ids = render_product(scene_to_device(blocks, dev), R.to(dev), T.to(dev), K, (96, 128), 0.0, 1, z_clip=0.001, return_ids=True)
+            outs.append((out.clone(), ids.clone()))
+        finally:
+            _lib.lib().dbw_debug_generic_kernel_only(0)
+    assert (outs[0][1] >= 0).float().mean() > 0.3
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][0], outs[1][0])
+    ref = D.render(blocks, R, T, K, (96, 128), sigma=0, faces_per_pixel=1, z_clip=0.001)
+    _check_image(outs[1][0].cpu(), ref, max_bad_frac=3e-4)
