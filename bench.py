@@ -63,12 +63,12 @@ def peaks():
 
 
 def kernel_fingerprint():
-    """sha256 over the kernel sources: ties a committed ncu capture (profiles/ncu_traffic.json) to the build that is benched"""
+    """sha256 over the sources of the raster kernels (dbw_render.cu and the headers it includes): ties a committed ncu capture
+    (profiles/ncu_traffic.json) to the build that is benched"""
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'differentiable-blocksworld_b200', 'csrc')
-    for fn in sorted(os.listdir(d)):
-        if fn.endswith(('.cu', '.cuh')):
-            h.update(open(os.path.join(d, fn), 'rb').read())
+    for fn in ('dbw_render.cu', 'dbw_math.cuh', 'dbw_fraglist.cuh', 'dbw_clip.cuh'):
+        h.update(open(os.path.join(d, fn), 'rb').read())
     return h.hexdigest()[:16]
 
 
