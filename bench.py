@@ -187,15 +187,21 @@ def run_ours(args):
     dev_passes = [{k: v.to(dev) for k, v in p.items()} for p in passes]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
     acc = torch.zeros_like(vp.bucket.flat) if n_pass > 1 else None
+    if n_pass > 1:
+        vp.gather_grads = True          # the passes' gradients are accumulated through the flat bucket
+    # Where the step's gradients are summed over the ranks (parallel.py): inside the backward at the scene tensors (GradSumPoint:
+    # vertices, opacities, decimated texture cells -- one small all-reduce per pass, no leaf all-reduce), else at the leaves
+    # (one all-reduce of the parameter-gradient bucket per step)
+    inside = vp.reduces_inside_backward(dev_passes[0])
 
     def step_eager(collective=True):
         for i, p in enumerate(dev_passes):
-            vp.forward_backward(p, None, already_sharded=True, n_total_views=B, all_reduce=False)
+            vp.forward_backward(p, None, already_sharded=True, n_total_views=B, all_reduce=collective and inside)
             if acc is not None:
                 acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
         if acc is not None:
             vp.bucket.flat.copy_(acc)
-        if collective:
+        if collective and not inside:
             vp.bucket.all_reduce(vp.group)
 
     graphed = piped = None
@@ -203,7 +209,7 @@ def run_ours(args):
     if not args.no_graph:
         # the peer-memory all-reduce is captured inside the graph when the step is a single pass (it then cannot be skipped:
         # a second graph without it serves the "what does the collective add" measurement)
-        in_graph = vp.graph_capturable_collective and n_pass == 1
+        in_graph = vp.graph_capturable_collective and (n_pass == 1 or inside)
         piped = PipelinedGraphedStep(vp, dev_passes[0], B, capture_all_reduce=in_graph)
         graphed = piped.steps[0]
         nocoll = GraphedStep(vp, dev_passes[0], B, capture_all_reduce=False) if (in_graph and world > 1) else graphed
@@ -218,7 +224,7 @@ def run_ours(args):
                 acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
         if acc is not None:
             vp.bucket.flat.copy_(acc)
-        if collective and not g.capture_all_reduce:
+        if collective and not g.capture_all_reduce and not inside:
             vp.bucket.all_reduce(vp.group)
 
     def step_e2e():
@@ -228,7 +234,7 @@ def run_ours(args):
         if piped is None:
             for i, p in enumerate(passes):
                 inp = {k: v.to(dev, non_blocking=True) for k, v in p.items()}
-                losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B, all_reduce=False)
+                losses = vp.forward_backward(inp, None, already_sharded=True, n_total_views=B, all_reduce=inside)
                 if acc is not None:
                     acc.copy_(vp.bucket.flat) if i == 0 else acc.add_(vp.bucket.flat)
                 loss = loss + losses['rgb']
@@ -240,7 +246,7 @@ def run_ours(args):
                 loss = loss + losses['rgb']
         if acc is not None:
             vp.bucket.flat.copy_(acc)
-        if piped is None or not piped.steps[0].capture_all_reduce:
+        if not inside and (piped is None or not piped.steps[0].capture_all_reduce):
             vp.bucket.all_reduce(vp.group)
         return float(loss.item())                                                 # D2H read of the step's result
 
@@ -335,7 +341,11 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'{args.workload}: {w["what"]}; BASELINE {w["baseline"]}; coarse phase (sigma=1e-4, per-block '
                                    f'opacities + noise, 8x decimated textures); the step\'s {B} views are split over the ranks at '
-                                   f'(view, 16-row band) granularity, gradients reduced by one all-reduce ({vp.collective_name})',
+                                   f'(view, 16-row band) granularity, gradients summed over the ranks '
+                                   + ('inside the backward at the scene tensors (vertices, opacities, decimated texture cells: '
+                                      f'{model.grad_sum_floats() * 4 / 1e6:.2f} MB) ' if inside else
+                                      f'at the leaves ({vp.bucket.nbytes / 1e6:.1f} MB bucket) ')
+                                   + f'by one all-reduce ({vp.collective_name})',
                        'views_per_step': B, 'views_per_pass_per_rank': views_per_pass, 'passes_per_step': n_pass,
                        'l2': 'flushed (256 MB memset) between steps, outside the per-step event pairs',
                        'loss': 'rgb (MSE) only; LPIPS excluded (SURVEY 8d)', 'seed': SEED,

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # DBW_RENDER_LIB: explicit path of another build of the same library (kernel experiments); never a fallback
 LIB_PATH = os.environ.get('DBW_RENDER_LIB') or os.path.join(_HERE, 'libdbw_render.so')
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class DbwRenderSettings(ctypes.Structure):
@@ -42,7 +42,7 @@ class DbwLossEpilogue(ctypes.Structure):
 class DbwTexJob(ctypes.Structure):
     _fields_ = [('textures', ctypes.c_void_p), ('atlas', ctypes.c_void_p), ('g_textures', ctypes.c_void_p),
                 ('n_maps', ctypes.c_int32), ('txt_size', ctypes.c_int32), ('p_left', ctypes.c_int32), ('p_right', ctypes.c_int32),
-                ('decimate', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('decimate', ctypes.c_int32), ('stage', ctypes.c_int32)]
 
 
 class DbwMapDesc(ctypes.Structure):
@@ -54,7 +54,8 @@ EXPORTS = ['dbw_abi_version', 'dbw_debug_generic_kernel_only', 'dbw_sizeof_setti
            'dbw_render_forward_loss', 'dbw_render_backward_scaled',
            'dbw_composite_mse', 'dbw_composite_mse_backward', 'dbw_render_forward_host', 'dbw_host_arena_release', 'dbw_launch_count',
            'dbw_timing_enable', 'dbw_timing_read', 'dbw_timing_reset', 'dbw_scene_geometry_forward',
-           'dbw_scene_geometry_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward',
+           'dbw_scene_geometry_backward', 'dbw_scene_geometry_forward_env', 'dbw_scene_geometry_backward_parts',
+           'dbw_opacity_forward', 'dbw_opacity_backward', 'dbw_texture_prep_forward', 'dbw_texture_prep_backward',
            'dbw_texture_prep_forward_multi', 'dbw_texture_prep_backward_multi',
            'dbw_comm_create', 'dbw_comm_buffer', 'dbw_comm_ipc_handle', 'dbw_comm_connect', 'dbw_comm_all_reduce', 'dbw_comm_error', 'dbw_comm_destroy']
 
@@ -89,6 +90,10 @@ def lib():
         L.dbw_host_arena_release.restype = None
         L.dbw_scene_geometry_forward.argtypes = [ctypes.POINTER(DbwSceneGeometry), vp, vp]
         L.dbw_scene_geometry_backward.argtypes = [ctypes.POINTER(DbwSceneGeometry)] + [vp] * 8
+        L.dbw_scene_geometry_forward_env.argtypes = [ctypes.POINTER(DbwSceneGeometry), vp, ctypes.c_int32, vp, vp]
+        L.dbw_scene_geometry_backward_parts.argtypes = [ctypes.POINTER(DbwSceneGeometry)] + [vp] * 9
+        L.dbw_opacity_forward.argtypes = [vp, vp, ctypes.c_float, ctypes.c_float, vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp]
+        L.dbw_opacity_backward.argtypes = [vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, ctypes.c_int32, vp, vp]
         L.dbw_texture_prep_forward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp]
         L.dbw_texture_prep_backward.argtypes = [vp] + [ctypes.c_int32] * 5 + [vp, vp, vp]
         L.dbw_comm_create.argtypes = [ctypes.c_int32, ctypes.c_int32, sz, ctypes.POINTER(vp)]

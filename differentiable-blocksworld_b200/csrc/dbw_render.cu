@@ -1609,9 +1609,8 @@ static int render_forward_impl(const DbwRenderSettings* s, const float* verts, c
   const int K = s->faces_per_pixel;
   {
     ScopedTimer timer(0, K, st);
-    // a hard single-layer render without distances has its own kernel (DBW_NO_HARD_KERNEL=1 in the environment: generic one)
-    static const bool no_hard = getenv("DBW_NO_HARD_KERNEL") != nullptr;
-    const bool hard = K == 1 && s->sigma == 0.f && s->blur_radius == 0.f && !out_dists && !ep && !no_hard && !g_no_hard_kernel;
+    // a hard single-layer render without distances has its own kernel (dbw_debug_generic_kernel_only(1): the generic one)
+    const bool hard = K == 1 && s->sigma == 0.f && s->blur_radius == 0.f && !out_dists && !ep && !g_no_hard_kernel;
     if (!hard && w.cbin_list) {
       coarse_bin_kernel<<<dim3(B, w.cbin_nx * w.cbin_ny), 256, 0, st>>>(w.bbox, w.view_flags, F, s->height, s->width, w.cbin_nx,
                                                                         w.cbin_ny, w.cbin_count, w.cbin_list);

@@ -10,6 +10,7 @@
 //     atlas gradient through padding, decimation and the sigmoid.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/dbw_render.h"
@@ -21,11 +22,15 @@ extern void dbw_count_launch_(void);
 // ------------------------------------------------------------------------------------------------ geometry
 #include "dbw_scene_math.cuh"
 
-// out: (N*Vb + Vg, 3) world-space vertices, blocks first then the ground
-__global__ void scene_geometry_forward_kernel(const GeomParams P, float* __restrict__ out) {
+// out: (N*Vb + Vg, 3) world-space vertices, blocks first then the ground; with env_static (n_static > 0) the layout is
+// (n_static + Vg + N*Vb, 3): the static environment vertices (copied), the ground, then the blocks
+__global__ void scene_geometry_forward_kernel(const GeomParams P, float* __restrict__ out, const float* __restrict__ env_static,
+                                              int n_static) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int nb = P.n_blocks * P.verts_per_block;
+  if (i < n_static * 3) out[i] = env_static[i];
   if (i >= nb + P.n_ground_verts) return;
+  if (n_static > 0) out += (ptrdiff_t)(n_static + (i < nb ? P.n_ground_verts : -nb)) * 3;      // blocks move behind the ground
   const int prim = i < nb ? i / P.verts_per_block : P.n_blocks;
   const int v = i < nb ? i - prim * P.verts_per_block : i - nb;
   float u[3], aux[6], R[9], sc[3] = {1.f, 1.f, 1.f};
@@ -49,7 +54,8 @@ __global__ void scene_geometry_forward_kernel(const GeomParams P, float* __restr
 }
 
 // one CTA (64 threads) per primitive; outputs are WRITTEN (not accumulated)
-__global__ void __launch_bounds__(64) scene_geometry_backward_kernel(const GeomParams P, const float* __restrict__ g_out,
+__global__ void __launch_bounds__(64) scene_geometry_backward_kernel(const GeomParams P, const float* __restrict__ g_blocks,
+                                                                     const float* __restrict__ g_ground,
                                                                      float* __restrict__ g_sq_eps, float* __restrict__ g_S,
                                                                      float* __restrict__ g_R6, float* __restrict__ g_T,
                                                                      float* __restrict__ g_R6g, float* __restrict__ g_Tg) {
@@ -66,8 +72,8 @@ __global__ void __launch_bounds__(64) scene_geometry_backward_kernel(const GeomP
   for (int vv = v; vv < nv; vv += 64) {
     float u[3], aux[6] = {0, 0, 0, 0, 1, 1};
     local_vertex(P, prim, vv, u, aux);
-    const int i = is_block ? prim * P.verts_per_block + vv : P.n_blocks * P.verts_per_block + vv;
-    const float gx = g_out[i * 3], gy = g_out[i * 3 + 1], gz = g_out[i * 3 + 2];
+    const float* g_v = is_block ? g_blocks + (size_t)(prim * P.verts_per_block + vv) * 3 : g_ground + (size_t)vv * 3;
+    const float gx = g_v[0], gy = g_v[1], gz = g_v[2];
     const float* W = P.R_world.m;
     // world transform backward: g_p = S_world * (g @ R_world^T)
     const float gp[3] = {(gx * W[0] + gy * W[1] + gz * W[2]) * P.S_world, (gx * W[3] + gy * W[4] + gz * W[5]) * P.S_world,
@@ -140,19 +146,98 @@ extern "C" int dbw_scene_geometry_forward(const DbwSceneGeometry* g, float* vert
     return dbw_fail_("dbw_scene_geometry_forward: bad sizes", cudaSuccess);
   const int n = g->n_blocks * g->verts_per_block + g->n_ground_verts;
   if (n == 0) return 0;
-  scene_geometry_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_geom(g), verts_out);
+  scene_geometry_forward_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_geom(g), verts_out, nullptr, 0);
   SCENE_LAUNCH_CK("scene_geometry_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_scene_geometry_forward_env(const DbwSceneGeometry* g, const float* env_static_verts, int32_t n_env_static,
+                                              float* verts_out, void* stream) {
+  if (!g || !verts_out || (n_env_static > 0 && !env_static_verts)) return dbw_fail_("dbw_scene_geometry_forward_env: null pointer argument", cudaSuccess);
+  if (g->n_blocks < 0 || g->verts_per_block <= 0 || g->n_ground_verts < 0 || g->verts_per_block > 4096 || n_env_static < 0)
+    return dbw_fail_("dbw_scene_geometry_forward_env: bad sizes", cudaSuccess);
+  const int n = g->n_blocks * g->verts_per_block + g->n_ground_verts;
+  const int threads = n > n_env_static * 3 ? n : n_env_static * 3;
+  if (threads == 0) return 0;
+  scene_geometry_forward_kernel<<<(threads + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_geom(g), verts_out, env_static_verts,
+                                                                                         n_env_static);
+  SCENE_LAUNCH_CK("scene_geometry_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_scene_geometry_backward_parts(const DbwSceneGeometry* g, const float* g_block_verts, const float* g_ground_verts,
+                                                 float* g_sq_eps, float* g_S, float* g_R_6d, float* g_T, float* g_R_6d_ground,
+                                                 float* g_T_ground, void* stream) {
+  if (!g || (g->n_blocks > 0 && !g_block_verts) || (g->n_ground_verts > 0 && !g_ground_verts))
+    return dbw_fail_("dbw_scene_geometry_backward: null pointer argument", cudaSuccess);
+  const int prims = g->n_blocks + (g->n_ground_verts > 0 ? 1 : 0);
+  if (prims == 0) return 0;
+  scene_geometry_backward_kernel<<<prims, 64, 0, (cudaStream_t)stream>>>(make_geom(g), g_block_verts, g_ground_verts, g_sq_eps, g_S,
+                                                                         g_R_6d, g_T, g_R_6d_ground, g_T_ground);
+  SCENE_LAUNCH_CK("scene_geometry_backward_kernel");
   return 0;
 }
 
 extern "C" int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const float* g_verts, float* g_sq_eps, float* g_S,
                                            float* g_R_6d, float* g_T, float* g_R_6d_ground, float* g_T_ground, void* stream) {
   if (!g || !g_verts) return dbw_fail_("dbw_scene_geometry_backward: null pointer argument", cudaSuccess);
-  const int prims = g->n_blocks + (g->n_ground_verts > 0 ? 1 : 0);
-  if (prims == 0) return 0;
-  scene_geometry_backward_kernel<<<prims, 64, 0, (cudaStream_t)stream>>>(make_geom(g), g_verts, g_sq_eps, g_S, g_R_6d, g_T,
-                                                                         g_R_6d_ground, g_T_ground);
-  SCENE_LAUNCH_CK("scene_geometry_backward_kernel");
+  return dbw_scene_geometry_backward_parts(g, g_verts, g_verts + (size_t)g->n_blocks * g->verts_per_block * 3, g_sq_eps, g_S, g_R_6d,
+                                           g_T, g_R_6d_ground, g_T_ground, stream);
+}
+
+// ------------------------------------------------------------------------------------------------ opacities
+// src/model/dbw.py:300-316 with static shapes, one launch: alpha = sigmoid(logit + noise_scale * noise); blocks whose NOISE-FREE
+// opacity is not above keep_threshold are disabled through the face map (-1) and zeroed in alpha_kept.
+__global__ void opacity_forward_kernel(const float* __restrict__ logit, const float* __restrict__ noise, float noise_scale,
+                                       float keep_threshold, const int* __restrict__ face_map_in, int n_blocks, int faces_per_block,
+                                       float* __restrict__ alpha, float* __restrict__ alpha_kept, int* __restrict__ face_map_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks * faces_per_block) return;
+  const int k = i / faces_per_block;
+  const float l = logit[k];
+  const bool keep = keep_threshold < 0.f || 1.f / (1.f + expf(-l)) > keep_threshold;
+  if (face_map_out) face_map_out[i] = keep ? face_map_in[i] : -1;
+  if (i == k * faces_per_block) {
+    const float a = 1.f / (1.f + expf(-(noise ? l + noise_scale * noise[k] : l)));
+    alpha[k] = a;
+    if (alpha_kept) alpha_kept[k] = keep ? a : 0.f;
+  }
+}
+
+__global__ void opacity_backward_kernel(const float* __restrict__ logit, const float* __restrict__ noise, float noise_scale,
+                                        float keep_threshold, const float* __restrict__ g_alpha, const float* __restrict__ g_alpha_kept,
+                                        int n_blocks, float* __restrict__ g_logit) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_blocks) return;
+  const float l = logit[k];
+  const bool keep = keep_threshold < 0.f || 1.f / (1.f + expf(-l)) > keep_threshold;
+  const float a = 1.f / (1.f + expf(-(noise ? l + noise_scale * noise[k] : l)));
+  float g = g_alpha ? g_alpha[k] : 0.f;
+  if (g_alpha_kept && keep) g += g_alpha_kept[k];
+  g_logit[k] = g * a * (1.f - a);
+}
+
+extern "C" int dbw_opacity_forward(const float* alpha_logit, const float* noise, float noise_scale, float keep_threshold,
+                                   const int32_t* face_map_in, int32_t n_blocks, int32_t faces_per_block, float* alpha,
+                                   float* alpha_kept, int32_t* face_map_out, void* stream) {
+  if (!alpha_logit || !alpha || (face_map_out && !face_map_in)) return dbw_fail_("dbw_opacity_forward: null pointer argument", cudaSuccess);
+  if (n_blocks < 0 || faces_per_block <= 0) return dbw_fail_("dbw_opacity_forward: bad sizes", cudaSuccess);
+  if (n_blocks == 0) return 0;
+  const int n = n_blocks * faces_per_block;
+  opacity_forward_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(alpha_logit, noise, noise_scale, keep_threshold, face_map_in,
+                                                                            n_blocks, faces_per_block, alpha, alpha_kept, face_map_out);
+  SCENE_LAUNCH_CK("opacity_forward_kernel");
+  return 0;
+}
+
+extern "C" int dbw_opacity_backward(const float* alpha_logit, const float* noise, float noise_scale, float keep_threshold,
+                                    const float* g_alpha, const float* g_alpha_kept, int32_t n_blocks, float* g_alpha_logit,
+                                    void* stream) {
+  if (!alpha_logit || !g_alpha_logit) return dbw_fail_("dbw_opacity_backward: null pointer argument", cudaSuccess);
+  if (n_blocks <= 0) return n_blocks == 0 ? 0 : dbw_fail_("dbw_opacity_backward: bad sizes", cudaSuccess);
+  opacity_backward_kernel<<<(n_blocks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(alpha_logit, noise, noise_scale, keep_threshold,
+                                                                                    g_alpha, g_alpha_kept, n_blocks, g_alpha_logit);
+  SCENE_LAUNCH_CK("opacity_backward_kernel");
   return 0;
 }
 
@@ -170,18 +255,25 @@ __global__ void texture_prep_forward_kernel(const TexJobs J) {
   const DbwTexJob& jb = J.j[job];
   const float* __restrict__ tex = jb.textures;
   float4* __restrict__ atlas = reinterpret_cast<float4*>(jb.atlas);
-  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate;
+  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate, stage = jb.stage;
   if ((int)blockIdx.x * 32 >= TS || (int)blockIdx.y * 8 >= TS) return;          // the grid is sized for the largest stack
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z - J.zoff[job];
   __shared__ float s_sum[8][32][3];
   float s[3] = {0.f, 0.f, 0.f};
   const bool ok = x < TS && y < TS;
+  const int CS = TS / f;                                                         // cells per side
+  const size_t cell = (((size_t)m * CS + y / f) * CS + x / f) * 3;
   if (ok) {
-    const float* t = tex + (((size_t)m * TS + y) * TS + x) * 3;
+    if (stage == DBW_TEX_STAGE_EXPAND) {                                         // `textures` holds the cell colours
 #pragma unroll
-    for (int c = 0; c < 3; ++c) s[c] = 1.f / (1.f + expf(-t[c]));
+      for (int c = 0; c < 3; ++c) s[c] = tex[cell + c];
+    } else {
+      const float* t = tex + (((size_t)m * TS + y) * TS + x) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s[c] = 1.f / (1.f + expf(-t[c]));
+    }
   }
-  if (f == 8) {
+  if (f == 8 && stage != DBW_TEX_STAGE_EXPAND) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float v = s[c];
@@ -198,6 +290,13 @@ __global__ void texture_prep_forward_kernel(const TexJobs J) {
     }
   }
   if (!ok) return;
+  if (stage == DBW_TEX_STAGE_CELLS) {                                            // `atlas` receives the (n_maps, CS, CS, 3) cell colours
+    if (x % f == 0 && y % f == 0) {
+      float* out = jb.atlas + cell;
+      out[0] = s[0]; out[1] = s[1]; out[2] = s[2];
+    }
+    return;
+  }
   const int Wp = TS + p_left + p_right;
   float4* row = atlas + ((size_t)m * TS + y) * Wp;
   const float4 val = make_float4(s[0], s[1], s[2], 0.f);
@@ -213,12 +312,28 @@ __global__ void texture_prep_backward_kernel(const TexJobs J) {
   const float* __restrict__ tex = jb.textures;
   const float4* __restrict__ g_atlas = reinterpret_cast<const float4*>(jb.atlas);
   float* __restrict__ g_tex = jb.g_textures;
-  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate;
+  const int TS = jb.txt_size, p_left = jb.p_left, p_right = jb.p_right, f = jb.decimate, stage = jb.stage;
   if ((int)blockIdx.x * 32 >= TS || (int)blockIdx.y * 8 >= TS) return;
   const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y, m = blockIdx.z - J.zoff[job];
   __shared__ float s_sum[8][32][3];
   const bool ok = x < TS && y < TS;
+  const int CS = TS / f;
+  const size_t cell = (((size_t)m * CS + y / f) * CS + x / f) * 3;
   float g[3] = {0.f, 0.f, 0.f};
+  if (stage == DBW_TEX_STAGE_CELLS) {
+    // `atlas` holds the CELL gradient (n_maps, CS, CS, 3), already summed over the cell's texels (and over ranks)
+    if (ok) {
+      const float* gc = jb.atlas + cell;
+      const size_t o = (((size_t)m * TS + y) * TS + x) * 3;
+      const float scale = f == 8 ? 1.f / 64.f : 1.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float sg = 1.f / (1.f + expf(-tex[o + c]));
+        g_tex[o + c] = gc[c] * scale * sg * (1.f - sg);
+      }
+    }
+    return;
+  }
   if (ok) {
     const int Wp = TS + p_left + p_right;
     const float4* row = g_atlas + ((size_t)m * TS + y) * Wp;
@@ -240,10 +355,14 @@ __global__ void texture_prep_backward_kernel(const TexJobs J) {
       float v = 0.f;
 #pragma unroll
       for (int r = 0; r < 8; ++r) v += s_sum[r][threadIdx.x][c];
-      g[c] = v * (1.f / 64.f);
+      g[c] = stage == DBW_TEX_STAGE_EXPAND ? v : v * (1.f / 64.f);
     }
   }
   if (!ok) return;
+  if (stage == DBW_TEX_STAGE_EXPAND) {                       // `g_textures` receives the cell gradient: the sum over the cell's texels
+    if (x % f == 0 && y % f == 0) { g_tex[cell] = g[0]; g_tex[cell + 1] = g[1]; g_tex[cell + 2] = g[2]; }
+    return;
+  }
   const size_t o = (((size_t)m * TS + y) * TS + x) * 3;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -269,6 +388,7 @@ static int launch_tex(const DbwTexJob* jobs, int n_jobs, bool backward, void* st
   for (int i = 0; i < n_jobs; ++i) {
     const DbwTexJob& j = jobs[i];
     if (!j.textures || !j.atlas || (backward && !j.g_textures)) return dbw_fail_("texture prep: null pointer argument", cudaSuccess);
+    if (j.stage < 0 || j.stage > 2) return dbw_fail_("texture prep: stage must be DBW_TEX_STAGE_FUSED, _CELLS or _EXPAND", cudaSuccess);
     if (check_tex(who, j.n_maps, j.txt_size, j.p_left, j.p_right, j.decimate)) return -1;
     J.j[i] = j; J.zoff[i + 1] = J.zoff[i] + j.n_maps;
     ts_max = j.txt_size > ts_max ? j.txt_size : ts_max;

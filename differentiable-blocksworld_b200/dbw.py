@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib, geometry as G, losses as L
 from .renderer import Renderer, render_scene, _c, _stream
 from .fused_loss import ScenePass, scene_mse
-from .scene_ops import scene_geometry_parts, texture_atlas, scene_atlases
+from .scene_ops import scene_geometry_passes, block_opacities, scene_atlases, scene_texture_cells, atlases_from_cells
 from .structures import Meshes, TexturesUV, join_meshes_as_scene
 
 # accepted keys and defaults of the config sub-dicts (configs/*/*.yml -> model.{mesh,rend_optim,loss}); unknown keys are
@@ -113,15 +113,13 @@ class DifferentiableBlocksWorld(nn.Module):
         self.fused_scene = True           # scene_ops kernels for mesh build + texture prep
         self.fused_loss = True            # compositing + MSE in the rasterizer's epilogue (fused_loss.py) when nothing else reads rec
         self._passes = None
-        self.overlap_passes = False       # environment pass on a side stream (measured: +1 %)
-        import os as _os
-        self.alpha_group_faces = int(_os.environ.get('DBW_ALPHA_GROUP', 0)) or None      # experiment switch: 1 = one opacity entry per face
+        self.alpha_group_faces = None     # None: one opacity entry per block (alpha_group = BNF); 1: one per face, as dbw.py:219 packs them
         self.n_total_views = None         # data-parallel context (parallel.py): views of the whole step
+        self.grad_sum_point = None        # likewise: parallel.GradSumPoint, sums the scene tensors' gradients over ranks inside the backward
         self.noise_generator = None       # RNG shared by all ranks for opacity noise / overlap samples
         self.opacity_noise_buffer = None  # pre-drawn randn (N,) used instead of drawing inside forward (graph.py)
         self.overlap_samples_buffer = None  # pre-drawn U(0,1) (N,1000,3) for the overlap term, likewise
         self._static = None
-        self._env_stream = None
         self._reg_state_stale = False
 
     # ------------------------------------------------------------------ construction
@@ -326,8 +324,14 @@ class DifferentiableBlocksWorld(nn.Module):
         """per-block opacities (+ exploration noise while coarse) and the face_map that disables filtered blocks
         (dbw.py:300-316 with static shapes); written for few launches: it runs every step"""
         st = self._static_arrays()
+        noisy = bool(self.opacity_noise) and coarse_training
+        if self.fused_scene and self.alpha_logit.is_cuda:
+            thr = 0.5 if hard_filter else (0.01 if self.kill_blocks else -1.0)
+            self._alpha, self._alpha_full, fmap = block_opacities(self.alpha_logit, self._draw_opacity_noise() if noisy else None,
+                                                                  float(self.opacity_noise) if noisy else 0.0, thr, st['fmap_b'], self.BNF)
+            return fmap
         logit = self.alpha_logit
-        if self.opacity_noise and coarse_training:
+        if noisy:
             logit = torch.add(logit, self._draw_opacity_noise(), alpha=float(self.opacity_noise))
         self._alpha = torch.sigmoid(logit)
         self._alpha_full = self._alpha
@@ -353,19 +357,26 @@ class DifferentiableBlocksWorld(nn.Module):
         coarse_training = self.training and self.is_live('coarse_learning')
         decim_env = self.decim_factor if (self.training and self.is_live('decimate_txt')) else 1
         decim_blocks = self.decim_factor if (coarse_training and self.is_live('decimate_txt')) else 1
-        blk_verts, ground_verts = scene_geometry_parts(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground,
-                                                       st['geom'])
-        # environment: constant background sphere + posed ground, two square maps in one atlas
-        env_verts = torch.cat([st['bkg_world'], ground_verts])
-        env_atlas, atlas = scene_atlases(self.texture_bkg, self.texture_ground, self.textures, self.txt_padding, decim_env, decim_blocks)
+        # environment vertices = constant background sphere + posed ground; both passes' arrays come out of one launch
+        blk_verts, env_verts = scene_geometry_passes(self.sq_eps, self.S, self.R_6d, self.T, self.R_6d_ground, self.T_ground,
+                                                     st['geom'], st['bkg_world'])
+        fmap = self._opacities(hard_filter, coarse_training)
+        alpha = None if hard_filter else self._alpha          # one opacity per block: alpha_group = BNF faces share an entry
+        if self.grad_sum_point is not None and decim_env == 8 and decim_blocks == 8:
+            # data parallel: everything the two raster passes differentiate goes through ONE gradient-sum point, textures as
+            # their decimated cells (parallel.GradSumPoint); what lies before it turns summed gradients into leaf gradients
+            cells_env, cells_blk = scene_texture_cells(self.texture_bkg, self.texture_ground, self.textures, decim_env, decim_blocks)
+            summed = self.grad_sum_point(blk_verts, env_verts, cells_env, cells_blk, *([alpha] if alpha is not None else []))
+            blk_verts, env_verts, cells_env, cells_blk = summed[:4]
+            alpha = summed[4] if alpha is not None else None
+            env_atlas, atlas = atlases_from_cells(cells_env, cells_blk, self.txt_padding, decim_env, decim_blocks)
+        else:
+            env_atlas, atlas = scene_atlases(self.texture_bkg, self.texture_ground, self.textures, self.txt_padding, decim_env, decim_blocks)
         env_atlas = env_atlas.reshape(-1, 4)
         side = self.texture_bkg.shape[1]
         env_table = [(0, side, side), (side * side * 3, side, side)]
-        # blocks
-        fmap = self._opacities(hard_filter, coarse_training)
         rows, cols = atlas.shape[1], atlas.shape[2]
         table = [(i * rows * cols * 3, rows, cols) for i in range(self.n_blocks)]
-        alpha = None if hard_filter else self._alpha          # one opacity per block: alpha_group = BNF faces share an entry
         if alpha is not None and self.alpha_group_faces == 1:
             alpha = alpha[:, None].expand(-1, self.BNF).reshape(-1)
         self._reg_state_stale = True          # compute_losses() rebuilds what the regularisers read, if they are on
@@ -375,20 +386,10 @@ class DifferentiableBlocksWorld(nn.Module):
         """environment pass + blocks pass over the fused scene tensors -> (env RGBA, blocks RGBA)"""
         st = self._static_arrays()
         (env_verts, env_atlas, env_table), (blk_verts, atlas, table, fmap, alpha) = self._scene_tensors(hard_filter)
-        main = torch.cuda.current_stream()
-        stream = main
-        if self.overlap_passes:
-            self._env_stream = self._env_stream or torch.cuda.Stream()
-            stream = self._env_stream
-            stream.wait_stream(main)
-        with torch.cuda.stream(stream):
-            env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
-                                    R, T, None, texels4=True, n_static_faces=self.bkg_n_faces)
+        env_rgba = self._raster(self.renderer_env, env_verts, st['faces_e'], st['fvu_e'], st['fmap_e'], env_atlas, env_table,
+                                R, T, None, texels4=True, n_static_faces=self.bkg_n_faces)
         fg_rgba = self._raster(renderer, blk_verts, st['faces_b'], st['fvu_b'], fmap, atlas, table, R, T, alpha, texels4=True,
                                alpha_group=self.alpha_group_faces or self.BNF)
-        if stream is not main:
-            main.wait_stream(stream)
-            env_rgba.record_stream(main)
         return env_rgba, fg_rgba
 
     def _fused_loss_ok(self, imgs):
@@ -410,6 +411,21 @@ class DifferentiableBlocksWorld(nn.Module):
                             ScenePass(st['faces_b'], st['fvu_b'], st['fmap_b'], table, renderer, alpha_group=self.alpha_group_faces or self.BNF))
         return scene_mse(env_verts, env_atlas, blk_verts, atlas, alpha, inp['R'], inp['T'], inp['imgs'], self._passes[1],
                          self._passes[2], fmap, n_total_views=self.n_total_views or len(inp['imgs']), view_rows=inp.get('rows'))
+
+    def can_sum_gradients_at_scene_tensors(self, imgs):
+        """the step's gradients may be summed over data-parallel ranks at the scene tensors (vertices, opacities, texture CELLS)
+        instead of at the leaves: fused-loss path, and both texture stacks box-decimated (the cells are then 64x smaller than
+        the texture parameters; undecimated they are as large and the leaf all-reduce is used)"""
+        return (self._fused_loss_ok(imgs) and self.training and self.is_live('decimate_txt') and self.is_live('coarse_learning')
+                and self.decim_factor == 8)
+
+    def grad_sum_floats(self):
+        """floats a parallel.GradSumPoint moves per step (vertices of both passes, decimated cells of all maps, opacities)"""
+        f = self.decim_factor
+        ts, side = self.textures.shape[1], self.texture_bkg.shape[1]
+        cells = (self.n_blocks * (ts // f) ** 2 + 2 * (side // f) ** 2) * 3
+        verts = (self.n_blocks * self.sq_eta.shape[1] + self.bkg.verts_packed().shape[0] + self.ground.verts_packed().shape[0]) * 3
+        return cells + verts + self.n_blocks + 8
 
     def _blocks_static(self, hard_filter):
         """eager (PyTorch ops) construction of the blocks scene with fixed shapes -- the reference's arithmetic

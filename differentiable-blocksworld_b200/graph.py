@@ -61,9 +61,9 @@ class GraphedStep:
             self.losses = self._body()
 
     def _body(self):
-        losses = self.model(self.static_inp, None)
-        self.vp.bucket.backward(self.vp.weighted_total(losses, len(self.static_inp['imgs']), self.n_total))
-        if self.capture_all_reduce:
+        losses, reduced = self.vp.local_step(self.static_inp, None, self.n_total, collective=self.capture_all_reduce)
+        self.inside = self.vp.reduces_inside_backward(self.static_inp)      # the collective sits INSIDE the backward (parallel.GradSumPoint)
+        if self.capture_all_reduce and not reduced:
             self.vp.bucket.all_reduce(self.vp.group)
         return losses
 
@@ -81,7 +81,10 @@ class GraphedStep:
         if self.overlap_buf is not None:
             self.overlap_buf.uniform_(generator=self.gen)
         self.graph.replay()
-        if not self.capture_all_reduce and all_reduce:
+        if not self.capture_all_reduce and all_reduce and self.vp.world_size > 1:
+            if self.inside:
+                raise RuntimeError('this step sums its gradients inside the backward (parallel.GradSumPoint) but was captured '
+                                   'with capture_all_reduce=False: its gradients are local and cannot be reduced afterwards')
             self.vp.bucket.all_reduce(self.vp.group)
         return self.losses
 

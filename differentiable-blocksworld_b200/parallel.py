@@ -89,21 +89,65 @@ class PeerAllReduce:
             self.handle = ctypes.c_void_p()
 
 
+class _GradSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, point, *tensors):
+        ctx.point = point
+        return tuple(t.view_as(t) for t in tensors)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        return (None, *ctx.point.sum_over_ranks(grads))
+
+
+class GradSumPoint:
+    """Data-parallel gradient reduction INSIDE the backward, at the scene tensors instead of at the leaves: `point(*tensors)` is the
+    identity in the forward; in the backward the tensors' gradients are packed into the peer-memory bucket (one gather kernel),
+    summed over the ranks by ONE dbw_comm_all_reduce launch, and handed on as views of the bucket.  The model routes everything
+    its two raster passes differentiate through one point -- both passes' vertices, the block opacities, and the textures as their
+    box-decimated CELLS (scene_ops.scene_texture_cells) -- so what lies before the point (texture-cell / geometry / opacity
+    backward kernels: deterministic, no atomics) turns GLOBAL gradients into leaf gradients, identically on every rank, and no
+    leaf all-reduce follows.  While textures are decimated 8x (the first `decimate_txt` iterations, src/model/dbw.py:276-279,
+    331-334) the cells hold 64x fewer values than the texture parameters: ~0.15 MB per step instead of ~9.4 MB on the DTU shape."""
+
+    def __init__(self, peer):
+        self.peer = peer
+
+    def __call__(self, *tensors):
+        return _GradSumFn.apply(self, *tensors)
+
+    def sum_over_ranks(self, grads):
+        n = sum(g.numel() for g in grads)
+        n_pad = (n + 3) // 4 * 4
+        if n_pad > self.peer.flat.numel():
+            raise RuntimeError(f'{n_pad} gradient floats exceed the peer-memory bucket ({self.peer.flat.numel()})')
+        buf = self.peer.flat[:n_pad]
+        with torch.no_grad():
+            torch.cat([g.reshape(-1).float() for g in grads], out=buf[:n])
+            self.peer.all_reduce(buf)
+        out, o = [], 0
+        for g in grads:
+            out.append(buf[o:o + g.numel()].view_as(g))
+            o += g.numel()
+        return out
+
+
 class GradBucket:
     """All parameter gradients as views into one flat buffer -> a single all-reduce per step."""
 
-    def __init__(self, params, peer_factory=None):
+    def __init__(self, params, peer_factory=None, min_floats=0):
         """peer_factory(n_floats, device) -> PeerAllReduce or None: when given and successful, the flat buffer IS the peer-memory
-        arena's bucket (csrc/dbw_comm.cu) and all_reduce() is its kernel; else a plain tensor and torch.distributed"""
+        arena's bucket (csrc/dbw_comm.cu) and all_reduce() is its kernel; else a plain tensor and torch.distributed.
+        min_floats: capacity the arena needs for its other user (GradSumPoint)"""
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.n = n
         n_pad = (n + 3) // 4 * 4                     # padded: 128-bit all-reduce lanes
-        self.peer = peer_factory(n_pad, ref.device) if peer_factory is not None else None
+        self.peer = peer_factory(max(n_pad, (int(min_floats) + 3) // 4 * 4), ref.device) if peer_factory is not None else None
         if self.peer is not None:
-            self.flat = self.peer.flat
-            self.flat.zero_()
+            self.peer.flat.zero_()
+            self.flat = self.peer.flat[:n_pad]
         else:
             self.flat = torch.zeros(n_pad, dtype=ref.dtype, device=ref.device)
         self._zeros = {}
@@ -116,14 +160,17 @@ class GradBucket:
     def zero_(self):
         self.flat.zero_()
 
-    def backward(self, total):
+    def backward(self, total, gather=True):
         """Back-propagate `total` and leave every parameter's gradient in the flat bucket with ONE gather kernel: the
         parameters enter the backward without .grad, so autograd hands over each gradient tensor as it is (no zero-fill
         of the bucket, no accumulate-add per parameter); a single cat then writes them into the flat buffer and the
-        .grad attributes become the bucket views again.  CUDA-graph capturable."""
+        .grad attributes become the bucket views again.  CUDA-graph capturable.  gather=False stops after the backward:
+        the .grad attributes are autograd's own tensors and the flat buffer is not written (no collective reads it)."""
         for p in self.params:
             p.grad = None
         total.backward()
+        if not gather:
+            return
         pieces = []
         for p in self.params:
             g = p.grad
@@ -136,6 +183,10 @@ class GradBucket:
             torch.cat(pieces, out=self.flat[:self.n])
         for p, v in zip(self.params, self.views):
             p.grad = v
+
+    def grads_flat(self):
+        """the gradients as one flat vector in bucket order, whichever way the last backward left them"""
+        return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params])
 
     def all_reduce(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -155,10 +206,18 @@ class ViewParallel:
 
     VIEW_KEYS = ('imgs', 'R', 'T', 'K')
 
-    def __init__(self, model, group=None, seed=227391, row_bands=False, collective='nccl'):
+    def __init__(self, model, group=None, seed=227391, row_bands=False, collective='nccl', reduce_at='auto', gather_grads=None):
         """collective: 'nccl' (torch.distributed all_reduce; also what gloo groups use), 'p2p' (the NVLink peer-memory kernel
-        of csrc/dbw_comm.cu, CUDA-graph capturable) or 'auto' (p2p if it initialises on this node, else nccl)"""
+        of csrc/dbw_comm.cu, CUDA-graph capturable) or 'auto' (p2p if it initialises on this node, else nccl).
+        reduce_at: 'leaf' (all-reduce the parameter gradients after the backward), 'scene' (sum the gradients of the scene
+        tensors inside the backward, GradSumPoint: needs the peer-memory collective; applies while the model's textures are
+        decimated on its fused-loss path, see can_sum_gradients_at_scene_tensors) or 'auto' (scene whenever it applies,
+        leaf otherwise -- decided per step).
+        gather_grads: gather the gradients into bucket.flat (and make the .grad attributes views of it) after every backward;
+        None: only when a leaf all-reduce reads the bucket (world > 1 and no reduction inside the backward) -- otherwise the
+        .grad attributes are autograd's own tensors and bucket.grads_flat() concatenates them on demand"""
         self.model, self.group, self.seed = model, group, seed
+        self.reduce_at, self.gather_grads = reduce_at, gather_grads
         self.row_bands = row_bands          # shard at (view, row band) granularity (needs the model's fused-loss path)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -173,7 +232,11 @@ class ViewParallel:
                 print(f'[dbw_b200] peer-memory all-reduce unavailable ({exc}); using NCCL')
                 return None
 
-        self.bucket = GradBucket(model.parameters(), peer_factory)
+        want_point = reduce_at in ('scene', 'auto') and hasattr(model, 'grad_sum_floats')
+        self.bucket = GradBucket(model.parameters(), peer_factory, model.grad_sum_floats() if want_point else 0)
+        self.sum_point = GradSumPoint(self.bucket.peer) if (want_point and self.bucket.peer is not None) else None
+        if reduce_at == 'scene' and self.sum_point is None and self.world_size > 1:
+            raise RuntimeError("reduce_at='scene' needs the peer-memory collective (collective='p2p' or 'auto') and a model with grad_sum_floats()")
         self._step = 0
         self.collective_name = 'none (1 rank)' if self.world_size == 1 else 'ncclAllReduce'
         if self.bucket.peer is not None:
@@ -207,25 +270,44 @@ class ViewParallel:
             self.model.noise_generator = g
         g.manual_seed(self.seed + self._step)      # identical on every rank, fresh every step
 
+    def reduces_inside_backward(self, inp):
+        """this step's gradients are summed over the ranks inside the backward, at the scene tensors (GradSumPoint)"""
+        return self.sum_point is not None and self.model.can_sum_gradients_at_scene_tensors(inp['imgs'])
+
+    def local_step(self, inp, labels, n_total_views, collective=True):
+        """forward + backward over this rank's shard.  Returns (losses, reduced): reduced = the gradients are already the
+        sum over ranks (the GradSumPoint ran inside the backward); otherwise a leaf all-reduce of the bucket is due.
+        collective=False on a step that would reduce inside the backward leaves LOCAL gradients (timing breakdowns only)."""
+        inside = self.reduces_inside_backward(inp)
+        self.model.n_total_views = n_total_views
+        self.model.grad_sum_point = self.sum_point if (inside and collective) else None
+        try:
+            losses = self.model(inp, labels)
+            gather = self.gather_grads if self.gather_grads is not None else (self.world_size > 1 and not inside)
+            self.bucket.backward(self.weighted_total(losses, len(inp['imgs']), n_total_views, replicated_everywhere=inside),
+                                 gather=gather)
+        finally:
+            self.model.grad_sum_point = None
+        return losses, inside and collective
+
     def forward_backward(self, inp, labels=None, already_sharded=False, n_total_views=None, all_reduce=True):
-        """zero grads -> local forward -> backward -> ONE all-reduce.  Returns the (local) loss dict."""
+        """local forward -> backward -> ONE all-reduce (inside the backward or after it).  Returns the (local) loss dict."""
         if not already_sharded:
             inp, n_total_views = self.shard(inp)
-        self.model.n_total_views = n_total_views
         self._sync_rng(inp['imgs'].device)
         self._step += 1
-        losses = self.model(inp, labels)
-        self.bucket.backward(self.weighted_total(losses, len(inp['imgs']), n_total_views))
-        if all_reduce:
+        losses, reduced = self.local_step(inp, labels, n_total_views, collective=all_reduce)
+        if all_reduce and not reduced:
             self.bucket.all_reduce(self.group)
         return losses
 
-    def weighted_total(self, losses, n_local_views, n_total_views):
-        """the scalar each rank back-propagates: its share of the per-view terms + 1/world of the replicated terms"""
+    def weighted_total(self, losses, n_local_views, n_total_views, replicated_everywhere=False):
+        """the scalar each rank back-propagates: its share of the per-view terms + the replicated terms (regularisers:
+        identical on every rank) at 1/world when a leaf all-reduce will sum them, at 1 when no leaf all-reduce follows"""
         shared = [v for k, v in losses.items() if k not in ('rgb', 'perceptual', 'total')]
         total = losses['rgb'] if 'rgb' in losses else 0.
         if 'perceptual' in losses:
             total = total + losses['perceptual'] * (n_local_views / float(n_total_views))
         if shared:
-            total = total + sum(shared) / self.world_size
+            total = total + sum(shared) / (1 if replicated_everywhere else self.world_size)
         return total

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBW_ABI_VERSION 6
+#define DBW_ABI_VERSION 7
 #define DBW_MAX_FACES_PER_PIXEL 64
 
 /*
@@ -211,16 +211,48 @@ int dbw_scene_geometry_forward(const DbwSceneGeometry* g, float* verts_out, void
 /* g_verts (N*Vb + Vg, 3) -> gradients of the leaf parameters (written, not accumulated). */
 int dbw_scene_geometry_backward(const DbwSceneGeometry* g, const float* g_verts, float* g_sq_eps, float* g_S, float* g_R_6d,
                                 float* g_T, float* g_R_6d_ground, float* g_T_ground, void* stream);
+/* The layout the two render passes consume without a concatenation: verts_out (n_env_static + Vg + N*Vb, 3) = the static
+ * environment vertices (the background sphere in world space, dbw.py:271-274; copied), the ground, then the blocks -- the
+ * environment pass takes the first n_env_static + Vg rows, the blocks pass the rest.  The backward takes the two gradient
+ * blocks where they lie (any two device pointers: no gather). */
+int dbw_scene_geometry_forward_env(const DbwSceneGeometry* g, const float* env_static_verts, int32_t n_env_static,
+                                   float* verts_out, void* stream);
+int dbw_scene_geometry_backward_parts(const DbwSceneGeometry* g, const float* g_block_verts, const float* g_ground_verts,
+                                      float* g_sq_eps, float* g_S, float* g_R_6d, float* g_T, float* g_R_6d_ground,
+                                      float* g_T_ground, void* stream);
+
+/* Block opacities of a step (src/model/dbw.py:300-316 with static shapes), one launch each way:
+ *   alpha[k]      = sigmoid(alpha_logit[k] + noise_scale * noise[k])      (noise may be NULL)
+ *   keep[k]       = keep_threshold < 0  ||  sigmoid(alpha_logit[k]) > keep_threshold      (0.5: hard filter, 0.01: kill_blocks)
+ *   alpha_kept[k] = keep[k] ? alpha[k] : 0                                (optional)
+ *   face_map_out[k*faces_per_block + j] = keep[k] ? face_map_in[..] : -1  (optional; -1 = never rasterized)
+ * backward: g_alpha_logit = (g_alpha + keep * g_alpha_kept) * alpha * (1 - alpha)   (either gradient may be NULL). */
+int dbw_opacity_forward(const float* alpha_logit, const float* noise, float noise_scale, float keep_threshold,
+                        const int32_t* face_map_in, int32_t n_blocks, int32_t faces_per_block, float* alpha, float* alpha_kept,
+                        int32_t* face_map_out, void* stream);
+int dbw_opacity_backward(const float* alpha_logit, const float* noise, float noise_scale, float keep_threshold,
+                         const float* g_alpha, const float* g_alpha_kept, int32_t n_blocks, float* g_alpha_logit, void* stream);
 
 /* textures (M,TS,TS,3) logits -> atlas (M, TS, p_left+TS+p_right) float4 texels: sigmoid, optional `decimate`xdecimate box
  * filter (1 = off, 8 = dbw.py:331-334), circular padding along u (dbw.py:339-341).  Backward: g_atlas -> g_textures. */
 /* One texture stack of a multi-stack texture preparation: (n_maps, txt_size, txt_size, 3) logits -> float4 texel atlas
  * (n_maps, txt_size, p_left + txt_size + p_right) [forward: `atlas` is written; backward: `atlas` is the atlas GRADIENT that is read
  * and `g_textures` receives d/d logits]. */
+/* `stage` splits the preparation at the CELL COLOURS c = box_mean(sigmoid(logits)), (n_maps, txt_size/decimate, txt_size/decimate, 3)
+ * floats -- the smallest tensor on the way (64x smaller than the textures while they are decimated), where a data-parallel
+ * trainer sums gradients over ranks (parallel.GradSumPoint):
+ *   DBW_TEX_STAGE_FUSED   logits -> atlas                                     (backward: atlas gradient -> logit gradient)
+ *   DBW_TEX_STAGE_CELLS   logits -> cells, written to `atlas`                 (backward: `atlas` = CELL gradient -> logit gradient)
+ *   DBW_TEX_STAGE_EXPAND  cells (passed as `textures`) -> atlas               (backward: atlas gradient -> cell gradient, written
+ *                                                                              to `g_textures`; `textures` is not read)
+ * CELLS then EXPAND equals FUSED bit for bit, forward and backward. */
 #define DBW_MAX_TEX_JOBS 4
+#define DBW_TEX_STAGE_FUSED 0
+#define DBW_TEX_STAGE_CELLS 1
+#define DBW_TEX_STAGE_EXPAND 2
 typedef struct DbwTexJob {
   const float* textures; float* atlas; float* g_textures;
-  int32_t n_maps, txt_size, p_left, p_right, decimate, reserved;
+  int32_t n_maps, txt_size, p_left, p_right, decimate, stage;
 } DbwTexJob;
 /* Several stacks in ONE launch (the step's three: background, ground, blocks; `jobs` is a HOST array of n_jobs <= 4). */
 int dbw_texture_prep_forward_multi(const DbwTexJob* jobs, int32_t n_jobs, void* stream);

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f'{n} declared in include/dbw_render.h but not exported'
     assert set(_lib.EXPORTS) == set(names)
-    assert L.dbw_abi_version() == _lib.ABI_VERSION == 6
+    assert L.dbw_abi_version() == _lib.ABI_VERSION == 7
 
 
 def test_settings_struct_layout_and_workspace_query():

@@ -126,16 +126,17 @@ def test_cuda_graph_step_equals_eager_step():
     vp = ViewParallel(model, seed=5)
     graphed = GraphedStep(vp, inp, len(inp['imgs']))
     losses = graphed.run()
-    g_graph = vp.bucket.flat.clone()
+    g_graph = vp.bucket.grads_flat().clone()
     noise = model.opacity_noise_buffer.clone()
     l_graph = losses['rgb'].item()
     # eager step with the same noise
     model.opacity_noise_buffer = noise
-    vp.bucket.zero_()
+    for q in model.parameters():
+        q.grad = None
     l = model(inp, None)
     l['total'].backward()
     assert abs(l['rgb'].item() - l_graph) < 1e-7
-    assert (vp.bucket.flat - g_graph).norm() <= 1e-4 * g_graph.norm()
+    assert (vp.bucket.grads_flat() - g_graph).norm() <= 1e-4 * g_graph.norm()
     # replay with new inputs changes the result, and is repeatable
     inp2 = {k: (v.flip(0).contiguous() if k in ('imgs',) else v) for k, v in inp.items()}
     l2 = graphed.run(inp2)['rgb'].item()
@@ -279,7 +280,6 @@ def test_graphed_step_recaptures_when_the_schedule_switches_phase():
     l_coarse = graphed.run()['rgb'].item()
     model.set_cur_epoch(2000)                      # past coarse_learning (1500) and decimate_txt (750)
     l_fine = graphed.run()['rgb'].item()
-    vp.bucket.zero_()
     model.opacity_noise_buffer = None
     ref = model(inp, None)['rgb'].item()
     assert abs(l_fine - ref) < 1e-7 and abs(l_fine - l_coarse) > 1e-9
@@ -550,3 +550,118 @@ def test_scene_atlases_one_launch_equals_three(decim):
     gr = torch.autograd.grad((ref_env * we).sum() + (ref_blk * wb).sum(), [tb, tg, tk])
     for a, b in zip(ga, gr):
         assert torch.equal(a, b)
+
+
+def test_scene_geometry_passes_equals_parts_plus_concatenation():
+    """dbw_scene_geometry_forward_env / _backward_parts: (static environment | ground | blocks) out of one launch ==
+    dbw_scene_geometry_forward + torch.cat, values and leaf gradients bit for bit"""
+    from dbw_b200.scene_ops import scene_geometry_parts, scene_geometry_passes
+    model, tpl, p, dev = _model_and_oracle()
+    with torch.no_grad():
+        model.sq_eps.copy_(torch.randn_like(model.sq_eps))
+        model.R_6d_ground.add_(0.1 * torch.randn_like(model.R_6d_ground))
+    st = model._fused_arrays()
+    leaves = [model.sq_eps, model.S, model.R_6d, model.T, model.R_6d_ground, model.T_ground]
+    blk, env = scene_geometry_passes(*leaves, st['geom'], st['bkg_world'])
+    blk_ref, ground_ref = scene_geometry_parts(*leaves, st['geom'])
+    env_ref = torch.cat([st['bkg_world'], ground_ref])
+    assert torch.equal(blk, blk_ref) and torch.equal(env, env_ref)
+    wb, we = torch.randn_like(blk), torch.randn_like(env)
+    ga = torch.autograd.grad((blk * wb).sum() + (env * we).sum(), leaves)
+    gr = torch.autograd.grad((blk_ref * wb).sum() + (env_ref * we).sum(), leaves)
+    for a, b in zip(ga, gr):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize('thr', [-1.0, 0.01, 0.5])
+@pytest.mark.parametrize('noisy', [False, True])
+def test_block_opacities_kernel_matches_the_eager_ops(thr, noisy):
+    """dbw_opacity_forward / _backward vs the eager ops of src/model/dbw.py:300-316 (static shapes)"""
+    from dbw_b200.scene_ops import block_opacities
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(11)
+    N, BNF = 7, 12
+    logit = (3 * torch.randn(N, generator=g)).to(dev).requires_grad_(True)
+    with torch.no_grad():
+        logit[2] = -6.0                                          # sigmoid = 0.0025: killed at 0.01
+    noise = torch.randn(N, generator=g).to(dev) if noisy else None
+    fmap0 = torch.arange(N, device=dev, dtype=torch.int32).repeat_interleave(BNF)
+    alpha, kept, fmap = block_opacities(logit, noise, 0.7 if noisy else 0.0, thr, fmap0, BNF)
+    ref_alpha = torch.sigmoid(logit + 0.7 * noise) if noisy else torch.sigmoid(logit)
+    keep = torch.sigmoid(logit.detach()) > thr if thr >= 0 else torch.ones(N, dtype=torch.bool, device=dev)
+    ref_kept = ref_alpha * keep
+    ref_fmap = torch.where(keep[:, None], fmap0.view(N, BNF), torch.full((), -1, dtype=torch.int32, device=dev)).reshape(-1)
+    assert (alpha - ref_alpha).abs().max().item() < 2e-7 and (kept - ref_kept).abs().max().item() < 2e-7
+    assert torch.equal(fmap, ref_fmap) and (thr >= 0 or fmap.data_ptr() == fmap0.data_ptr())
+    assert thr < 0.01 or not bool(keep[2])
+    wa, wk = torch.randn(N, generator=g).to(dev), torch.randn(N, generator=g).to(dev)
+    ga, = torch.autograd.grad((alpha * wa).sum() + (kept * wk).sum(), logit, retain_graph=True)
+    gr, = torch.autograd.grad((ref_alpha * wa).sum() + (ref_kept * wk).sum(), logit, retain_graph=True)
+    assert (ga - gr).abs().max().item() < 1e-6
+    g_only_alpha, = torch.autograd.grad((alpha * wa).sum(), logit)          # alpha_kept unused: its gradient arrives as None
+    assert (g_only_alpha - torch.autograd.grad((ref_alpha * wa).sum(), logit)[0]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize('decim', [(1, 1), (8, 8), (8, 1)])
+def test_texture_cells_then_expand_equals_the_fused_preparation(decim):
+    """DBW_TEX_STAGE_CELLS + DBW_TEX_STAGE_EXPAND (the split a data-parallel step sums gradients at) == DBW_TEX_STAGE_FUSED,
+    bit for bit, forward and backward"""
+    from dbw_b200.scene_ops import scene_atlases, scene_texture_cells, atlases_from_cells
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(4)
+    tb, tg = (torch.randn(1, 64, 64, 3, generator=g).to(dev).requires_grad_(True) for _ in range(2))
+    tk = torch.randn(3, 32, 32, 3, generator=g).to(dev).requires_grad_(True)
+    ref_env, ref_blk = scene_atlases(tb, tg, tk, (3, 5), decim[0], decim[1])
+    cells_env, cells_blk = scene_texture_cells(tb, tg, tk, decim[0], decim[1])
+    assert cells_env.shape == (2, 64 // decim[0], 64 // decim[0], 3) and cells_blk.shape == (3, 32 // decim[1], 32 // decim[1], 3)
+    env, blk = atlases_from_cells(cells_env, cells_blk, (3, 5), decim[0], decim[1])
+    assert torch.equal(env, ref_env) and torch.equal(blk, ref_blk)
+    if decim[1] == 8:                                                      # a cell = the mean of its 8 x 8 sigmoids
+        want = torch.sigmoid(tk.detach()).view(3, 4, 8, 4, 8, 3).mean(dim=(2, 4))
+        assert (cells_blk - want).abs().max().item() < 1e-6
+    we, wb = torch.randn_like(env), torch.randn_like(blk)
+    ga = torch.autograd.grad((env * we).sum() + (blk * wb).sum(), [tb, tg, tk])
+    gr = torch.autograd.grad((ref_env * we).sum() + (ref_blk * wb).sum(), [tb, tg, tk])
+    for a, b in zip(ga, gr):
+        assert torch.equal(a, b)
+
+
+def test_gradient_sum_point_is_the_identity_on_one_rank():
+    """parallel.GradSumPoint wired through the model (vertices, opacities and texture CELLS of a step go through it) with a
+    one-rank stand-in for the peer-memory bucket: the step's loss equals the plain step's bit for bit, its leaf gradients to the
+    rounding of the raster backward's atomics (two executions of the SAME step differ by as much), and every gradient the
+    raster passes produce went through the bucket in one piece"""
+    from dbw_b200.parallel import GradSumPoint
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1}
+
+    class OneRankBucket:
+        def __init__(self):
+            self.flat = torch.zeros(model.grad_sum_floats() + 3, device=dev)
+            self.calls = []
+
+        def all_reduce(self, buf):
+            assert buf.data_ptr() == self.flat.data_ptr() and buf.numel() % 4 == 0
+            self.calls.append(buf.numel())
+
+    assert model.can_sum_gradients_at_scene_tensors(inp['imgs'])
+    params = [q for q in model.parameters() if q.requires_grad]
+    ref_loss = model(inp)['total']
+    ref = torch.autograd.grad(ref_loss, params, allow_unused=True)
+    bucket = OneRankBucket()
+    model.grad_sum_point = GradSumPoint(bucket)
+    try:
+        loss = model(inp)['total']
+        got = torch.autograd.grad(loss, params, allow_unused=True)
+    finally:
+        model.grad_sum_point = None
+    assert torch.equal(loss, ref_loss)
+    assert len(bucket.calls) == 1 and bucket.calls[0] <= model.grad_sum_floats() + 3
+    again = torch.autograd.grad(model(inp)['total'], params, allow_unused=True)
+    for a, b, c in zip(got, ref, again):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert (a - b).norm() <= 1e-5 * b.norm() + 4 * (c - b).norm() + 1e-12, ((a - b).norm().item(), (c - b).norm().item())
+    model.set_cur_epoch(2000)                                  # decimation over: the leaf all-reduce takes over
+    assert not model.can_sum_gradients_at_scene_tensors(inp['imgs'])

@@ -73,7 +73,11 @@ def test_peer_memory_all_reduce_matches_nccl():
             assert ok and err == 0, (rank, n, ok, err)
 
 
-def _w_step(rank, world, port, out, collective):
+LOSS_RGB = {'rgb_weight': 1}
+LOSS_REG = {'rgb_weight': 1, 'parsimony_weight': 0.01, 'tv_weight': 0.1}      # + replicated terms (identical on every rank)
+
+
+def _w_step(rank, world, port, out, collective, reduce_at, loss):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -86,33 +90,40 @@ def _w_step(rank, world, port, out, collective):
     from oracle import dbw_path as D
     from copy import deepcopy
     cfg = deepcopy(CFG)
-    cfg['loss'] = {'rgb_weight': 1}
+    cfg['loss'] = dict(loss)
     torch.manual_seed(5)
     model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
     model.train()
     R, T, K = D.ring_cameras(5, jitter=0.3, seed=7)
     g = torch.Generator().manual_seed(7)
     inp = {'imgs': torch.rand(5, 3, 48, 64, generator=g), 'R': R, 'T': T, 'K': K[None].expand(5, -1, -1).contiguous()}
-    vp = ViewParallel(model, seed=5, row_bands=True, collective=collective)
+    vp = ViewParallel(model, seed=5, row_bands=True, collective=collective, reduce_at=reduce_at)
     local, n_total = vp.shard(inp)
     local = {k: v.to(dev) for k, v in local.items()}
     graphed = GraphedStep(vp, local, n_total)
     graphed.run()
+    graphed.run()                                   # a replay after the first: the bucket / gradient views are reused
     torch.cuda.synchronize()
-    out[rank] = (vp.bucket.flat.cpu(), graphed.capture_all_reduce, local['rows'].cpu().tolist(), graphed.noise_buf.cpu())
+    out[rank] = (vp.bucket.grads_flat().cpu(), graphed.capture_all_reduce, local['rows'].cpu().tolist(), graphed.noise_buf.cpu(),
+                 graphed.inside, vp.bucket.peer.error() if vp.bucket.peer is not None else 0)
     dist.barrier()
     dist.destroy_process_group()
 
 
 @needs2
-@pytest.mark.parametrize('collective', ['p2p', 'nccl'])
-def test_two_rank_row_band_step_equals_single_gpu_step(collective):
-    """5 views of 48 rows over 2 ranks = 7.5 bands each: the ranks split view 2 in the middle; the all-reduced gradient bucket
-    (peer-memory kernel captured inside the step's CUDA graph, or NCCL after the replay) == the single-GPU step's"""
+@pytest.mark.parametrize('collective,reduce_at,loss', [('p2p', 'auto', LOSS_RGB), ('p2p', 'auto', LOSS_REG), ('p2p', 'leaf', LOSS_REG),
+                                                       ('nccl', 'auto', LOSS_RGB)])
+def test_two_rank_row_band_step_equals_single_gpu_step(collective, reduce_at, loss):
+    """5 views of 48 rows over 2 ranks = 7.5 bands each: the ranks split view 2 in the middle; the gradients -- summed over the
+    ranks inside the backward at the scene tensors (GradSumPoint; textures are decimated at iteration 0), or all-reduced at the
+    leaves by the peer-memory kernel inside the step's CUDA graph, or by NCCL after the replay -- == the single-GPU step's,
+    replicated regularisers included"""
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_w_step, args=(2, 29600 + os.getpid() % 1000, out, collective), nprocs=2, join=True)
+    mp.spawn(_w_step, args=(2, 29600 + os.getpid() % 1000, out, collective, reduce_at, loss), nprocs=2, join=True)
     assert out[0][1] == (collective == 'p2p')
+    assert out[0][4] == out[1][4] == (collective == 'p2p' and reduce_at == 'auto')
+    assert out[0][5] == out[1][5] == 0
     assert out[0][2][-1][1] < 48 and out[1][2][0][0] > 0             # view 2 is shared
     assert torch.equal(out[0][0], out[1][0]) if collective == 'p2p' else torch.allclose(out[0][0], out[1][0], rtol=1e-6, atol=1e-9)
     import dbw_b200  # noqa: F401
@@ -122,7 +133,7 @@ def test_two_rank_row_band_step_equals_single_gpu_step(collective):
     from oracle import dbw_path as D
     from copy import deepcopy
     cfg = deepcopy(CFG)
-    cfg['loss'] = {'rgb_weight': 1}
+    cfg['loss'] = dict(loss)
     torch.manual_seed(5)
     dev = torch.device('cuda:0')
     model = DifferentiableBlocksWorld((48, 64), **cfg).to(dev)
@@ -133,5 +144,5 @@ def test_two_rank_row_band_step_equals_single_gpu_step(collective):
     vp = ViewParallel(model, seed=5)
     model.opacity_noise_buffer = out[0][3].to(dev)
     vp.forward_backward(inp)
-    ref = vp.bucket.flat.cpu()
+    ref = vp.bucket.grads_flat().cpu()
     assert (out[0][0] - ref).norm() <= 1e-4 * ref.norm(), ((out[0][0] - ref).norm().item(), ref.norm().item())
