@@ -167,11 +167,12 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     import dbw_b200  # noqa: F401
-    from dbw_b200 import _lib
+    from dbw_b200 import _lib, fused_loss
     from dbw_b200.dbw import DifferentiableBlocksWorld
     from dbw_b200.parallel import ViewParallel
     from dbw_b200.graph import GraphedStep, PipelinedGraphedStep
     from copy import deepcopy
+    fused_loss.OVERLAP_BACKWARD_PASSES = args.overlap_bwd == 'on' or (args.overlap_bwd == 'auto' and world >= 4)
 
     w = WORKLOADS[args.workload]
     B, H, W, K = w['n_views'], w['height'], w['width'], w['faces_per_pixel']
@@ -291,10 +292,12 @@ def run_ours(args):
     # the launch was submitted)
     _lib.lib().dbw_timing_reset()
     _lib.lib().dbw_timing_enable(1)
+    overlap, fused_loss.OVERLAP_BACKWARD_PASSES = fused_loss.OVERLAP_BACKWARD_PASSES, False      # one kernel at a time here
     for _ in range(args.steps):
         flush.zero_()
         step_eager(False)
     barrier()
+    fused_loss.OVERLAP_BACKWARD_PASSES = overlap
     _lib.lib().dbw_timing_enable(0)
     kt = {(kind, kk): _lib.kernel_time_ms(kind, kk) for kind in (0, 1) for kk in (1, K)}
     _lib.lib().dbw_timing_reset()
@@ -350,6 +353,7 @@ def run_ours(args):
                        'l2': 'flushed (256 MB memset) between steps, outside the per-step event pairs',
                        'loss': 'rgb (MSE) only; LPIPS excluded (SURVEY 8d)', 'seed': SEED,
                        'submission': 'eager' if graphed is None else 'each pass captured once in a CUDA graph and replayed',
+                       'backward_passes': 'concurrent (two graph branches)' if fused_loss.OVERLAP_BACKWARD_PASSES else 'back to back',
                        'e2e_pipeline': 'none' if piped is None else 'inputs of the next pass copied H2D on a side stream during this pass (double-buffered)'},
             'e2e': {'value': e2e_value, 'unit': 'views/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches_per_step * args.steps,
@@ -448,6 +452,9 @@ def main():
     ap.add_argument('--workload', default='dtu', choices=sorted(WORKLOADS))
     ap.add_argument('--collective', default='auto', choices=['auto', 'nccl', 'p2p'],
                     help='gradient all-reduce: hand-written NVLink peer-memory kernel (p2p), NCCL, or p2p when it initialises (auto)')
+    ap.add_argument('--overlap-bwd', default='auto', choices=['auto', 'on', 'off'],
+                    help="run the two passes' backward kernels concurrently (fused_loss.OVERLAP_BACKWARD_PASSES); auto: when the "
+                         'step is split over 4 or more GPUs (short launches whose tails then overlap)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='submit the step eagerly instead of replaying a CUDA graph')
     args = ap.parse_args()

@@ -16,6 +16,12 @@
 // peers' inboxes only after barrier B of this epoch, which an owner signals after its reduce has read them.
 // Barriers are epoch-stamped flags stored into the PEERS' arenas with st.release.sys and polled locally with
 // ld.acquire.sys; a poll that exceeds ~30 s sets the arena's error word instead of hanging the GPU.
+//
+// Small exchanges (<= ONE_SHOT_BYTES: the step's scene-tensor gradients, parallel.GradSumPoint, ~0.15 MB) are latency bound and
+// take the ONE-SHOT path: every rank pushes its whole vector into its slot of EVERY inbox, one rank barrier, then every rank adds
+// the world copies itself, in rank order (bit-identical again) -- one NVLink round trip instead of two, 16 CTAs instead of 96.
+// Its barrier B is DEFERRED: a rank stamps "I have finished reading my inbox" without waiting, and every exchange (either
+// path) starts by checking the peers' stamps of the previous one, long since there.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -29,6 +35,7 @@ void dbw_count_launch_(void);
 
 #define COMM_MAX_WORLD 8
 #define COMM_BLOCKS 96
+#define COMM_SMALL_BLOCKS 16
 #define COMM_THREADS 512
 #define ONE_SHOT_BYTES (512 * 1024)
 #define CTRL_BYTES 4096
@@ -93,6 +100,15 @@ __device__ __forceinline__ void rank_barrier(const CommDev& c, unsigned* ctl, in
   }
 }
 
+// deferred barrier B of the PREVIOUS exchange: every peer has finished reading the inbox this one is about to overwrite
+__device__ __forceinline__ void wait_previous_exchange(const CommDev& c, unsigned* ctl, unsigned prev_epoch) {
+  if (threadIdx.x < c.world) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(ctl + CW_FLAGS_B + threadIdx.x) < prev_epoch) if (clock64() - t0 > SPIN_LIMIT) { ctl[CW_ERROR] = 3u; break; }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void st_peer(float4* p, float4 v) {       // posted store into a peer's arena
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -106,6 +122,7 @@ __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev 
   const float4* src = reinterpret_cast<const float4*>(buf);
   const size_t slice = (n4 + W - 1) / W;                              // float4 elements per owner
   const size_t cap4 = c.slice_floats / 4;                             // inbox stride between the ranks' slices
+  wait_previous_exchange(c, ctl, epoch - 1u);
   // ---- scatter: push every element to its owner's inbox (my own slice: a local copy)
   for (size_t i0 = tid; i0 < n4; i0 += 4 * nthr) {
     float4 v[4];
@@ -139,6 +156,42 @@ __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev 
   }
   grid_barrier(ctl, base + 3u * G);
   rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every owner's sums have landed in my bucket
+}
+
+// one-shot variant for small vectors (n4 <= the inbox stride): see the header
+template <int W>
+__global__ void __launch_bounds__(COMM_THREADS) all_reduce_small_kernel(const CommDev c, float* __restrict__ buf, size_t n4) {
+  unsigned* ctl = c.ctrl[c.rank];
+  const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];
+  const int G = gridDim.x, r = c.rank;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)G * blockDim.x;
+  const size_t cap4 = c.slice_floats / 4;
+  wait_previous_exchange(c, ctl, epoch - 1u);
+  // ---- push my whole vector into slot `r` of every rank's inbox
+  const float4* src = reinterpret_cast<const float4*>(buf);
+  for (size_t i = tid; i < n4; i += nthr) {
+    const float4 v = src[i];
+#pragma unroll
+    for (int q = 0; q < W; ++q) st_peer(reinterpret_cast<float4*>(c.inbox[(r + q) % W]) + (size_t)r * cap4 + i, v);
+  }
+  grid_barrier(ctl, base + 1u * G);
+  rank_barrier(c, ctl, CW_FLAGS_A, epoch);                            // A: every rank's vector has landed in my inbox
+  grid_barrier(ctl, base + 2u * G);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + 3u * G; }
+  // ---- every rank forms every sum itself, in rank order
+  float4* dst = reinterpret_cast<float4*>(buf);
+  const float4* in = reinterpret_cast<const float4*>(c.inbox[r]);
+  for (size_t i = tid; i < n4; i += nthr) {
+    float4 v[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) v[q] = ld_peer(in + (size_t)q * cap4 + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int q = 1; q < W; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
+    dst[i] = acc;
+  }
+  grid_barrier(ctl, base + 3u * G);                                   // all my blocks have finished reading the inbox
+  if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.ctrl[threadIdx.x] + CW_FLAGS_B + r, epoch);      // B, not waited for
 }
 
 static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_flat, size_t* off_inbox, size_t* slice_floats) {
@@ -217,6 +270,22 @@ extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void
   if (c->d.world == 1 || n_floats == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n4 = n_floats / 4;
+  if (n_floats * sizeof(float) <= ONE_SHOT_BYTES && n4 <= c->d.slice_floats / 4) {
+    switch (c->d.world) {
+      case 2: all_reduce_small_kernel<2><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 3: all_reduce_small_kernel<3><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 4: all_reduce_small_kernel<4><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 5: all_reduce_small_kernel<5><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 6: all_reduce_small_kernel<6><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 7: all_reduce_small_kernel<7><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 8: all_reduce_small_kernel<8><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      default: return dbw_fail_("dbw_comm_all_reduce: world sizes 2..8 are compiled in (one NVSwitch node)", cudaSuccess);
+    }
+    dbw_count_launch_();
+    cudaError_t e1 = cudaGetLastError();
+    if (e1 != cudaSuccess) return dbw_fail_("all_reduce_small_kernel", e1);
+    return 0;
+  }
   switch (c->d.world) {
     case 2: all_reduce_kernel<2><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
     case 3: all_reduce_kernel<3><<<COMM_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
@@ -233,7 +302,7 @@ extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void
   return 0;
 }
 
-// 0: fine; 1 / 2: a grid / rank barrier timed out (a peer did not arrive within ~30 s) -- results are then garbage
+// 0: fine; 1 / 2 / 3: a grid barrier / rank barrier / the wait for the previous exchange timed out (a peer did not arrive within ~30 s) -- results are then garbage
 extern "C" int dbw_comm_error(void* comm, int32_t* out) {
   Comm* c = (Comm*)comm;
   if (!c || !out) return dbw_fail_("dbw_comm_error: null argument", cudaSuccess);

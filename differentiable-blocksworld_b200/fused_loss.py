@@ -20,6 +20,11 @@ from ._lib import DbwLossEpilogue
 from .renderer import _c, _stream, scene_settings
 
 N_PARTIALS = 1024
+# run the two passes' backward kernels concurrently (the environment's on a side stream: parallel branches of the step's CUDA
+# graph).  One GPU, 49 views: no gain (the kernels fill the machine by themselves); 8 GPUs, ~6 views each: the launches are
+# short and one kernel's ramp-up hides the other's tail -- bench.py --overlap-bwd measures it
+OVERLAP_BACKWARD_PASSES = False
+_side_stream = None
 
 
 class ScenePass:
@@ -114,9 +119,19 @@ class _SceneMSEFn(torch.autograd.Function):
                                                     _c(gl), _c(g_verts), _c(g_alpha), _c(g_maps), _c(scratch), scratch.numel(),
                                                     _stream()), 'dbw_render_backward_scaled')
 
-        # (running the environment's backward on a side stream, concurrently with the blocks', was measured: -0.3 %, not kept)
-        run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ws_b, g_fg, bwd_b, g['gv_b'], g['gm_b'], g['ga_b'])
-        run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ws_e, g_env, bwd_e, g['gv_e'], g['gm_e'], None)
+        if OVERLAP_BACKWARD_PASSES:
+            global _side_stream
+            cur = torch.cuda.current_stream()
+            if _side_stream is None or _side_stream.device != dev:
+                _side_stream = torch.cuda.Stream(device=dev)
+            _side_stream.wait_stream(cur)
+            with torch.cuda.stream(_side_stream):
+                run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ws_e, g_env, bwd_e, g['gv_e'], g['gm_e'], None)
+            run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ws_b, g_fg, bwd_b, g['gv_b'], g['gm_b'], g['ga_b'])
+            cur.wait_stream(_side_stream)
+        else:
+            run(cfg_b, blk_pass, fmap_b, blk_verts, blk_maps, table_b, fa, ws_b, g_fg, bwd_b, g['gv_b'], g['gm_b'], g['ga_b'])
+            run(cfg_e, env_pass, env_pass.face_map, env_verts, env_maps, table_e, None, ws_e, g_env, bwd_e, g['gv_e'], g['gm_e'], None)
         gv_e, gm_e, gv_b, gm_b, ga_b = g['gv_e'], g['gm_e'], g['gv_b'], g['gm_b'], g['ga_b']
         return gv_e, gm_e, gv_b, gm_b, ga_b, None, None, None, None, None, None, None, None, None
 

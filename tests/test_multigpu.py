@@ -20,7 +20,7 @@ def _w_allreduce(rank, world, port, out):
     import dbw_b200  # noqa: F401
     from dbw_b200.parallel import PeerAllReduce
     res = {}
-    for n in (64, 36864, 2_400_004):                         # one-shot (small), one-shot (the pooled bucket), two-shot (9.6 MB)
+    for n in (64, 36864, 2_400_004):                         # one-shot (tiny), one-shot (the scene-tensor gradients), two-shot (9.6 MB)
         n4 = (n + 3) // 4 * 4
         comm = PeerAllReduce(n4, dev)
         g = torch.Generator(device=dev).manual_seed(100 + rank)
@@ -37,6 +37,21 @@ def _w_allreduce(rank, world, port, out):
             gathered = [torch.empty_like(y) for _ in range(world)]
             dist.all_gather(gathered, y)
             ok = ok and all(torch.equal(gathered[0], t) for t in gathered)       # bit-identical on every rank
+            if n4 > 131072:
+                # a small exchange on a PREFIX of the same bucket (the one-shot path and its deferred barrier) between two
+                # large ones, twice in a row: the paths share the inbox and the flags
+                for _ in range(2):
+                    small = comm.flat[:36864]
+                    xs = torch.randn(36864, device=dev, generator=g)
+                    refs = xs.clone()
+                    dist.all_reduce(refs)
+                    small.copy_(xs)
+                    comm.all_reduce(small)
+                    torch.cuda.synchronize()
+                    ok = ok and bool((small - refs).abs().max() <= 1e-5 * refs.abs().max())
+                    gs = [torch.empty_like(small) for _ in range(world)]
+                    dist.all_gather(gs, small)
+                    ok = ok and all(torch.equal(gs[0], t) for t in gs)
         # captured in a CUDA graph and replayed
         static = comm.flat
         side = torch.cuda.Stream()
