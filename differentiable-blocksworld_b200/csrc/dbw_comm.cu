@@ -18,10 +18,11 @@
 // ld.acquire.sys; a poll that exceeds ~30 s sets the arena's error word instead of hanging the GPU.
 //
 // Small exchanges (<= ONE_SHOT_BYTES: the step's scene-tensor gradients, parallel.GradSumPoint, ~0.15 MB) are latency bound and
-// take the ONE-SHOT path: every rank pushes its whole vector into its slot of EVERY inbox, one rank barrier, then every rank adds
-// the world copies itself, in rank order (bit-identical again) -- one NVLink round trip instead of two, 16 CTAs instead of 96.
-// Its barrier B is DEFERRED: a rank stamps "I have finished reading my inbox" without waiting, and every exchange (either
-// path) starts by checking the peers' stamps of the previous one, long since there.
+// take the FLAGGED ONE-SHOT path, no barrier at all: every rank pushes its whole vector into its slot of EVERY rank's `ll` region
+// as 64-bit words {value, epoch} (one posted store each: value and flag arrive together), then adds the world copies itself,
+// in rank order (bit-identical again), spinning per word until its flag shows this epoch -- one NVLink one-way trip.  A rank
+// stamps "I have finished reading" (flagsB) without waiting, and every exchange (either path) starts by checking the peers'
+// stamps of the previous one, long since there: that is what keeps a fast rank from overwriting words a slow one still reads.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -45,8 +46,10 @@ struct CommDev {
   unsigned* ctrl[COMM_MAX_WORLD];        // each rank's control block: [0,world) flagsA, [64, 64+world) flagsB
   float* flat[COMM_MAX_WORLD];           // each rank's bucket
   float* inbox[COMM_MAX_WORLD];          // each rank's inbox: world slices of slice_floats
+  unsigned long long* ll[COMM_MAX_WORLD];  // each rank's flagged one-shot region: world slots of LL_CAP_FLOATS {value, epoch} words
   size_t cap_floats, slice_floats;
 };
+#define LL_CAP_FLOATS (ONE_SHOT_BYTES / 4)
 // local control words (indices into ctrl[rank]): 128 epoch, 129 grid-barrier arrivals, 130 barrier base, 131 error
 #define CW_FLAGS_A 0
 #define CW_FLAGS_B 64
@@ -158,47 +161,63 @@ __global__ void __launch_bounds__(COMM_THREADS) all_reduce_kernel(const CommDev 
   rank_barrier(c, ctl, CW_FLAGS_B, epoch);                            // B: every owner's sums have landed in my bucket
 }
 
-// one-shot variant for small vectors (n4 <= the inbox stride): see the header
+// flagged one-shot variant for small vectors (n <= LL_CAP_FLOATS): see the header
 template <int W>
-__global__ void __launch_bounds__(COMM_THREADS) all_reduce_small_kernel(const CommDev c, float* __restrict__ buf, size_t n4) {
+__global__ void __launch_bounds__(COMM_THREADS) all_reduce_small_kernel(const CommDev c, float* __restrict__ buf, size_t n) {
   unsigned* ctl = c.ctrl[c.rank];
-  const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];
+  const unsigned epoch = ctl[CW_EPOCH] + 1u, base = ctl[CW_BASE];     // stable until the LAST block of this kernel advances them
   const int G = gridDim.x, r = c.rank;
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)G * blockDim.x;
-  const size_t cap4 = c.slice_floats / 4;
   wait_previous_exchange(c, ctl, epoch - 1u);
-  // ---- push my whole vector into slot `r` of every rank's inbox
-  const float4* src = reinterpret_cast<const float4*>(buf);
-  for (size_t i = tid; i < n4; i += nthr) {
-    const float4 v = src[i];
+  // ---- push {value, epoch} into slot `r` of every rank's region
+  for (size_t i = tid; i < n; i += nthr) {
+    const unsigned long long w = ((unsigned long long)epoch << 32) | (unsigned long long)__float_as_uint(buf[i]);
 #pragma unroll
-    for (int q = 0; q < W; ++q) st_peer(reinterpret_cast<float4*>(c.inbox[(r + q) % W]) + (size_t)r * cap4 + i, v);
+    for (int q = 0; q < W; ++q) {
+      unsigned long long* dst = c.ll[(r + q) % W] + (size_t)r * LL_CAP_FLOATS + i;
+      asm volatile("st.volatile.global.u64 [%0], %1;" :: "l"(dst), "l"(w) : "memory");
+    }
   }
-  grid_barrier(ctl, base + 1u * G);
-  rank_barrier(c, ctl, CW_FLAGS_A, epoch);                            // A: every rank's vector has landed in my inbox
-  grid_barrier(ctl, base + 2u * G);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + 3u * G; }
-  // ---- every rank forms every sum itself, in rank order
-  float4* dst = reinterpret_cast<float4*>(buf);
-  const float4* in = reinterpret_cast<const float4*>(c.inbox[r]);
-  for (size_t i = tid; i < n4; i += nthr) {
-    float4 v[W];
+  // ---- every rank forms every sum itself, in rank order, as the words arrive
+  const unsigned long long* in = c.ll[r];
+  bool late = false;
+  for (size_t i = tid; i < n; i += nthr) {
+    float acc = 0.f;
 #pragma unroll
-    for (int q = 0; q < W; ++q) v[q] = ld_peer(in + (size_t)q * cap4 + i);
-    float4 acc = v[0];
-#pragma unroll
-    for (int q = 1; q < W; ++q) { acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w; }
-    dst[i] = acc;
+    for (int q = 0; q < W; ++q) {
+      const unsigned long long* src = in + (size_t)q * LL_CAP_FLOATS + i;
+      unsigned long long w;
+      const long long t0 = clock64();
+      for (;;) {
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w) : "l"(src) : "memory");
+        if ((unsigned)(w >> 32) == epoch) break;
+        if (clock64() - t0 > SPIN_LIMIT) { late = true; break; }
+      }
+      const float v = __uint_as_float((unsigned)w);
+      acc = q == 0 ? v : acc + v;
+    }
+    buf[i] = acc;
   }
-  grid_barrier(ctl, base + 3u * G);                                   // all my blocks have finished reading the inbox
-  if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.ctrl[threadIdx.x] + CW_FLAGS_B + r, epoch);      // B, not waited for
+  if (late) ctl[CW_ERROR] = 2u;
+  // ---- the last block to finish advances the epoch and tells the peers this rank's region may be overwritten (not waited for)
+  __shared__ bool s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&ctl[CW_ARRIVE], 1u) + 1u == base + (unsigned)G;
+  __syncthreads();
+  if (s_last) {
+    if (threadIdx.x == 0) { ctl[CW_EPOCH] = epoch; ctl[CW_BASE] = base + (unsigned)G; }
+    if (threadIdx.x < c.world) st_release_sys(c.ctrl[threadIdx.x] + CW_FLAGS_B + r, epoch);
+  }
 }
 
-static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_flat, size_t* off_inbox, size_t* slice_floats) {
+static size_t arena_layout(size_t cap_floats, size_t world, size_t* off_flat, size_t* off_inbox, size_t* slice_floats,
+                           size_t* off_ll = nullptr) {
   const size_t cap = (cap_floats + 3) / 4 * 4;
   const size_t slice = ((cap / 4 + world - 1) / world) * 4;
   *off_flat = CTRL_BYTES; *off_inbox = CTRL_BYTES + cap * sizeof(float); *slice_floats = slice;
-  return *off_inbox + world * slice * sizeof(float);
+  const size_t ll = (*off_inbox + world * slice * sizeof(float) + 255) / 256 * 256;
+  if (off_ll) *off_ll = ll;
+  return ll + world * (size_t)LL_CAP_FLOATS * sizeof(unsigned long long);
 }
 
 extern "C" int dbw_comm_create(int32_t world, int32_t rank, size_t max_floats, void** comm_out) {
@@ -231,8 +250,8 @@ extern "C" int dbw_comm_ipc_handle(void* comm, void* out_handle64) {
 extern "C" int dbw_comm_connect(void* comm, const void* all_handles) {
   Comm* c = (Comm*)comm;
   if (!c || !all_handles) return dbw_fail_("dbw_comm_connect: null argument", cudaSuccess);
-  size_t od, orr, sl;
-  arena_layout(c->d.cap_floats, c->d.world, &od, &orr, &sl);
+  size_t od, orr, sl, oll;
+  arena_layout(c->d.cap_floats, c->d.world, &od, &orr, &sl, &oll);
   for (int p = 0; p < c->d.world; ++p) {
     void* base = c->arena;
     if (p != c->d.rank) {
@@ -245,6 +264,7 @@ extern "C" int dbw_comm_connect(void* comm, const void* all_handles) {
     c->d.ctrl[p] = (unsigned*)b;
     c->d.flat[p] = (float*)(b + od);
     c->d.inbox[p] = (float*)(b + orr);
+    c->d.ll[p] = (unsigned long long*)(b + oll);
   }
   c->d.slice_floats = sl;
   c->connected = true;
@@ -270,15 +290,15 @@ extern "C" int dbw_comm_all_reduce(void* comm, float* buf, size_t n_floats, void
   if (c->d.world == 1 || n_floats == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n4 = n_floats / 4;
-  if (n_floats * sizeof(float) <= ONE_SHOT_BYTES && n4 <= c->d.slice_floats / 4) {
+  if (n_floats <= LL_CAP_FLOATS) {
     switch (c->d.world) {
-      case 2: all_reduce_small_kernel<2><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 3: all_reduce_small_kernel<3><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 4: all_reduce_small_kernel<4><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 5: all_reduce_small_kernel<5><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 6: all_reduce_small_kernel<6><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 7: all_reduce_small_kernel<7><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
-      case 8: all_reduce_small_kernel<8><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n4); break;
+      case 2: all_reduce_small_kernel<2><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 3: all_reduce_small_kernel<3><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 4: all_reduce_small_kernel<4><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 5: all_reduce_small_kernel<5><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 6: all_reduce_small_kernel<6><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 7: all_reduce_small_kernel<7><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
+      case 8: all_reduce_small_kernel<8><<<COMM_SMALL_BLOCKS, COMM_THREADS, 0, st>>>(c->d, buf, n_floats); break;
       default: return dbw_fail_("dbw_comm_all_reduce: world sizes 2..8 are compiled in (one NVSwitch node)", cudaSuccess);
     }
     dbw_count_launch_();
