@@ -206,7 +206,8 @@ class ViewParallel:
 
     VIEW_KEYS = ('imgs', 'R', 'T', 'K')
 
-    def __init__(self, model, group=None, seed=227391, row_bands=False, collective='nccl', reduce_at='auto', gather_grads=None):
+    def __init__(self, model, group=None, seed=227391, row_bands=False, collective='nccl', reduce_at='auto', gather_grads=None,
+                 peer_factory=None):
         """collective: 'nccl' (torch.distributed all_reduce; also what gloo groups use), 'p2p' (the NVLink peer-memory kernel
         of csrc/dbw_comm.cu, CUDA-graph capturable) or 'auto' (p2p if it initialises on this node, else nccl).
         reduce_at: 'leaf' (all-reduce the parameter gradients after the backward), 'scene' (sum the gradients of the scene
@@ -215,13 +216,15 @@ class ViewParallel:
         leaf otherwise -- decided per step).
         gather_grads: gather the gradients into bucket.flat (and make the .grad attributes views of it) after every backward;
         None: only when a leaf all-reduce reads the bucket (world > 1 and no reduction inside the backward) -- otherwise the
-        .grad attributes are autograd's own tensors and bucket.grads_flat() concatenates them on demand"""
+        .grad attributes are autograd's own tensors and bucket.grads_flat() concatenates them on demand.
+        peer_factory(n_floats, device) -> object with `.flat` (the bucket) and `.all_reduce(prefix_of_flat)`: replaces the
+        peer-memory arena (tests run the scene-level reduction over gloo with it)"""
         self.model, self.group, self.seed = model, group, seed
         self.reduce_at, self.gather_grads = reduce_at, gather_grads
         self.row_bands = row_bands          # shard at (view, row band) granularity (needs the model's fused-loss path)
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
-        def peer_factory(n_floats, device):
+        def arena_factory(n_floats, device):
             if not (self.world_size > 1 and collective in ('p2p', 'auto') and device.type == 'cuda'):
                 return None
             try:
@@ -233,7 +236,7 @@ class ViewParallel:
                 return None
 
         want_point = reduce_at in ('scene', 'auto') and hasattr(model, 'grad_sum_floats')
-        self.bucket = GradBucket(model.parameters(), peer_factory, model.grad_sum_floats() if want_point else 0)
+        self.bucket = GradBucket(model.parameters(), peer_factory or arena_factory, model.grad_sum_floats() if want_point else 0)
         self.sum_point = GradSumPoint(self.bucket.peer) if (want_point and self.bucket.peer is not None) else None
         if reduce_at == 'scene' and self.sum_point is None and self.world_size > 1:
             raise RuntimeError("reduce_at='scene' needs the peer-memory collective (collective='p2p' or 'auto') and a model with grad_sum_floats()")

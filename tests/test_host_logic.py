@@ -325,3 +325,93 @@ def test_scene_settings_of_a_render_pass():
     assert cfg2.save_fragment_state == 0 and cfg2.alpha_view_stride == F and cfg2.z_clip == -1.0
     with pytest.raises(DbwError):
         scene_settings(verts, faces, atlas, table, B, intr, (16, 24), 1e-4, 10, faces_alpha=torch.ones(F + 1))
+
+
+class _ToyScenePoint(torch.nn.Module):
+    """a scene model that routes what its 'render' differentiates through the data-parallel gradient-sum point the way
+    DifferentiableBlocksWorld does (dbw.py _scene_tensors): scene tensors = f(leaves), rgb = g(scene tensors), plus a
+    view-independent regulariser that does NOT pass through the point"""
+
+    def __init__(self):
+        super().__init__()
+        self.w = torch.nn.Parameter(torch.linspace(0.1, 0.9, 5))
+        self.textures = torch.nn.Parameter(torch.linspace(-1, 1, 6))
+        self.n_total_views, self.noise_generator, self.grad_sum_point = None, None, None
+        self.point_calls = 0
+
+    def _fused_loss_ok(self, imgs):
+        return True
+
+    def can_sum_gradients_at_scene_tensors(self, imgs):
+        return True
+
+    def grad_sum_floats(self):
+        return 5 + 3
+
+    def forward(self, inp, labels=None):
+        verts, cells = self.w.exp(), torch.sigmoid(self.textures).view(3, 2).mean(1)          # leaves -> scene tensors
+        if self.grad_sum_point is not None:
+            verts, cells = self.grad_sum_point(verts, cells)
+            self.point_calls += 1
+        imgs = inp['imgs']
+        B, H, W = imgs.shape
+        err = (imgs * verts[None, None] + cells.sum() * inp['R'].sum((1, 2))[:, None, None] - 0.5) ** 2
+        if inp.get('rows') is not None:
+            y = torch.arange(H)[None, :, None]
+            err = err * ((y >= inp['rows'][:, 0, None, None]) & (y < inp['rows'][:, 1, None, None]))
+        rgb = err.sum() / (self.n_total_views * H * W)
+        reg = self.textures.pow(2).sum() + self.w.sum()
+        return {'rgb': rgb, 'tv': reg, 'total': rgb + reg}
+
+
+class _GlooBucket:
+    """stands in for parallel.PeerAllReduce on CPU: a flat bucket and an in-place sum over the ranks of a prefix of it"""
+
+    def __init__(self, n_floats, device):
+        self.flat = torch.zeros(n_floats)
+        self.sizes = []
+
+    def all_reduce(self, buf):
+        assert buf.data_ptr() == self.flat.data_ptr() and buf.numel() % 4 == 0
+        self.sizes.append(buf.numel())
+        dist.all_reduce(buf)
+
+
+def _worker_point(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from dbw_b200.parallel import ViewParallel
+    torch.manual_seed(0)
+    model = _ToyScenePoint()
+    vp = ViewParallel(model, seed=123, row_bands=True, peer_factory=_GlooBucket)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(5, 48, 5, generator=g), 'R': torch.rand(5, 3, 3, generator=g), 'T': torch.rand(5, 3, generator=g)}
+    assert vp.sum_point is not None and vp.reduces_inside_backward(inp)
+    vp.forward_backward(inp)
+    vp.forward_backward(inp)                       # the bucket is reused
+    out[rank] = (vp.bucket.grads_flat().clone(), model.point_calls, list(vp.bucket.peer.sizes),
+                 model.w.grad.data_ptr() != vp.bucket.flat.data_ptr())
+    dist.destroy_process_group()
+
+
+def test_gradients_summed_at_the_scene_tensors_equal_single_process_gloo():
+    """world_size-2 gloo run of the scene-level reduction (parallel.GradSumPoint over a gloo stand-in for the peer-memory
+    bucket): ONE small exchange inside each backward, no leaf all-reduce, no gather; the leaf gradients -- chain rule applied
+    to the summed scene-tensor gradients, regulariser counted once -- equal the single-process step's on both ranks"""
+    from dbw_b200.parallel import ViewParallel
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_point, args=(2, 33000 + os.getpid() % 2000, out), nprocs=2, join=True)
+    torch.manual_seed(0)
+    model = _ToyScenePoint()
+    vp = ViewParallel(model, seed=123)
+    g = torch.Generator().manual_seed(1)
+    inp = {'imgs': torch.rand(5, 48, 5, generator=g), 'R': torch.rand(5, 3, 3, generator=g), 'T': torch.rand(5, 3, generator=g)}
+    vp.forward_backward(inp)
+    ref = vp.bucket.grads_flat()
+    assert model.point_calls == 0                                     # one rank: no sum point in the graph
+    for rank in (0, 1):
+        got, calls, sizes, own_grads = out[rank]
+        assert calls == 2 and sizes == [8, 8] and own_grads           # 5 + 3 floats per step; .grad not gathered into the bucket
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7), (rank, got, ref)
+    assert torch.equal(out[0][0], out[1][0])
