@@ -2,13 +2,15 @@
 that runs).
 
 Views of a step are independent given the replicated scene parameters, so they shard with NO data-path collective:
-rank r renders a contiguous range of the B views and back-propagates into its own full-size parameter gradients;
-ONE all-reduce(SUM) over a single flat fp32 bucket (about 9.4 MB for 10 blocks with 256^2 textures) over
-NVLink 5 / NVSwitch then gives every rank the full gradient.  Correctness conditions handled here:
+rank r renders a contiguous range of the B views (or of their 16-row bands) and back-propagates into its own gradients;
+ONE all-reduce(SUM) per step over NVLink 5 / NVSwitch then gives every rank the full gradient -- either of a single flat
+fp32 bucket of the parameter gradients after the backward (about 9.4 MB for 10 blocks with 256^2 textures), or, while the
+textures are box-decimated, of the scene tensors' gradients inside the backward (GradSumPoint: about 0.16 MB).
+Correctness conditions handled here:
   * the RGB loss is a MEAN over all B views (dbw.py:367): each rank divides by the GLOBAL pixel count
     (model.n_total_views), so the SUM of the per-rank gradients is the gradient of the global mean;
-  * view-independent terms (parsimony / TV / overlap, dbw.py:373-405) are computed identically on every rank and
-    divided by the world size before the SUM;
+  * view-independent terms (parsimony / TV / overlap, dbw.py:373-405) are computed identically on every rank: divided by
+    the world size before a leaf SUM, counted once when the SUM happens at the scene tensors (they do not pass through it);
   * the opacity noise (dbw.py:300-301) and the overlap sample points (dbw.py:393) come from a generator that every
     rank seeds identically at every step."""
 import ctypes
