@@ -176,3 +176,39 @@ void hm_superquadric(const float* sq_eta, const float* sq_omega, const float* sq
     for (int v = 0; v < Vb; ++v) local_vertex(P, b, v, out + (b * Vb + v) * 3, aux + (b * Vb + v) * 6);
 }
 }  // extern "C"
+
+extern "C" {
+// The tile binner's conservative triangle / rectangle test (tri_overlaps_rect), driven as raster_forward_kernel drives it:
+// for every TS x TS pixel tile of an H x W image, the rectangle spanned by the tile's pixel centres, expanded by sqrt(blur).
+// out[tile] = 1 if the face would be listed for the tile.
+void hm_tile_overlap(const float* fv, int H, int W, int TS, float blur, int* out) {
+  const float sb = sqrtf(blur);
+  const f2 v0 = {fv[0], fv[1]}, v1 = {fv[3], fv[4]}, v2 = {fv[6], fv[7]};
+  const int ntx = (W + TS - 1) / TS, nty = (H + TS - 1) / TS;
+  for (int ty = 0; ty < nty; ++ty)
+    for (int tx = 0; tx < ntx; ++tx) {
+      const int xa = tx * TS, xb = (tx + 1) * TS - 1 < W - 1 ? (tx + 1) * TS - 1 : W - 1;
+      const int ya = ty * TS, yb = (ty + 1) * TS - 1 < H - 1 ? (ty + 1) * TS - 1 : H - 1;
+      // pixel xi maps to NDC pix_to_ndc(W - 1 - xi): decreasing in xi
+      const float x_lo = pix_to_ndc(W - 1 - xb, W, H), x_hi = pix_to_ndc(W - 1 - xa, W, H);
+      const float y_lo = pix_to_ndc(H - 1 - yb, H, W), y_hi = pix_to_ndc(H - 1 - ya, H, W);
+      out[ty * ntx + tx] = tri_overlaps_rect(v0, v1, v2, x_lo - sb, x_hi + sb, y_lo - sb, y_hi + sb) ? 1 : 0;
+    }
+}
+
+// tri_dist2_edge over an image: the distance (must equal tri_dist2 bit for bit), the edge it names, and the three segment
+// distances, so that the test can check the edge realises the minimum with tri_dist_backward's tie order
+void hm_dist_edge(const float* fv, int H, int W, float* dist, float* dist_ref, int* edge, float* seg) {
+  const TriGeom t = make_tri(fv);
+  for (int yi = 0; yi < H; ++yi)
+    for (int xi = 0; xi < W; ++xi) {
+      const int o = yi * W + xi;
+      const f2 p = {pix_to_ndc(W - 1 - xi, W, H), pix_to_ndc(H - 1 - yi, H, W)};
+      int e = -1;
+      dist[o] = tri_dist2_edge(p, t, e);
+      dist_ref[o] = tri_dist2(p, t);
+      edge[o] = e;
+      seg[o * 3] = seg_dist2(p, t.v0, t.v1, t.il01); seg[o * 3 + 1] = seg_dist2(p, t.v0, t.v2, t.il02); seg[o * 3 + 2] = seg_dist2(p, t.v1, t.v2, t.il12);
+    }
+}
+}  // extern "C"

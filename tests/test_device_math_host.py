@@ -238,3 +238,38 @@ def test_scene_vertex_math_matches_torch(hm):
                        _p(np.ascontiguousarray(raw.numpy().astype(np.float32))), N, Vb, ctypes.c_float(0.25), _p(out), _p(aux))
     assert np.abs(out - ref.numpy()).max() < 1e-5
     assert np.abs(aux[:, 0, 4:] - eps.numpy()).max() < 1e-6
+
+
+@pytest.mark.parametrize('blur', [BLUR, 0.0])
+def test_tile_binning_test_never_drops_a_face_that_reaches_the_tile(hm, blur):
+    """tri_overlaps_rect (the binner's edge-line test on the halo-expanded tile) is CONSERVATIVE: every tile that holds a pixel
+    the per-pixel candidate test accepts lists the face; and it is useful: it rejects most tiles of the face's bounding box
+    that the face does not reach (slivers and diagonal faces are why it exists)"""
+    H, W, TS = 48, 64, 8
+    ntx, nty = W // TS, H // TS
+    kept_needlessly = boxed = 0
+    for fv in _triangles(3, 60):
+        hit, *_ = _device(hm, fv, H, W, blur, True, True)
+        listed = np.zeros((nty, ntx), np.int32)
+        hm.hm_tile_overlap(_p(np.ascontiguousarray(fv)), H, W, TS, ctypes.c_float(blur), _p(listed))
+        reached = hit.reshape(nty, TS, ntx, TS).any(axis=(1, 3))
+        assert not (reached & (listed == 0)).any(), 'a tile with accepted pixels was not listed'
+        kept_needlessly += int(((listed == 1) & ~reached).sum())
+        boxed += int((~reached).sum())
+    assert kept_needlessly < 0.25 * boxed
+
+
+def test_closest_edge_recorded_by_the_forward(hm):
+    """tri_dist2_edge == tri_dist2 bit for bit, and the edge it names realises the minimum (first in the order v0v1, v0v2, v1v2
+    among equals -- the order tri_dist_backward resolves ties in), incl. at pixels equidistant from two edges (a vertex region)"""
+    H, W = 40, 56
+    ties = 0
+    for fv in _triangles(9, 30):
+        dist, ref = np.zeros((H, W), np.float32), np.zeros((H, W), np.float32)
+        edge, seg = np.zeros((H, W), np.int32), np.zeros((H, W, 3), np.float32)
+        hm.hm_dist_edge(_p(np.ascontiguousarray(fv)), H, W, _p(dist), _p(ref), _p(edge), _p(seg))
+        assert np.array_equal(dist, ref)
+        assert np.array_equal(np.take_along_axis(seg, edge[..., None].astype(np.int64), -1)[..., 0], dist)
+        assert np.array_equal(edge, np.argmin(seg, axis=-1))            # argmin takes the FIRST minimum
+        ties += int((np.sort(seg, axis=-1)[..., 0] == np.sort(seg, axis=-1)[..., 1]).sum())
+    assert ties > 0                                                      # vertex regions: two segments share the closest point
