@@ -59,6 +59,9 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = self._body()
+        # the gradient tensors THIS capture writes (bucket views when the gradients are gathered, else tensors of the graph's
+        # private pool): another GraphedStep on the same model (PipelinedGraphedStep) leaves its own in the .grad attributes
+        self.grads = [p.grad for p in self.vp.bucket.params]
 
     def _body(self):
         losses, reduced = self.vp.local_step(self.static_inp, None, self.n_total, collective=self.capture_all_reduce)
@@ -81,6 +84,8 @@ class GraphedStep:
         if self.overlap_buf is not None:
             self.overlap_buf.uniform_(generator=self.gen)
         self.graph.replay()
+        for p, g in zip(self.vp.bucket.params, self.grads):
+            p.grad = g
         if not self.capture_all_reduce and all_reduce and self.vp.world_size > 1:
             if self.inside:
                 raise RuntimeError('this step sums its gradients inside the backward (parallel.GradSumPoint) but was captured '

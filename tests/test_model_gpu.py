@@ -479,6 +479,35 @@ def test_pipelined_steps_each_draw_their_own_opacity_noise():
     assert abs(model(inp, None)['rgb'].item() - seen[3][1]) < 1e-7
 
 
+def test_pipelined_steps_leave_their_own_gradients_in_the_grad_attributes():
+    """two GraphedSteps on one model, gradients not gathered into the bucket (one rank): after a replay the .grad attributes are
+    the tensors THAT step's graph wrote -- not the other step's, which the later capture had left there"""
+    from dbw_b200.parallel import ViewParallel
+    from dbw_b200.graph import PipelinedGraphedStep
+    model, tpl, p, dev = _model_and_oracle()
+    inp, *_ = _inputs(dev)
+    model.loss_weights = {'rgb': 1.0}
+    vp = ViewParallel(model, seed=5)
+    piped = PipelinedGraphedStep(vp, inp, len(inp['imgs']))
+    host_a = {k: v.cpu().pin_memory() for k, v in inp.items()}
+    host_b = dict(host_a, imgs=host_a['imgs'].flip(0).contiguous().pin_memory())
+    got = []
+    for cur, nxt in ((host_a, host_b), (host_b, host_a), (host_a, host_b), (host_b, None)):
+        piped.run(cur, nxt)
+        torch.cuda.synchronize()
+        got.append(vp.bucket.grads_flat().clone())
+    refs = []
+    for host in (host_a, host_b):
+        for q in model.parameters():
+            q.grad = None
+        model({k: v.to(dev) for k, v in host.items()}, None)['total'].backward()
+        refs.append(vp.bucket.grads_flat().clone())
+    assert (refs[0] - refs[1]).norm() > 1e-2 * refs[0].norm()
+    for i, g in enumerate(got):
+        ref = refs[i % 2]
+        assert (g - ref).norm() <= 1e-4 * ref.norm(), (i, (g - ref).norm().item(), ref.norm().item())
+
+
 def test_row_band_shards_sum_to_the_batch():
     """(view, row band) sharding (parallel.shard_row_bands + dbw_render.h view_rows): the loss and every leaf gradient of the
     full batch == the sum over 3 'ranks' that each render their bands of the views they touch"""
