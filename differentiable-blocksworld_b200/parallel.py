@@ -160,7 +160,11 @@ class GradBucket:
             off += p.numel()
 
     def zero_(self):
+        """the classic protocol: zero the bucket and make the .grad attributes its views again (a backward(gather=False) leaves
+        autograd's own tensors there), so that a plain loss.backward() accumulates into the bucket"""
         self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def backward(self, total, gather=True):
         """Back-propagate `total` and leave every parameter's gradient in the flat bucket with ONE gather kernel: the

@@ -299,6 +299,17 @@ def test_grad_bucket_backward_gathers_like_accumulation():
     bucket.zero_()                                                   # the classic path still works on the same views
     loss_fn().backward()
     assert torch.allclose(bucket.flat, ref, rtol=1e-6, atol=1e-7)
+    # gather=False (no collective reads the bucket): .grad are autograd's own tensors, the flat buffer is left alone,
+    # grads_flat() concatenates on demand, and zero_() re-installs the views for the classic protocol
+    before = bucket.flat.clone()
+    bucket.backward(3 * loss_fn(), gather=False)
+    assert torch.equal(bucket.flat, before) and unused.grad is None
+    assert a.grad.untyped_storage().data_ptr() != bucket.flat.untyped_storage().data_ptr()
+    assert torch.allclose(bucket.grads_flat(), 3 * ref[:21], rtol=1e-6, atol=1e-7)
+    bucket.zero_()
+    assert a.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr()
+    loss_fn().backward()
+    assert torch.allclose(bucket.flat, ref, rtol=1e-6, atol=1e-7)
 
 
 def test_scene_settings_of_a_render_pass():
